@@ -1,0 +1,152 @@
+"""The oracle (oracle/ref_port.py) against outputs of the unmodified reference.
+
+Fixtures: tests/golden/*.npz, produced by tests/golden/make_golden.py which
+imports /root/reference/analyse/* in the build container.  These tests pin the
+oracle; the GPU parity tests then compare the CUDA path with the oracle.
+"""
+
+from __future__ import annotations
+
+import numpy as np
+import pytest
+
+import oracle
+from conftest import load_golden
+
+SR = 48000
+
+
+def rows_from_fits(fits: dict) -> np.ndarray:
+    out = np.full((3, 7), np.nan)
+    for r, name in enumerate(("EDT", "T20", "T30")):
+        f = fits.get(name)
+        if f is None:
+            out[r, 6] = 0.0
+        else:
+            out[r] = [f["t_start"], f["t_end"], f["slope"], f["intercept"], f["r2"], f["rt60"], 1.0]
+    return out
+
+
+def assert_rows_equal(got, want, rtol=1e-9):
+    assert np.array_equal(np.isnan(got), np.isnan(want))
+    np.testing.assert_allclose(got[~np.isnan(got)], want[~np.isnan(want)], rtol=rtol, atol=1e-12)
+
+
+def test_decay_matches_reference(golden):
+    x = golden["x"]
+    d = oracle.decay_metrics(x, SR, oracle.DecayParams(compute_edt=True))
+    assert d["start"] == int(golden["decay_start"])
+    assert np.array_equal(d["edc_db"], golden["decay_edc_db"])  # bit-exact float32 curve
+    assert_rows_equal(rows_from_fits(d["fits"]), golden["decay_fits"])
+    want = float(golden["decay_early10"])
+    assert (d["early10"] is None) == np.isnan(want)
+    if d["early10"] is not None:
+        assert d["early10"] == pytest.approx(want, rel=1e-12)
+
+
+def test_decay_variants_match_reference(golden):
+    x = golden["x"]
+    d = oracle.decay_metrics(x, SR, oracle.DecayParams(compute_edt=True, ignore_leading_seconds=0.01))
+    assert d["start"] == int(golden["decay_ign_start"])
+    assert_rows_equal(rows_from_fits(d["fits"]), golden["decay_ign_fits"])
+    d = oracle.decay_metrics(x, SR, oracle.DecayParams(compute_edt=True, edc_smoothing_window_samples=31))
+    assert_rows_equal(rows_from_fits(d["fits"]), golden["decay_smooth_fits"])
+    assert np.array_equal(d["edc_db"][::16], golden["decay_smooth_edc_db_dec16"])
+    d = oracle.decay_metrics(x, SR, oracle.DecayParams(compute_edt=True, trim_to_peak=False))
+    assert d["start"] == 0
+    assert_rows_equal(rows_from_fits(d["fits"]), golden["decay_notrim_fits"])
+
+
+@pytest.mark.parametrize("mode", ["three", "octave", "third"])
+def test_band_metrics_match_reference(golden, mode):
+    p = oracle.BandParams(band_mode=mode, include_t20=True, include_edt=True)
+    r = oracle.band_metrics(golden["x"], SR, p)
+    names = [b["name"] for b in r["bands"]]
+    assert names == [str(s) for s in golden[f"bands_{mode}_names"]]
+    edges = np.array([[np.nan if b["low"] is None else b["low"], np.nan if b["high"] is None else b["high"],
+                       b["centre"]] for b in r["bands"]])
+    want_edges = golden[f"bands_{mode}_edges"]
+    assert np.array_equal(np.isnan(edges), np.isnan(want_edges))
+    assert np.array_equal(edges[~np.isnan(edges)], want_edges[~np.isnan(want_edges)])
+    got = np.array([[np.nan if v is None else v for v in r["metrics"][n]] for n in names])
+    assert_rows_equal(got, golden[f"bands_{mode}_metrics"])
+
+
+def test_band_signal_matches_reference(golden):
+    x = golden["x"]
+    n = x.size
+    freqs = np.fft.rfftfreq(n, d=1.0 / SR).astype(np.float32)
+    bands = {b["name"]: b for b in oracle.band_table(oracle.BandParams(band_mode="third"), SR)}
+    for probe in ("1000Hz", "62Hz"):
+        m = oracle.band_mask(freqs, bands[probe], 1.0 / 6.0, 0.5 * SR)
+        y = oracle.band_filter(x, m)
+        assert np.array_equal(y[::8], golden[f"band_{probe}_signal_dec8"])
+        nz = np.array([int(np.argmax(m > 0)), int(m.size - np.argmax(m[::-1] > 0))])
+        assert np.array_equal(nz, golden[f"band_{probe}_mask_nonzero"])
+
+
+def test_waterfall_matches_reference(golden):
+    x = golden["x"]
+    for only_sel in (True, False):
+        w = oracle.waterfall(x, SR, oracle.CsdParams(), only_selected_frames=only_sel)
+        assert w["start"] == int(golden["wf_start"])
+        assert w["length"] == int(golden["wf_length"])
+        assert np.array_equal(w["slice_times"], golden["wf_times"])
+        assert np.array_equal(w["freq"], golden["wf_freq"])
+        assert np.array_equal(w["rel_db"], golden["wf_rel_db"])
+    w2 = oracle.waterfall(x, SR, oracle.CsdParams(db_reference="slice_max", num_slices=7,
+                                                   slice_mode="uniform_frames", dynamic_range_db=60.0))
+    assert np.array_equal(w2["slice_times"], golden["wf2_times"])
+    assert np.array_equal(w2["rel_db"], golden["wf2_rel_db"])
+    w3 = oracle.waterfall(x, SR, oracle.CsdParams(smoothing_log_bins=9, slice_mode="uniform_time",
+                                                   slice_spacing_seconds=0.08))
+    assert np.array_equal(w3["slice_times"], golden["wf3_times"])
+    assert np.array_equal(w3["rel_db"], golden["wf3_rel_db"])
+
+
+def test_analytic_exponential_known_answers():
+    g = load_golden("analytic")
+    for rt in (0.3, 1.2):
+        n = int(SR * 2.0)
+        x = (10.0 ** (-3.0 * np.arange(n) / (SR * rt))).astype(np.float32)
+        d = oracle.decay_metrics(x, SR, oracle.DecayParams(compute_edt=True))
+        assert_rows_equal(rows_from_fits(d["fits"]), g[f"rt{rt}_fits"])
+        for name in ("EDT", "T20", "T30"):
+            assert d["fits"][name]["rt60"] == pytest.approx(rt, rel=2e-5)
+            assert d["fits"][name]["r2"] == pytest.approx(1.0, abs=1e-9)
+        assert d["early10"] == pytest.approx(rt / 6.0, rel=2e-4)
+        assert d["early10"] == pytest.approx(float(g[f"rt{rt}_early10"]), rel=1e-12)
+        assert np.float32(d["edc_db"][-1]) == g[f"rt{rt}_edc_last"]
+
+
+def test_band_table_known_answers():
+    """SURVEY.md section 4 item 3."""
+    names = [b["name"] for b in oracle.band_table(oracle.BandParams(band_mode="third"), SR)]
+    assert len(names) == 26 and names[0] == "39Hz" and names[-1] == "12699Hz"  # no 16 kHz band
+    octv = [b["name"] for b in oracle.band_table(oracle.BandParams(band_mode="octave"), SR)]
+    assert octv == ["62Hz", "125Hz", "250Hz", "500Hz", "1000Hz", "2000Hz", "4000Hz", "8000Hz", "16000Hz"]
+    three = oracle.band_table(oracle.BandParams(), SR)
+    assert [b["kind"] for b in three] == ["lowpass", "bandpass", "highpass"]
+    assert three[1]["low"] == pytest.approx(500.0) and three[1]["high"] == pytest.approx(2000.0)
+
+
+def test_deconvolve_matches_reference():
+    g = load_golden("deconvolve")
+    h = oracle.deconvolve(g["recorded"], g["sweep"])
+    assert np.array_equal(h, g["ir"])
+
+
+def test_error_cases():
+    with pytest.raises(ValueError):
+        oracle.schroeder_edc_db(np.zeros((4, 2), np.float32), SR, oracle.DecayParams())
+    with pytest.raises(ValueError):
+        oracle.schroeder_edc_db(np.array([0, 0, 1.0], np.float32), SR, oracle.DecayParams())
+    with pytest.raises(ValueError):
+        oracle.band_metrics(np.ones(7, np.float32), SR, oracle.BandParams())
+    with pytest.raises(ValueError):
+        oracle.waterfall(np.ones(4000, np.float32), SR, oracle.CsdParams())
+    with pytest.raises(ValueError):
+        oracle.band_table(oracle.BandParams(band_mode="quarter"), SR)
+    # all-zero IR: flat 0 dB curve, no fits (decay.py:154 clamps to epsilon)
+    d = oracle.decay_metrics(np.zeros(1000, np.float32), SR, oracle.DecayParams(compute_edt=True))
+    assert np.all(d["edc_db"] == 0.0) and d["fits"] == {} and d["early10"] is None
