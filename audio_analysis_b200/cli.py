@@ -1,0 +1,233 @@
+"""Command line for the accelerated path: `decay`, `rt60bands`, `waterfall`, `bundle`.
+
+    python -m analyse.cli decay --input ir.wav --no_show
+    python -m analyse.cli rt60bands --input ir.wav --mono --band_mode third --no_show
+    python -m analyse.cli waterfall --input ir.wav --no_show
+    python -m analyse.cli bundle --input analysis_runs/20250101_120000
+
+Argument names, defaults and quirks follow the reference's `analyse/cli.py`
+(decay :461-531, rt60bands :536-636, waterfall :1010-1100, bundle :377-388), including
+`decay --compute_edt` defaulting to true, `rt60bands --trim_to_peak` being impossible to
+switch off, and the tri-state `rt60bands --legend_values`.  Each command prints the same
+summary text as the reference.  The reference's other ten subcommands are outside this
+build and are rejected by argparse.
+"""
+
+from __future__ import annotations
+
+import argparse
+from pathlib import Path
+from typing import Optional, Sequence
+
+from .bundle import BundleRunSettings, run_bundle_report
+from .decay import DecayAnalysisSettings, DecayPlotSettings, plot_decay_from_wav_file, summarise_decay_results_text
+from .rt60bands import (Rt60BandsAnalysisSettings, Rt60BandsPlotSettings, plot_rt60_bands_from_wav_file,
+                        summarise_rt60_bands_results_text)
+from .waterfall import (WaterfallAnalysisSettings, WaterfallPlotSettings, plot_waterfall_from_wav_file,
+                        summarise_waterfall_results_text)
+
+BoolOpt = argparse.BooleanOptionalAction
+
+
+def _io_arguments(p: argparse.ArgumentParser, png_hint: str) -> None:
+    p.add_argument("--input", dest="input_wav_file_path", type=str, required=True,
+                   help="Path to input WAV file (mono or stereo, 48 kHz expected).")
+    p.add_argument("--output", dest="output_basename", type=str, default=None, help=f"If provided, saves {png_hint}")
+    p.add_argument("--no_show", action="store_true",
+                   help="If set, do not display plots interactively (useful when saving files).")
+
+
+def build_parser() -> argparse.ArgumentParser:
+    top = argparse.ArgumentParser(prog="analyse",
+                                  description="Offline analysis tools for reverb outputs (B200 decay path).")
+    sub = top.add_subparsers(dest="command_name", required=True, help="Analysis to run. Use: analyse <command> --help")
+
+    bundle = sub.add_parser("bundle", help="Analyse an IR bundle folder (meta.json + taps/*.wav), per-tap reports.")
+    bundle.add_argument("--input", dest="bundle_root", type=str, required=True, help="Bundle root folder")
+    bundle.add_argument("--reports-subdir", dest="reports_subdir", type=str, default="reports",
+                        help="Subfolder under bundle root to write outputs (default: reports)")
+
+    decay = sub.add_parser("decay", help="Schroeder EDC + T20/T30/RT60 decay estimation")
+    _io_arguments(decay, "a PNG: <basename>_decay.png")
+    decay.add_argument("--trim_to_peak", action=BoolOpt, default=True,
+                       help="If true, start analysis at the absolute peak sample (default: true).")
+    decay.add_argument("--ignore-leading", dest="ignore_leading_seconds", type=float, default=0.0)
+    decay.add_argument("--edc_floor_db", type=float, default=-120.0)
+    decay.add_argument("--fit_lower_limit_db", type=float, default=-80.0)
+    decay.add_argument("--smoothing", dest="edc_smoothing_window_samples", type=int, default=0)
+    decay.add_argument("--mono", dest="use_mono_downmix", action="store_true", default=False)
+    decay.add_argument("--compute_edt", action=BoolOpt, default=True,
+                       help="If set, also compute EDT (fit 0..-10 dB and extrapolate).")
+
+    bands = sub.add_parser("rt60bands", help="Band-limited RT60: Low/Mid/High T30 by default (optional T20/EDT).")
+    _io_arguments(bands, "one PNG: <basename>_rt60bands.png")
+    bands.add_argument("--band_mode", type=str, default="three", choices=["three", "octave", "third"],
+                       help="Band mode: three (Low/Mid/High), octave, or third (1/3-octave). Default: three.")
+    bands.add_argument("--f_min_hz", type=float, default=31.5,
+                       help="Minimum band centre frequency for octave/third modes (Hz).")
+    bands.add_argument("--f_max_hz", type=float, default=16000.0,
+                       help="Maximum band centre frequency for octave/third modes (Hz).")
+    bands.add_argument("--legend_values", action=BoolOpt, default=None,
+                       help="Per-band numeric values in the legend. Default: on for three, off otherwise.")
+    bands.add_argument("--low_upper_hz", type=float, default=250.0, help="Low band upper cutoff (Hz).")
+    bands.add_argument("--mid_center_hz", type=float, default=1000.0, help="Mid band centre (Hz).")
+    bands.add_argument("--mid_width_octaves", type=float, default=2.0, help="Mid band width in octaves.")
+    bands.add_argument("--high_lower_hz", type=float, default=4000.0, help="High band lower cutoff (Hz).")
+    bands.add_argument("--transition_width_octaves", type=float, default=(1.0 / 6.0),
+                       help="FFT mask transition width (octaves). Default: 1/6 octave.")
+    bands.add_argument("--include_t20", action="store_true", help="Also compute T20-derived RT60 per band.")
+    bands.add_argument("--include_edt", action="store_true", help="Also compute EDT per band.")
+    bands.add_argument("--mono", dest="use_mono_downmix", action="store_true",
+                       help="If set, downmix stereo to mono before analysis.")
+    bands.add_argument("--trim_to_peak", action="store_true", default=True)  # cannot be disabled (reference :632)
+    bands.add_argument("--ignore-leading", dest="ignore_leading_seconds", type=float, default=0.0)
+    bands.add_argument("--edc_floor_db", type=float, default=-120.0)
+    bands.add_argument("--fit_lower_limit_db", type=float, default=-80.0)
+    bands.add_argument("--smoothing", dest="edc_smoothing_window_samples", type=int, default=0)
+
+    wf = sub.add_parser("waterfall", help="Waterfall (CSD-style): spectral slices over time (3D default, 2D ridges).")
+    _io_arguments(wf, "PNG(s): <basename>_waterfall_<CH>.png")
+    wf.add_argument("--mono", dest="use_mono_downmix", action="store_true",
+                    help="If set, downmix stereo to mono before analysis.")
+    wf.add_argument("--trim_to_peak", action=BoolOpt, default=True,
+                    help="If true, start analysis at the absolute peak sample (default: true).")
+    wf.add_argument("--ignore-leading", dest="ignore_leading_seconds", type=float, default=0.0)
+    wf.add_argument("--duration", dest="analysis_duration_seconds", type=float, default=None)
+    wf.add_argument("--n_fft", type=int, default=4096)
+    wf.add_argument("--hop_length", type=int, default=512)
+    wf.add_argument("--no_hann_window", action="store_true")
+    wf.add_argument("--f_min_hz", type=float, default=20.0)
+    wf.add_argument("--f_max_hz", type=float, default=20000.0)
+    wf.add_argument("--style", type=str, choices=["3d", "2d"], default="3d",
+                    help="Plot style: 3d waterfall (default) or 2d stacked ridges.")
+    wf.add_argument("--slice_mode", type=str, choices=["auto", "uniform_time", "uniform_frames"], default="auto",
+                    help="How to choose slice times/frames.")
+    wf.add_argument("--num_slices", type=int, default=18)
+    wf.add_argument("--slice_spacing_seconds", type=float, default=0.05)
+    wf.add_argument("--start_time_seconds", type=float, default=0.0)
+    wf.add_argument("--end_time_seconds", type=float, default=None)
+    wf.add_argument("--db_reference", type=str, choices=["global_max", "slice_max"], default="global_max",
+                    help="Normalisation: global_max keeps absolute decay; slice_max shows shape only.")
+    wf.add_argument("--dynamic_range_db", type=float, default=80.0)
+    wf.add_argument("--floor_db", type=float, default=-120.0)
+    wf.add_argument("--smoothing_log_bins", type=int, default=0)
+    wf.add_argument("--log_bins_per_octave", type=int, default=96)
+    wf.add_argument("--elev_deg", type=float, default=30.0)
+    wf.add_argument("--azim_deg", type=float, default=-60.0)
+    wf.add_argument("--ridge_offset_db", type=float, default=6.0)
+    return top
+
+
+def parse_arguments(argv: Optional[Sequence[str]] = None) -> argparse.Namespace:
+    return build_parser().parse_args(argv)
+
+
+def _basename(args: argparse.Namespace) -> Optional[str]:
+    return None if args.output_basename is None else str(Path(args.output_basename))
+
+
+def decay_settings_from_args(a: argparse.Namespace, compute_edt: bool) -> DecayAnalysisSettings:
+    return DecayAnalysisSettings(
+        trim_to_peak=bool(a.trim_to_peak),
+        ignore_leading_seconds=float(a.ignore_leading_seconds),
+        edc_floor_db=float(a.edc_floor_db),
+        fit_lower_limit_db=float(a.fit_lower_limit_db),
+        edc_smoothing_window_samples=int(a.edc_smoothing_window_samples),
+        use_mono_downmix_for_stereo=bool(a.use_mono_downmix),
+        compute_edt=bool(compute_edt),
+    )
+
+
+def run_decay_command(a: argparse.Namespace) -> str:
+    results = plot_decay_from_wav_file(
+        input_wav_file_path=str(a.input_wav_file_path),
+        analysis_settings=decay_settings_from_args(a, a.compute_edt),
+        plot_settings=DecayPlotSettings(),
+        output_basename=_basename(a),
+        show_interactive=not bool(a.no_show),
+    )
+    return summarise_decay_results_text(results)
+
+
+def run_rt60bands_command(a: argparse.Namespace) -> str:
+    settings = Rt60BandsAnalysisSettings(
+        band_mode=str(a.band_mode),
+        low_upper_hz=float(a.low_upper_hz),
+        mid_center_hz=float(a.mid_center_hz),
+        mid_width_octaves=float(a.mid_width_octaves),
+        high_lower_hz=float(a.high_lower_hz),
+        f_min_hz=float(a.f_min_hz),
+        f_max_hz=float(a.f_max_hz),
+        transition_width_octaves=float(a.transition_width_octaves),
+        include_t20=bool(a.include_t20),
+        include_edt=bool(a.include_edt),
+        decay_settings=decay_settings_from_args(a, a.include_edt),
+    )
+    legend = (str(a.band_mode) == "three") if a.legend_values is None else bool(a.legend_values)
+    results = plot_rt60_bands_from_wav_file(
+        input_wav_file_path=str(a.input_wav_file_path),
+        settings=settings,
+        plot_settings=Rt60BandsPlotSettings(legend_values=legend),
+        output_basename=_basename(a),
+        show_interactive=not bool(a.no_show),
+    )
+    return summarise_rt60_bands_results_text(results, include_t20=settings.include_t20, include_edt=settings.include_edt)
+
+
+def run_waterfall_command(a: argparse.Namespace) -> str:
+    analysis = WaterfallAnalysisSettings(
+        use_mono_downmix_for_stereo=bool(a.use_mono_downmix),
+        trim_to_peak=bool(a.trim_to_peak),
+        ignore_leading_seconds=float(a.ignore_leading_seconds),
+        analysis_duration_seconds=a.analysis_duration_seconds,
+        n_fft=int(a.n_fft),
+        hop_length=int(a.hop_length),
+        use_hann_window=not bool(a.no_hann_window),
+        f_min_hz=float(a.f_min_hz),
+        f_max_hz=float(a.f_max_hz),
+        slice_mode=str(a.slice_mode),
+        num_slices=int(a.num_slices),
+        slice_spacing_seconds=float(a.slice_spacing_seconds),
+        start_time_seconds=float(a.start_time_seconds),
+        end_time_seconds=a.end_time_seconds,
+        db_reference=str(a.db_reference),
+        smoothing_log_bins=int(a.smoothing_log_bins),
+        log_bins_per_octave=int(a.log_bins_per_octave),
+        dynamic_range_db=float(a.dynamic_range_db),
+        floor_db=float(a.floor_db),
+    )
+    plot = WaterfallPlotSettings(style=str(a.style), elev_deg=float(a.elev_deg), azim_deg=float(a.azim_deg),
+                                 ridge_offset_db=float(a.ridge_offset_db))
+    results = plot_waterfall_from_wav_file(
+        input_wav_file_path=str(a.input_wav_file_path),
+        analysis_settings=analysis,
+        plot_settings=plot,
+        output_basename=_basename(a),
+        show_interactive=not bool(a.no_show),
+    )
+    return summarise_waterfall_results_text(results)
+
+
+def run_bundle_command(a: argparse.Namespace) -> str:
+    index = run_bundle_report(str(a.bundle_root), settings=BundleRunSettings(reports_subdir=str(a.reports_subdir)))
+    return f"Wrote bundle report index: {index}"
+
+
+COMMANDS = {
+    "decay": run_decay_command,
+    "rt60bands": run_rt60bands_command,
+    "waterfall": run_waterfall_command,
+    "bundle": run_bundle_command,
+}
+
+
+def main(argv: Optional[Sequence[str]] = None) -> None:
+    args = parse_arguments(argv)
+    handler = COMMANDS.get(str(args.command_name))
+    if handler is None:
+        raise ValueError(f"Unknown command: {args.command_name}")
+    print(handler(args))
+
+
+if __name__ == "__main__":
+    main()

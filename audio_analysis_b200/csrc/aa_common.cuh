@@ -1,0 +1,77 @@
+// Shared helpers for the audio_analysis_b200 CUDA library (sm_100a).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include "../../include/audio_analysis_b200.h"
+
+namespace aa {
+
+void set_error(const char* fmt, ...);
+void count_launch();  // every kernel launch of this library is counted (aa_kernel_launch_count)
+
+#define AA_CUDA_TRY(expr)                                                                        \
+    do {                                                                                         \
+        cudaError_t _e = (expr);                                                                 \
+        if (_e != cudaSuccess) {                                                                 \
+            ::aa::set_error("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, __LINE__); \
+            return AA_ERR_CUDA;                                                                  \
+        }                                                                                        \
+    } while (0)
+
+#define AA_REQUIRE(cond, code, msg)                                  \
+    do {                                                             \
+        if (!(cond)) {                                               \
+            ::aa::set_error("%s (%s:%d)", msg, __FILE__, __LINE__);  \
+            return code;                                             \
+        }                                                            \
+    } while (0)
+
+inline int launch_check(const char* what) {
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) {
+        set_error("launch of %s failed: %s", what, cudaGetErrorString(e));
+        return AA_ERR_CUDA;
+    }
+    count_launch();
+    return AA_OK;
+}
+
+constexpr int kWarp = 32;
+constexpr unsigned kFullMask = 0xffffffffu;
+
+#ifdef __CUDACC__
+
+// 10*log10(2): dB per octave of energy ratio.
+__device__ __forceinline__ float db10_from_ratio(float r) { return 3.010299956639812f * log2f(r); }
+
+// Inclusive -> exclusive suffix sum over the lanes of a warp (sum of strictly
+// HIGHER lanes).  One fixed instruction sequence so that every caller gets
+// bit-identical partial sums for the same inputs (the EDC tile carries rely on it).
+__device__ __forceinline__ float warp_suffix_exclusive(float v) {
+    float inc = v;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        float o = __shfl_down_sync(kFullMask, inc, d);
+        if ((threadIdx.x & 31) + d < 32) inc = __fadd_rn(inc, o);
+    }
+    float ex = __shfl_down_sync(kFullMask, inc, 1);
+    return ((threadIdx.x & 31) == 31) ? 0.0f : ex;
+}
+
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) v += __shfl_xor_sync(kFullMask, v, d);
+    return v;
+}
+
+__device__ __forceinline__ float4 ldg_f4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
+
+// streaming 128-bit store (output written once, never re-read by this kernel)
+__device__ __forceinline__ void st_cs_f4(float* p, float4 v) { __stcs(reinterpret_cast<float4*>(p), v); }
+
+#endif  // __CUDACC__
+
+}  // namespace aa

@@ -1,0 +1,138 @@
+// extern "C" surface of libaudio_analysis_b200 (see include/audio_analysis_b200.h).
+#include <stdarg.h>
+
+#include <atomic>
+#include <stdio.h>
+
+#include "fft.cuh"
+#include "kernels.cuh"
+
+struct aa_bands_plan;
+struct aa_deconv_plan;
+
+namespace aa {
+
+static thread_local char g_err[512] = "";
+static std::atomic<long long> g_launches{0};
+
+void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
+
+void set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+
+int bands_plan_create(int n, aa_bands_plan** out);
+void bands_plan_destroy(aa_bands_plan* p);
+size_t bands_workspace_bytes(const aa_bands_plan* p, int rows, int nb);
+int bands_plan_kind(const aa_bands_plan* p);
+int rt60bands_batch(const aa_bands_plan* plan, const float* d_x, long long row_stride, int n_rows,
+                    const int* d_start_idx, const aa_band* bands, int nb, double tw_oct, const aa_decay_params* p,
+                    double* d_metrics_out, float* d_band_signal_out, void* d_ws, size_t ws_bytes, cudaStream_t stream);
+int deconv_plan_create(int n_fft, aa_deconv_plan** out);
+void deconv_plan_destroy(aa_deconv_plan* p);
+size_t deconv_workspace_bytes(const aa_deconv_plan* p, int rows);
+int deconvolve_batch(const aa_deconv_plan* plan, const float* d_sweep, int n_sweep, const float* d_rec,
+                     long long rec_stride, int n_rec, int n_rows, double reg_rel, int remove_dc, double target_peak,
+                     int norm_group, int n_out, float* d_ir_out, long long ir_stride, void* d_ws, size_t ws_bytes,
+                     cudaStream_t stream);
+
+}  // namespace aa
+
+extern "C" {
+
+int aa_abi_version(void) { return AA_ABI_VERSION; }
+
+const char* aa_last_error(void) { return aa::g_err; }
+
+long long aa_kernel_launch_count(void) { return aa::g_launches.load(std::memory_order_relaxed); }
+
+int aa_device_count(void) {
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess) {
+        aa::set_error("cudaGetDeviceCount: %s", cudaGetErrorString(e));
+        cudaGetLastError();
+        return AA_ERR_NO_DEVICE;
+    }
+    return n;
+}
+
+int aa_peak_index_batch(const float* d_x, int64_t row_stride, const int32_t* d_lengths, int32_t n_rows,
+                        int32_t* d_peak_out, void* stream) {
+    AA_REQUIRE(d_lengths != nullptr, AA_ERR_INVALID_ARGUMENT, "d_lengths is required");
+    return aa::launch_peak(d_x, row_stride, d_lengths, 0, n_rows, d_peak_out, static_cast<cudaStream_t>(stream));
+}
+
+int aa_decay_batch(const float* d_x, int64_t row_stride, const int32_t* d_lengths, int32_t uniform_length,
+                   int32_t n_rows, const aa_decay_params* p, const int32_t* d_start_in, float* d_edc_db_out,
+                   int64_t edc_stride, int32_t* d_start_out, double* d_fits_out, double* d_early10_out,
+                   int32_t* d_status_out, void* stream) {
+    AA_REQUIRE(uniform_length >= 0 && uniform_length <= row_stride, AA_ERR_INVALID_ARGUMENT,
+               "uniform_length (the maximum row length) must be in [0, row_stride]");
+    return aa::launch_edc(d_x, row_stride, d_lengths, uniform_length, uniform_length, n_rows, p, d_start_in, 1, 4,
+                          d_edc_db_out, edc_stride, d_start_out, d_fits_out, nullptr, d_early10_out, d_status_out,
+                          static_cast<cudaStream_t>(stream));
+}
+
+int aa_curve_fits_batch(const float* d_curve, int64_t stride, const int32_t* d_lengths, int32_t uniform_length,
+                        const int32_t* d_offsets, int32_t n_rows, const aa_decay_params* p, double* d_fits_out,
+                        double* d_early10_out, void* stream) {
+    return aa::launch_curve_fits(d_curve, stride, d_lengths, uniform_length, d_offsets, n_rows, p, d_fits_out,
+                                 nullptr, d_early10_out, static_cast<cudaStream_t>(stream));
+}
+
+int aa_box_smooth_db_batch(const float* d_in, float* d_out, int64_t stride, const int32_t* d_lengths,
+                           int32_t uniform_length, const int32_t* d_offsets, int32_t n_rows, int32_t window,
+                           double floor_db, void* stream) {
+    return aa::launch_box_smooth(d_in, d_out, stride, d_lengths, uniform_length, d_offsets, n_rows, window, floor_db,
+                                 static_cast<cudaStream_t>(stream));
+}
+
+int aa_bands_plan_create(int32_t n, aa_bands_plan** out) { return aa::bands_plan_create(n, out); }
+void aa_bands_plan_destroy(aa_bands_plan* plan) { aa::bands_plan_destroy(plan); }
+int aa_bands_plan_kind(const aa_bands_plan* plan) { return aa::bands_plan_kind(plan); }
+size_t aa_bands_workspace_bytes(const aa_bands_plan* plan, int32_t rows_per_chunk, int32_t n_bands) {
+    return aa::bands_workspace_bytes(plan, rows_per_chunk, n_bands);
+}
+
+int aa_rt60bands_batch(const aa_bands_plan* plan, const float* d_x, int64_t row_stride, int32_t n_rows,
+                       const int32_t* d_start_idx, const aa_band* bands, int32_t n_bands,
+                       double transition_width_octaves, const aa_decay_params* p, double* d_metrics_out,
+                       float* d_band_signal_out, void* d_workspace, size_t workspace_bytes, void* stream) {
+    return aa::rt60bands_batch(plan, d_x, row_stride, n_rows, d_start_idx, bands, n_bands, transition_width_octaves, p,
+                               d_metrics_out, d_band_signal_out, d_workspace, workspace_bytes,
+                               static_cast<cudaStream_t>(stream));
+}
+
+int aa_csd_batch(const float* d_x, int64_t row_stride, const int32_t* d_lengths, int32_t uniform_length,
+                 int32_t n_rows, const int32_t* d_start_idx, const int32_t* d_frame_idx, const int32_t* d_n_slices,
+                 int32_t max_slices, const aa_csd_params* p, float* d_out, void* stream) {
+    return aa::launch_csd(d_x, row_stride, d_lengths, uniform_length, n_rows, d_start_idx, d_frame_idx, d_n_slices,
+                          max_slices, p, d_out, static_cast<cudaStream_t>(stream));
+}
+
+int aa_pcm16_to_float_batch(const int16_t* d_pcm, int64_t pcm_stride, int32_t n_files, int32_t n_frames,
+                            int32_t n_channels, int32_t mode, float* d_out, int64_t out_stride, void* stream) {
+    return aa::launch_pcm16(d_pcm, pcm_stride, n_files, n_frames, n_channels, mode, d_out, out_stride,
+                            static_cast<cudaStream_t>(stream));
+}
+
+int aa_deconv_plan_create(int32_t n_fft, aa_deconv_plan** out) { return aa::deconv_plan_create(n_fft, out); }
+void aa_deconv_plan_destroy(aa_deconv_plan* plan) { aa::deconv_plan_destroy(plan); }
+size_t aa_deconv_workspace_bytes(const aa_deconv_plan* plan, int32_t n_rows) {
+    return aa::deconv_workspace_bytes(plan, n_rows);
+}
+
+int aa_deconvolve_batch(const aa_deconv_plan* plan, const float* d_sweep, int32_t n_sweep, const float* d_rec,
+                        int64_t rec_stride, int32_t n_rec, int32_t n_rows, double regularization_relative,
+                        int32_t remove_dc, double target_peak, int32_t norm_group, int32_t n_out, float* d_ir_out,
+                        int64_t ir_stride, void* d_workspace, size_t workspace_bytes, void* stream) {
+    return aa::deconvolve_batch(plan, d_sweep, n_sweep, d_rec, rec_stride, n_rec, n_rows, regularization_relative,
+                                remove_dc, target_peak, norm_group, n_out, d_ir_out, ir_stride, d_workspace,
+                                workspace_bytes, static_cast<cudaStream_t>(stream));
+}
+
+}  // extern "C"

@@ -1,0 +1,300 @@
+// Band-limited RT60 (analyse/rt60bands.py:324-413) for a batch of equal-length rows.
+//
+// Per chunk of rows:
+//   1. one forward length-N real FFT per row (the reference recomputes it for every band,
+//      rt60bands.py:172) -> half spectrum X kept in the workspace;
+//   2. one inverse per (row, band): the raised-cosine mask (rt60bands.py:116-167), the
+//      Hermitian packing and the conjugation are generated inside the first FFT pass while
+//      it loads its columns, so the masked spectrum never exists in memory;
+//   3. the fused EDC kernel in metrics-only mode on every band signal with the row's shared
+//      start index (rt60bands.py:342,393), writing only the RT60 table.
+#include <math.h>
+#include <string.h>
+
+#include <vector>
+
+#include "fft.cuh"
+#include "kernels.cuh"
+
+struct aa_bands_plan {
+    int n = 0;
+    int kind = 0;   // 0 direct, 1 Bluestein on n/2, 2 odd n (complex length n; Bluestein unless n is smooth)
+    int M = 0;      // complex transform length: n/2 (even) or n (odd)
+    int x_stride = 0;   // float2 per row of the kept half spectrum
+    int y_stride = 0;   // floats per band signal row (n rounded up to 4)
+    aa::C2CPlan* c2c = nullptr;
+    aa::TwoLevelTable twN;
+};
+
+namespace aa {
+
+namespace {
+
+constexpr size_t kAlign = 256;
+inline size_t align_up(size_t v) { return (v + kAlign - 1) / kAlign * kAlign; }
+
+__global__ void untangle_kernel(const float2* __restrict__ Z, float2* __restrict__ X, int M, int x_stride,
+                                TwoLevelTwiddle twN) {
+    const long long row = blockIdx.y;
+    const float2* __restrict__ z = Z + row * (long long)M;
+    float2* __restrict__ o = X + row * (long long)x_stride;
+    for (int k = blockIdx.x * blockDim.x + threadIdx.x; k <= M; k += gridDim.x * blockDim.x) {
+        const int km = (k == M) ? 0 : k;
+        const int mk = (k == 0) ? 0 : M - k;
+        o[k] = untangle_half_spectrum(__ldg(z + km), __ldg(z + mk), twiddle2(twN, k));
+    }
+}
+
+// Host mirror of _make_lowpass_mask / _make_highpass_mask / _make_bandpass_mask edge handling
+// (analyse/rt60bands.py:127-167); python floats are doubles, numpy rounds them to float32 when they
+// meet the float32 frequency array.
+int make_band_dev(const aa_band& b, double tw_oct, double nyq, double freq_scale, int n_bins, BandDev* o) {
+    memset(o, 0, sizeof(*o));
+    o->kind = b.kind;
+    const double fac = pow(2.0, tw_oct);
+    auto clipd = [](double v, double lo, double hi) { return v < lo ? lo : (v > hi ? hi : v); };
+    double lo_edge = b.low_edge_hz, hi_edge = b.high_edge_hz;
+    if (b.kind == AA_BAND_BANDPASS) {
+        lo_edge = clipd(lo_edge, 1.0, nyq);
+        hi_edge = clipd(hi_edge, 1.0, nyq);
+        if (hi_edge <= lo_edge) o->degenerate = 1;
+    } else if (b.kind != AA_BAND_LOWPASS && b.kind != AA_BAND_HIGHPASS) {
+        set_error("unknown band kind %d", b.kind);
+        return AA_ERR_INVALID_ARGUMENT;
+    }
+    double hp_stop = 0.0, lp_stop = nyq;
+    if (b.kind != AA_BAND_LOWPASS) {
+        double pass = clipd(lo_edge, 1.0, nyq);
+        double stop = fmax(1.0, pass / fac);
+        if (pass <= stop) stop = fmax(1.0, pass - 1.0);
+        o->hp_pass = (float)pass;
+        o->hp_stop = (float)stop;
+        o->hp_span = (float)(pass - stop);
+        o->hp_step = (pass <= stop) ? 1 : 0;
+        hp_stop = stop;
+    }
+    if (b.kind != AA_BAND_HIGHPASS) {
+        double pass = clipd(hi_edge, 1.0, nyq);
+        double stop = fmin(nyq, pass * fac);
+        if (stop <= pass) stop = fmin(nyq, pass + 1.0);
+        o->lp_pass = (float)pass;
+        o->lp_stop = (float)stop;
+        o->lp_span = (float)(stop - pass);
+        o->lp_step = (stop <= pass) ? 1 : 0;
+        lp_stop = stop;
+    }
+    // conservative superset of the bins where the mask can be non-zero
+    int kf = 0, kl = n_bins - 1;
+    if (b.kind != AA_BAND_LOWPASS) kf = (int)floor(hp_stop / freq_scale) - 1;
+    if (b.kind != AA_BAND_HIGHPASS) kl = (int)ceil(lp_stop / freq_scale) + 1;
+    o->k_first = kf < 0 ? 0 : kf;
+    o->k_last = kl > n_bins - 1 ? n_bins - 1 : kl;
+    return AA_OK;
+}
+
+struct Layout {
+    size_t off_bands, off_X, off_y, off_scratch, off_db0, off_db1, off_unit_start, total;
+};
+
+Layout make_layout(const aa_bands_plan* p, long long rows, int nb, bool smoothing = false) {
+    Layout l{};
+    const long long units = rows * nb;
+    size_t o = 0;
+    l.off_bands = o;
+    o += align_up(sizeof(BandDev) * AA_MAX_BANDS);
+    l.off_X = o;
+    o += align_up(sizeof(float2) * (size_t)rows * (size_t)p->x_stride);
+    l.off_y = o;  // also the forward transform's packed output Z (rows * M float2 <= units * y_stride floats)
+    size_t ybytes = sizeof(float) * (size_t)units * (size_t)p->y_stride;
+    size_t zbytes = sizeof(float2) * (size_t)rows * (size_t)p->M;
+    o += align_up(ybytes > zbytes ? ybytes : zbytes);
+    l.off_scratch = o;
+    o += align_up(sizeof(float2) * c2c_scratch_elems(p->c2c, units));
+    if (smoothing) {  // dB curves of the band signals, before and after the box filter (decay.py:161-164)
+        l.off_db0 = o;
+        o += align_up(sizeof(float) * (size_t)units * (size_t)p->y_stride);
+        l.off_db1 = o;
+        o += align_up(sizeof(float) * (size_t)units * (size_t)p->y_stride);
+        l.off_unit_start = o;
+        o += align_up(sizeof(int) * (size_t)units);
+    }
+    l.total = o;
+    return l;
+}
+
+}  // namespace
+
+int bands_plan_create(int n, aa_bands_plan** out) {
+    AA_REQUIRE(out != nullptr, AA_ERR_INVALID_ARGUMENT, "null plan pointer");
+    AA_REQUIRE(n >= 8, AA_ERR_INVALID_ARGUMENT, "Not enough samples for rt60bands analysis.");  // rt60bands.py:346
+    AA_REQUIRE(n <= AA_MAX_ROW_SAMPLES, AA_ERR_TOO_LONG, "row longer than AA_MAX_ROW_SAMPLES");
+    aa_bands_plan* p = new aa_bands_plan();
+    p->n = n;
+    const bool even = (n % 2) == 0;
+    p->M = even ? n / 2 : n;
+    p->x_stride = even ? n / 2 + 1 : n;
+    p->y_stride = (n + 3) & ~3;
+    int rc = c2c_plan_create(p->M, &p->c2c);
+    if (rc == AA_OK) rc = build_two_level(n, &p->twN);
+    if (rc != AA_OK) {
+        if (p->c2c) c2c_plan_destroy(p->c2c);
+        free_two_level(&p->twN);
+        delete p;
+        return rc;
+    }
+    p->kind = even ? (p->c2c->bluestein ? 1 : 0) : 2;
+    *out = p;
+    return AA_OK;
+}
+
+int bands_plan_kind(const aa_bands_plan* p) { return p ? p->kind : AA_ERR_INVALID_ARGUMENT; }
+
+void bands_plan_destroy(aa_bands_plan* p) {
+    if (!p) return;
+    if (p->c2c) c2c_plan_destroy(p->c2c);
+    free_two_level(&p->twN);
+    delete p;
+}
+
+size_t bands_workspace_bytes(const aa_bands_plan* p, int rows, int nb) {
+    if (!p || rows < 1 || nb < 1) return 0;
+    return make_layout(p, rows, nb, true).total;  // sized for the (larger) smoothing variant
+}
+
+int rt60bands_batch(const aa_bands_plan* plan, const float* d_x, long long row_stride, int n_rows,
+                    const int* d_start_idx, const aa_band* bands, int nb, double tw_oct, const aa_decay_params* p,
+                    double* d_metrics_out, float* d_band_signal_out, void* d_ws, size_t ws_bytes,
+                    cudaStream_t stream) {
+    AA_REQUIRE(plan && d_x && d_start_idx && bands && p && d_metrics_out && d_ws, AA_ERR_INVALID_ARGUMENT,
+               "null argument");
+    AA_REQUIRE(nb >= 1 && nb <= AA_MAX_BANDS, AA_ERR_INVALID_ARGUMENT, "band count out of range");
+    AA_REQUIRE(row_stride >= plan->n && row_stride % 4 == 0, AA_ERR_INVALID_ARGUMENT,
+               "row_stride must be >= n and a multiple of 4");
+    AA_REQUIRE((reinterpret_cast<uintptr_t>(d_x) & 15) == 0 && (reinterpret_cast<uintptr_t>(d_ws) & 255) == 0,
+               AA_ERR_INVALID_ARGUMENT, "input rows / workspace not aligned");
+    AA_REQUIRE(p->sample_rate_hz > 0, AA_ERR_INVALID_ARGUMENT, "sample rate must be positive");
+    if (n_rows <= 0) return AA_OK;
+    const int N = plan->n, M = plan->M;
+    const bool even = (N % 2) == 0;
+    const double sr = (double)p->sample_rate_hz;
+    const double freq_scale = 1.0 / ((double)N * (1.0 / sr));  // numpy.fft.rfftfreq(n, d=1/sr) (rt60bands.py:350)
+    const double nyq = 0.5 * sr;
+
+    const bool smoothing = p->smoothing_window > 1;
+    aa_decay_params pk = *p;  // kernel-level parameters: smoothing is applied here, not in the fused kernel
+    pk.smoothing_window = 0;
+    // rows per chunk that fit the workspace
+    long long rc_rows = 0;
+    {
+        long long lo = 0, hi = n_rows;
+        while (lo < hi) {
+            long long mid = (lo + hi + 1) / 2;
+            if (make_layout(plan, mid, nb, smoothing).total <= ws_bytes) lo = mid; else hi = mid - 1;
+        }
+        rc_rows = lo;
+    }
+    AA_REQUIRE(rc_rows >= 1, AA_ERR_WORKSPACE, "workspace too small for one row (see aa_bands_workspace_bytes)");
+    const Layout lay = make_layout(plan, rc_rows, nb, smoothing);
+    unsigned char* ws = static_cast<unsigned char*>(d_ws);
+    BandDev* d_bands = reinterpret_cast<BandDev*>(ws + lay.off_bands);
+    float2* d_X = reinterpret_cast<float2*>(ws + lay.off_X);
+    float* d_y = reinterpret_cast<float*>(ws + lay.off_y);
+    float2* d_Z = reinterpret_cast<float2*>(ws + lay.off_y);
+    float2* d_scr = reinterpret_cast<float2*>(ws + lay.off_scratch);
+
+    std::vector<BandDev> hb((size_t)nb);
+    for (int i = 0; i < nb; ++i) {
+        int rc = make_band_dev(bands[i], tw_oct, nyq, freq_scale, N / 2 + 1, &hb[(size_t)i]);
+        if (rc != AA_OK) return rc;
+    }
+    AA_CUDA_TRY(cudaMemcpyAsync(d_bands, hb.data(), sizeof(BandDev) * (size_t)nb, cudaMemcpyHostToDevice, stream));
+    // the host vector must outlive the copy: pageable-memory async copies are staged before returning
+
+    for (long long r0 = 0; r0 < n_rows; r0 += rc_rows) {
+        const long long rows = (n_rows - r0 < rc_rows) ? (n_rows - r0) : rc_rows;
+        const long long units = rows * nb;
+        const float* xin = d_x + r0 * row_stride;
+        int rc;
+        // ---- 1. forward real FFT of every row
+        if (even) {
+            SrcDesc s{};
+            s.mode = SRC_REAL_PACKED;
+            s.base = xin;
+            s.unit_stride = row_stride;
+            s.n_valid = N;
+            rc = c2c_exec(plan->c2c, s, make_dst_complex(d_Z, M, M, 0, 1.0f), rows, d_scr, stream);
+            if (rc != AA_OK) return rc;
+            dim3 grid((unsigned)((M + 1 + 255) / 256 > 1024 ? 1024 : (M + 1 + 255) / 256), (unsigned)rows);
+            untangle_kernel<<<grid, 256, 0, stream>>>(d_Z, d_X, M, plan->x_stride, plan->twN.dev);
+            rc = launch_check("untangle_kernel");
+            if (rc != AA_OK) return rc;
+        } else {
+            SrcDesc s{};
+            s.mode = SRC_REAL_AS_COMPLEX;
+            s.base = xin;
+            s.unit_stride = row_stride;
+            s.n_valid = N;
+            rc = c2c_exec(plan->c2c, s, make_dst_complex(d_X, plan->x_stride, N, 0, 1.0f), rows, d_scr, stream);
+            if (rc != AA_OK) return rc;
+        }
+        // ---- 2. masked inverse per (row, band)
+        SrcDesc s{};
+        s.mode = even ? SRC_BAND_PACKED : SRC_BAND_FULL;
+        s.base = d_X;
+        s.unit_stride = plan->x_stride;
+        s.n_valid = M;
+        s.conj = 1;
+        s.n_bands = nb;
+        s.bands = d_bands;
+        s.freq_scale = freq_scale;
+        s.N = N;
+        s.M = even ? M : 0;
+        s.twN = plan->twN.dev;
+        DstDesc d{};
+        if (even) {
+            d = make_dst_complex(reinterpret_cast<float2*>(d_y), plan->y_stride / 2, M, 1, 1.0f / (float)M);
+        } else {
+            d.mode = DST_REAL_PART;
+            d.base = d_y;
+            d.unit_stride = plan->y_stride;
+            d.n_valid = N;
+            d.conj1 = 1;
+            d.scale1 = 1.0f / (float)N;
+            d.scale2 = 1.0f;
+        }
+        rc = c2c_exec(plan->c2c, s, d, units, d_scr, stream);
+        if (rc != AA_OK) return rc;
+        if (d_band_signal_out) {
+            AA_CUDA_TRY(cudaMemcpy2DAsync(d_band_signal_out + r0 * nb * (long long)N, sizeof(float) * (size_t)N, d_y,
+                                          sizeof(float) * (size_t)plan->y_stride, sizeof(float) * (size_t)N,
+                                          (size_t)units, cudaMemcpyDeviceToDevice, stream));
+        }
+        // ---- 3. band EDC + fits, metrics only
+        if (!smoothing) {
+            rc = launch_edc(d_y, plan->y_stride, nullptr, N, N, (int)units, &pk, d_start_idx + r0, nb, 8, nullptr, 0,
+                            nullptr, nullptr, d_metrics_out + r0 * nb * AA_MAX_FITS, nullptr, nullptr, stream);
+            if (rc != AA_OK) return rc;
+        } else {
+            // slow path: raw dB curve -> box filter -> floor -> generic (non-monotone) crossings and fits
+            float* d_db0 = reinterpret_cast<float*>(ws + lay.off_db0);
+            float* d_db1 = reinterpret_cast<float*>(ws + lay.off_db1);
+            int* d_ustart = reinterpret_cast<int*>(ws + lay.off_unit_start);
+            aa_decay_params praw = pk;
+            praw.n_fits = 0;
+            praw.want_early10 = 0;
+            praw.edc_floor_db = -INFINITY;
+            rc = launch_edc(d_y, plan->y_stride, nullptr, N, N, (int)units, &praw, d_start_idx + r0, nb, 8, d_db0,
+                            plan->y_stride, d_ustart, nullptr, nullptr, nullptr, nullptr, stream);
+            if (rc != AA_OK) return rc;
+            rc = launch_box_smooth(d_db0, d_db1, plan->y_stride, nullptr, N, d_ustart, (int)units, p->smoothing_window,
+                                   p->edc_floor_db, stream);
+            if (rc != AA_OK) return rc;
+            rc = launch_curve_fits(d_db1, plan->y_stride, nullptr, N, d_ustart, (int)units, &pk, nullptr,
+                                   d_metrics_out + r0 * nb * AA_MAX_FITS, nullptr, stream);
+            if (rc != AA_OK) return rc;
+        }
+    }
+    return AA_OK;
+}
+
+}  // namespace aa

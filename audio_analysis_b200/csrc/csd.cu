@@ -1,0 +1,279 @@
+// Waterfall / cumulative-spectral-decay slices (sm_100a).
+//
+// Replaces analyse/waterfall.py:188-230 (windowed rFFT magnitude in dB) for the
+// <= num_slices frames that reach the result, and analyse/waterfall.py:289-341
+// (frequency crop, subtraction of the global / per-slice maximum, clip).  The
+// reference computes every STFT frame and then keeps <= 18 of them.
+//
+// One CTA owns one row (channel): for each selected frame it stages n_fft
+// samples in shared memory with 128-bit loads (aligned superset, shifted while
+// windowing), runs an n_fft/2-point complex Stockham FFT in shared memory,
+// untangles to the real spectrum, converts |X| to dB and stores the cropped
+// bins.  The running maximum stays on chip; a final in-place pass over the
+// CTA's own (L2-resident) output applies the reference level and the clip.
+#include <math.h>
+
+#include <map>
+#include <mutex>
+#include <vector>
+
+#include "aa_common.cuh"
+#include "fft_access.cuh"
+#include "fft_plan_host.hpp"
+
+namespace aa {
+
+namespace {
+
+constexpr int kCsdThreads = 256;
+
+struct CsdTables {
+    SubPlanDev sp{};        // n_fft/2-point complex plan
+    float2* d_tw = nullptr;
+    float2* d_twN = nullptr;  // exp(-2 pi i k / n_fft), k in [0, n_fft/2]
+    float* d_hann = nullptr;  // np.hanning(n_fft) (waterfall.py:212)
+};
+
+std::mutex g_mu;
+std::map<std::pair<int, int>, CsdTables> g_tables;  // (device, n_fft) -> immutable tables
+
+int get_tables(int n_fft, CsdTables* out) {
+    int dev = 0;
+    AA_CUDA_TRY(cudaGetDevice(&dev));
+    std::lock_guard<std::mutex> lock(g_mu);
+    auto key = std::make_pair(dev, n_fft);
+    auto it = g_tables.find(key);
+    if (it != g_tables.end()) {
+        *out = it->second;
+        return AA_OK;
+    }
+    const int M = n_fft / 2;
+    HostSubPlan hp;
+    if (!host_subplan(M, &hp)) {
+        set_error("n_fft %d unsupported", n_fft);
+        return AA_ERR_UNSUPPORTED;
+    }
+    CsdTables t;
+    t.sp.L = hp.L;
+    t.sp.nst = hp.nst;
+    memcpy(t.sp.radix, hp.radix, sizeof(hp.radix));
+    std::vector<float2> twn((size_t)M + 1);
+    for (int k = 0; k <= M; ++k) {
+        double a = -2.0 * M_PI * (double)k / (double)n_fft;
+        twn[(size_t)k] = make_float2((float)cos(a), (float)sin(a));
+    }
+    std::vector<float> hann((size_t)n_fft);
+    for (int k = 0; k < n_fft; ++k)  // numpy.hanning: 0.5 - 0.5 cos(2 pi k / (n - 1)); n == 1 -> [1]
+        hann[(size_t)k] = (n_fft == 1) ? 1.0f : (float)(0.5 - 0.5 * cos(2.0 * M_PI * (double)k / (double)(n_fft - 1)));
+    AA_CUDA_TRY(cudaMalloc(&t.d_tw, sizeof(float2) * (size_t)M));
+    AA_CUDA_TRY(cudaMalloc(&t.d_twN, sizeof(float2) * ((size_t)M + 1)));
+    AA_CUDA_TRY(cudaMalloc(&t.d_hann, sizeof(float) * (size_t)n_fft));
+    AA_CUDA_TRY(cudaMemcpy(t.d_tw, hp.tw.data(), sizeof(float2) * (size_t)M, cudaMemcpyHostToDevice));
+    AA_CUDA_TRY(cudaMemcpy(t.d_twN, twn.data(), sizeof(float2) * ((size_t)M + 1), cudaMemcpyHostToDevice));
+    AA_CUDA_TRY(cudaMemcpy(t.d_hann, hann.data(), sizeof(float) * (size_t)n_fft, cudaMemcpyHostToDevice));
+    t.sp.tw = t.d_tw;
+    g_tables[key] = t;
+    *out = t;
+    return AA_OK;
+}
+
+struct CsdArgs {
+    const float* x;
+    long long row_stride;
+    const int* lengths;
+    int uniform_len;
+    const int* start_idx;
+    const int* frame_idx;
+    const int* n_slices;
+    int max_slices;
+    int n_fft, hop, use_hann;
+    int bin_lo, n_bins;
+    int db_reference;
+    float floor_lin_sq;  // (10^(floor_db/20))^2
+    float dyn;
+    float* out;
+    SubPlanDev sp;
+    const float2* twN;
+    const float* hann;
+};
+
+__device__ __forceinline__ float block_max(float v, float* red) {
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) v = fmaxf(v, __shfl_xor_sync(kFullMask, v, d));
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
+    __syncthreads();
+    float m = red[0];
+    for (int w = 1; w < (int)(blockDim.x >> 5); ++w) m = fmaxf(m, red[w]);
+    return m;
+}
+
+__global__ void __launch_bounds__(kCsdThreads) csd_kernel(CsdArgs a) {
+    extern __shared__ __align__(16) unsigned char dyn_smem[];
+    const int row = blockIdx.x;
+    const int M = a.n_fft >> 1;
+    float2* bufA = reinterpret_cast<float2*>(dyn_smem);
+    float2* bufB = bufA + M;
+    float* raw = reinterpret_cast<float*>(bufB + M);  // n_fft + 8 floats (aligned superset of the frame)
+    __shared__ float red[kCsdThreads / 32];
+    __shared__ float slice_ref[AA_MAX_SLICES];
+
+    const int len = a.lengths ? a.lengths[row] : a.uniform_len;
+    const float* __restrict__ x = a.x + (long long)row * a.row_stride;
+    const int start = a.start_idx[row];
+    const int ns = min(a.n_slices[row], a.max_slices);
+    float* __restrict__ out_row = a.out + (long long)row * a.max_slices * a.n_bins;
+    const int len4 = (len + 3) & ~3;  // row_stride >= len4: the pitch padding is readable
+
+    float run_max = -INFINITY;
+    for (int s = 0; s < ns; ++s) {
+        const int f0 = start + a.frame_idx[(long long)row * a.max_slices + s] * a.hop;
+        const int a0 = f0 & ~3;
+        const int shift = f0 - a0;
+        const int nvec = (a.n_fft + shift + 3) >> 2;  // float4s covering [a0, f0 + n_fft)
+        for (int q = threadIdx.x; q < nvec; q += blockDim.x) {
+            const int g = a0 + 4 * q;
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (g >= 0 && g + 4 <= len4) v = ldg_f4(x + g);
+            reinterpret_cast<float4*>(raw)[q] = v;
+        }
+        __syncthreads();
+        // window (waterfall.py:223) and pack z[m] = (w x)[2m] + i (w x)[2m+1]
+        for (int m = threadIdx.x; m < M; m += blockDim.x) {
+            float x0 = raw[shift + 2 * m], x1 = raw[shift + 2 * m + 1];
+            if (f0 + 2 * m >= len) x0 = 0.f;
+            if (f0 + 2 * m + 1 >= len) x1 = 0.f;
+            if (a.use_hann) {
+                x0 *= __ldg(a.hann + 2 * m);
+                x1 *= __ldg(a.hann + 2 * m + 1);
+            }
+            bufA[m] = make_float2(x0, x1);
+        }
+        __syncthreads();
+        float2* pa = bufA;
+        float2* pb = bufB;
+        int Ns = 1;
+        for (int st = 0; st < a.sp.nst; ++st) {
+            const int R = a.sp.radix[st];
+            const int nb = M / R;
+            for (int j = threadIdx.x; j < nb; j += blockDim.x) stockham_butterfly(R, j, M, Ns, pa, pb, a.sp.tw);
+            __syncthreads();
+            float2* t = pa;
+            pa = pb;
+            pb = t;
+            Ns *= R;
+        }
+        // untangle -> |X|^2 -> dB, cropped to [bin_lo, bin_lo + n_bins)   (waterfall.py:224-227, :304-309)
+        float smax = -INFINITY;
+        float* __restrict__ o = out_row + (long long)s * a.n_bins;
+        for (int b = threadIdx.x; b < a.n_bins; b += blockDim.x) {
+            const int k = a.bin_lo + b;
+            float2 zk = pa[k == M ? 0 : k];
+            float2 zm = pa[(M - k) == M ? 0 : (M - k)];
+            float2 X = untangle_half_spectrum(zk, zm, __ldg(a.twN + k));
+            float p = fmaxf(X.x * X.x + X.y * X.y, a.floor_lin_sq);
+            float db = 10.0f * log10f(p);
+            o[b] = db;
+            smax = fmaxf(smax, db);
+        }
+        if (a.db_reference == AA_DBREF_SLICE_MAX) {
+            float m = block_max(smax, red);
+            if (threadIdx.x == 0) slice_ref[s] = m;
+        } else {
+            run_max = fmaxf(run_max, smax);
+        }
+        __syncthreads();
+    }
+    if (a.db_reference == AA_DBREF_NONE) return;
+    float gref = 0.f;
+    if (a.db_reference == AA_DBREF_GLOBAL_MAX) gref = block_max(run_max, red);  // waterfall.py:335
+    __syncthreads();
+    // the CTA re-reads its own stores: ordered by the barrier above
+    for (int s = 0; s < ns; ++s) {
+        const float ref = (a.db_reference == AA_DBREF_SLICE_MAX) ? slice_ref[s] : gref;
+        float* __restrict__ o = out_row + (long long)s * a.n_bins;
+        for (int b = threadIdx.x; b < a.n_bins; b += blockDim.x) {
+            float r = o[b] - ref;
+            o[b] = fminf(fmaxf(r, -a.dyn), 0.0f);  // waterfall.py:338-339
+        }
+    }
+}
+
+__global__ void pcm16_kernel(const short* __restrict__ pcm, long long pcm_stride, int n_frames, int n_channels,
+                             int mode, float* __restrict__ out, long long out_stride) {
+    const int file = blockIdx.y;
+    const short* __restrict__ p = pcm + (long long)file * pcm_stride;
+    const float k = 1.0f / 32768.0f;  // io.py:59; |pcm/32768| <= 1 so the clip at io.py:109 never acts
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n_frames; i += gridDim.x * blockDim.x) {
+        if (n_channels == 1) {
+            out[(long long)file * out_stride + i] = (float)p[i] * k;
+        } else if (mode == 1) {
+            float l = (float)p[2 * i] * k, r = (float)p[2 * i + 1] * k;
+            out[(long long)file * out_stride + i] = 0.5f * __fadd_rn(l, r);  // io.py:90
+        } else {
+            for (int c = 0; c < n_channels; ++c)
+                out[((long long)file * n_channels + c) * out_stride + i] = (float)p[(long long)i * n_channels + c] * k;
+        }
+    }
+}
+
+}  // namespace
+
+int launch_csd(const float* d_x, long long row_stride, const int* d_lengths, int uniform_len, int n_rows,
+               const int* d_start_idx, const int* d_frame_idx, const int* d_n_slices, int max_slices,
+               const aa_csd_params* p, float* d_out, cudaStream_t stream) {
+    AA_REQUIRE(d_x && d_start_idx && d_frame_idx && d_n_slices && p && d_out, AA_ERR_INVALID_ARGUMENT, "null argument");
+    AA_REQUIRE(row_stride % 4 == 0 && (reinterpret_cast<uintptr_t>(d_x) & 15) == 0, AA_ERR_INVALID_ARGUMENT,
+               "rows must be 16-byte aligned (row_stride % 4 == 0)");
+    AA_REQUIRE(p->n_fft >= 64 && p->n_fft <= 8192 && (p->n_fft & (p->n_fft - 1)) == 0, AA_ERR_UNSUPPORTED,
+               "n_fft must be a power of two in [64, 8192]");
+    AA_REQUIRE(p->hop_length > 0, AA_ERR_INVALID_ARGUMENT, "hop_length must be positive");
+    AA_REQUIRE(max_slices >= 1 && max_slices <= AA_MAX_SLICES, AA_ERR_INVALID_ARGUMENT, "max_slices out of range");
+    AA_REQUIRE(p->bin_lo >= 0 && p->n_bins >= 1 && p->bin_lo + p->n_bins <= p->n_fft / 2 + 1, AA_ERR_INVALID_ARGUMENT,
+               "bin range outside the rfft");
+    if (n_rows <= 0) return AA_OK;
+    CsdTables t;
+    int rc = get_tables(p->n_fft, &t);
+    if (rc != AA_OK) return rc;
+    CsdArgs a{};
+    a.x = d_x;
+    a.row_stride = row_stride;
+    a.lengths = d_lengths;
+    a.uniform_len = uniform_len;
+    a.start_idx = d_start_idx;
+    a.frame_idx = d_frame_idx;
+    a.n_slices = d_n_slices;
+    a.max_slices = max_slices;
+    a.n_fft = p->n_fft;
+    a.hop = p->hop_length;
+    a.use_hann = p->use_hann_window;
+    a.bin_lo = p->bin_lo;
+    a.n_bins = p->n_bins;
+    a.db_reference = p->db_reference;
+    const double fl = pow(10.0, p->floor_db / 20.0);  // waterfall.py:218
+    a.floor_lin_sq = (float)(fl * fl);
+    a.dyn = (float)p->dynamic_range_db;
+    a.out = d_out;
+    a.sp = t.sp;
+    a.twN = t.d_twN;
+    a.hann = t.d_hann;
+    const size_t smem = sizeof(float2) * (size_t)p->n_fft + sizeof(float) * ((size_t)p->n_fft + 8);
+    AA_CUDA_TRY(cudaFuncSetAttribute(csd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 1024));
+    csd_kernel<<<n_rows, kCsdThreads, smem, stream>>>(a);
+    return launch_check("csd_kernel");
+}
+
+int launch_pcm16(const int16_t* d_pcm, long long pcm_stride, int n_files, int n_frames, int n_channels, int mode,
+                 float* d_out, long long out_stride, cudaStream_t stream) {
+    AA_REQUIRE(d_pcm && d_out, AA_ERR_INVALID_ARGUMENT, "null argument");
+    AA_REQUIRE(n_channels == 1 || n_channels == 2, AA_ERR_INVALID_ARGUMENT, "1 or 2 channels (io.py:172-178)");
+    if (n_files <= 0 || n_frames <= 0) return AA_OK;
+    int bx = (n_frames + 255) / 256;
+    if (bx > 1024) bx = 1024;
+    dim3 grid((unsigned)bx, (unsigned)n_files);
+    pcm16_kernel<<<grid, 256, 0, stream>>>(reinterpret_cast<const short*>(d_pcm), pcm_stride, n_frames, n_channels, mode,
+                                           d_out, out_stride);
+    return launch_check("pcm16_kernel");
+}
+
+}  // namespace aa

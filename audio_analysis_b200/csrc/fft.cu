@@ -1,0 +1,344 @@
+// Batched complex FFT engine for sm_100a: shared-memory Stockham passes, a
+// two-pass (four-step) split for transforms that do not fit one CTA, and a
+// Bluestein chirp-z fallback for lengths with prime factors above 13.
+//
+// Used for the exact length-N circular filterbank of analyse/rt60bands.py:170-175
+// (numpy pocketfft rfft/irfft on arbitrary N) and for the power-of-two
+// deconvolution transform (analyse/deconvolve.py:147-171).
+#include <math.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <vector>
+
+#include "fft.cuh"
+#include "fft_plan_host.hpp"
+
+namespace aa {
+
+namespace {
+
+constexpr int kPassThreads = 256;
+constexpr size_t kSmemSoft = 96 * 1024;  // aim for 2 CTAs per SM
+constexpr size_t kSmemHard = 200 * 1024;
+
+int upload(const std::vector<float2>& h, float2** d) {
+    AA_CUDA_TRY(cudaMalloc(d, sizeof(float2) * h.size()));
+    AA_CUDA_TRY(cudaMemcpy(*d, h.data(), sizeof(float2) * h.size(), cudaMemcpyHostToDevice));
+    return AA_OK;
+}
+
+int upload_subplan(const HostSubPlan& h, SubPlan* sp) {
+    memset(&sp->dev, 0, sizeof(sp->dev));
+    sp->dev.L = h.L;
+    sp->dev.nst = h.nst;
+    memcpy(sp->dev.radix, h.radix, sizeof(h.radix));
+    int rc = upload(h.tw, &sp->d_tw);
+    if (rc != AA_OK) return rc;
+    sp->dev.tw = sp->d_tw;
+    return AA_OK;
+}
+
+int upload_two_level(const HostTwoLevel& h, TwoLevelTable* out) {
+    int rc = upload(h.hi, &out->d_hi);
+    if (rc != AA_OK) return rc;
+    rc = upload(h.lo, &out->d_lo);
+    if (rc != AA_OK) return rc;
+    out->dev.hi = out->d_hi;
+    out->dev.lo = out->d_lo;
+    out->dev.shift = h.shift;
+    return AA_OK;
+}
+
+void choose_group(int L, int* G, int* Lp, size_t* smem) {
+    int lp = L | 1;  // odd row pitch: column-major accesses hit distinct banks
+    size_t per = 2 * sizeof(float2) * (size_t)lp;
+    int g = (int)(kSmemSoft / per);
+    if (g < 4) g = (int)(kSmemHard / per);
+    if (g > 16) g = 16;
+    if (g < 1) g = 1;
+    *G = g;
+    *Lp = lp;
+    *smem = per * (size_t)g;
+}
+
+// ------------------------------------------------------------------------------------
+// pass kernels
+// ------------------------------------------------------------------------------------
+
+struct PassArgs {
+    SubPlanDev sp;
+    int G, Lp;
+    int M1, M2;
+    int groups;  // CTAs per unit
+    TwoLevelTwiddle twM;
+};
+
+__device__ __forceinline__ void run_stages(const SubPlanDev& sp, int G, int Lp, float2*& a, float2*& b) {
+    const int L = sp.L;
+    int Ns = 1;
+    for (int s = 0; s < sp.nst; ++s) {
+        const int R = sp.radix[s];
+        const int nb = L / R;
+        const int total = G * nb;
+        for (int e = threadIdx.x; e < total; e += blockDim.x) {
+            const int g = e / nb;
+            const int j = e - g * nb;
+            stockham_butterfly(R, j, L, Ns, a + g * Lp, b + g * Lp, sp.tw);
+        }
+        __syncthreads();
+        float2* t = a;
+        a = b;
+        b = t;
+        Ns *= R;
+    }
+}
+
+// pass 1: columns.  CTA = G adjacent columns n2 of one unit; M1-point FFT over n1; twiddle; store [k1*M2 + n2].
+__global__ void __launch_bounds__(kPassThreads) fft_pass1_kernel(PassArgs pa, SrcDesc src, float2* scratch,
+                                                                 long long scratch_stride) {
+    extern __shared__ float2 smem[];
+    const long long unit = blockIdx.x / pa.groups;
+    const int cg = blockIdx.x - (int)(unit * pa.groups);
+    const int col0 = cg * pa.G;
+    const int L = pa.sp.L, G = pa.G, Lp = pa.Lp;
+    float2* a = smem;
+    float2* b = smem + (size_t)G * Lp;
+    for (int e = threadIdx.x; e < G * L; e += blockDim.x) {
+        const int i = e / G;
+        const int g = e - i * G;
+        const int col = col0 + g;
+        float2 v = make_float2(0.f, 0.f);
+        if (col < pa.M2) v = src_get(src, unit, (int)pass1_src_index(pa.M2, col, i));
+        a[g * Lp + i] = v;
+    }
+    __syncthreads();
+    run_stages(pa.sp, G, Lp, a, b);
+    float2* out = scratch + unit * scratch_stride;
+    for (int e = threadIdx.x; e < G * L; e += blockDim.x) {
+        const int i = e / G;
+        const int g = e - i * G;
+        const int col = col0 + g;
+        if (col < pa.M2) {
+            float2 v = a[g * Lp + i];
+            v = cmul(v, twiddle2(pa.twM, (long long)col * i));
+            out[pass1_dst_index(pa.M2, col, i)] = v;
+        }
+    }
+}
+
+// pass 2: rows.  CTA = G adjacent rows k1 of one unit; M2-point FFT over n2; store [k1 + M1*k2].
+__global__ void __launch_bounds__(kPassThreads) fft_pass2_kernel(PassArgs pa, SrcDesc src, DstDesc dst) {
+    extern __shared__ float2 smem[];
+    const long long unit = blockIdx.x / pa.groups;
+    const int rg = blockIdx.x - (int)(unit * pa.groups);
+    const int row0 = rg * pa.G;
+    const int L = pa.sp.L, G = pa.G, Lp = pa.Lp;
+    float2* a = smem;
+    float2* b = smem + (size_t)G * Lp;
+    for (int e = threadIdx.x; e < G * L; e += blockDim.x) {
+        const int g = e / L;
+        const int i = e - g * L;
+        const int row = row0 + g;
+        float2 v = make_float2(0.f, 0.f);
+        if (row < pa.M1) v = src_get(src, unit, (int)pass2_src_index(pa.M2, row, i));
+        a[g * Lp + i] = v;
+    }
+    __syncthreads();
+    run_stages(pa.sp, G, Lp, a, b);
+    for (int e = threadIdx.x; e < G * L; e += blockDim.x) {
+        const int i = e / G;
+        const int g = e - i * G;
+        const int row = row0 + g;
+        if (row < pa.M1) dst_put(dst, unit, (int)pass2_dst_index(pa.M1, row, i), a[g * Lp + i]);
+    }
+}
+
+int configure_kernels_once() {
+    static bool done = false;
+    if (done) return AA_OK;
+    AA_CUDA_TRY(cudaFuncSetAttribute(fft_pass1_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemHard));
+    AA_CUDA_TRY(cudaFuncSetAttribute(fft_pass2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemHard));
+    done = true;
+    return AA_OK;
+}
+
+int exec_direct(const C2CPlan* p, const SrcDesc& src, const DstDesc& dst, long long units, float2* scratch,
+                cudaStream_t stream) {
+    int rc = configure_kernels_once();
+    if (rc != AA_OK) return rc;
+    if (units <= 0) return AA_OK;
+    PassArgs pa{};
+    pa.M1 = p->M1;
+    pa.M2 = p->M2;
+    pa.twM = p->twM.dev;
+    SrcDesc src2 = src;
+    if (p->M1 > 1) {
+        AA_REQUIRE(scratch != nullptr, AA_ERR_WORKSPACE, "fft scratch missing");
+        pa.sp = p->s1.dev;
+        pa.G = p->G1;
+        pa.Lp = p->Lp1;
+        pa.groups = (p->M2 + p->G1 - 1) / p->G1;
+        long long grid = units * pa.groups;
+        AA_REQUIRE(grid < 2147483647LL, AA_ERR_INVALID_ARGUMENT, "fft grid too large");
+        fft_pass1_kernel<<<(unsigned)grid, kPassThreads, p->smem1, stream>>>(pa, src, scratch, (long long)p->M);
+        rc = launch_check("fft_pass1_kernel");
+        if (rc != AA_OK) return rc;
+        src2 = make_src_complex(scratch, p->M, p->M, 0);
+    }
+    pa.sp = p->s2.dev;
+    pa.G = p->G2;
+    pa.Lp = p->Lp2;
+    pa.groups = (p->M1 + p->G2 - 1) / p->G2;
+    long long grid = units * pa.groups;
+    AA_REQUIRE(grid < 2147483647LL, AA_ERR_INVALID_ARGUMENT, "fft grid too large");
+    fft_pass2_kernel<<<(unsigned)grid, kPassThreads, p->smem2, stream>>>(pa, src2, dst);
+    return launch_check("fft_pass2_kernel");
+}
+
+int build_direct(int M, C2CPlan* p) {
+    HostC2C h;
+    if (!host_direct_plan(M, &h)) {
+        set_error("no direct FFT plan for length %d", M);
+        return AA_ERR_UNSUPPORTED;
+    }
+    p->M = M;
+    p->bluestein = false;
+    p->M1 = h.M1;
+    p->M2 = h.M2;
+    int rc;
+    if (p->M1 > 1) {
+        if ((rc = upload_subplan(h.s1, &p->s1)) != AA_OK) return rc;
+        choose_group(p->M1, &p->G1, &p->Lp1, &p->smem1);
+        if ((rc = upload_two_level(h.twM, &p->twM)) != AA_OK) return rc;
+    }
+    if ((rc = upload_subplan(h.s2, &p->s2)) != AA_OK) return rc;
+    choose_group(p->M2, &p->G2, &p->Lp2, &p->smem2);
+    return AA_OK;
+}
+
+}  // namespace
+
+bool is_smooth(long long n) { return is_smooth_host(n); }
+
+int build_two_level(long long len, TwoLevelTable* out) {
+    HostTwoLevel h;
+    host_two_level(len, &h);
+    return upload_two_level(h, out);
+}
+
+void free_two_level(TwoLevelTable* t) {
+    if (t->d_hi) cudaFree(t->d_hi);
+    if (t->d_lo) cudaFree(t->d_lo);
+    t->d_hi = t->d_lo = nullptr;
+}
+
+void c2c_plan_destroy(C2CPlan* p) {
+    if (!p) return;
+    if (p->inner) c2c_plan_destroy(p->inner);
+    if (p->s1.d_tw) cudaFree(p->s1.d_tw);
+    if (p->s2.d_tw) cudaFree(p->s2.d_tw);
+    free_two_level(&p->twM);
+    if (p->d_chirp) cudaFree(p->d_chirp);
+    if (p->d_H) cudaFree(p->d_H);
+    delete p;
+}
+
+int c2c_plan_create(int M, C2CPlan** out) {
+    AA_REQUIRE(M >= 1, AA_ERR_INVALID_ARGUMENT, "fft length must be positive");
+    C2CPlan* p = new C2CPlan();
+    int rc = AA_OK;
+    if (direct_plan_possible(M)) {
+        rc = build_direct(M, p);
+        if (rc != AA_OK) {
+            c2c_plan_destroy(p);
+            return rc;
+        }
+        *out = p;
+        return AA_OK;
+    }
+    if (bluestein_length(M) > (long long)kMaxSubLen * kMaxSubLen) {
+        set_error("length %d too long for the Bluestein path", M);
+        c2c_plan_destroy(p);
+        return AA_ERR_TOO_LONG;
+    }
+    HostC2C h;
+    host_bluestein_tables(M, &h);
+    p->M = M;
+    p->bluestein = true;
+    const size_t P = (size_t)h.P;
+    rc = c2c_plan_create(h.P, &p->inner);
+    if (rc != AA_OK) {
+        c2c_plan_destroy(p);
+        return rc;
+    }
+    float2* d_hw = nullptr;
+    float2* d_scr = nullptr;
+    auto fail = [&](int code) {
+        if (d_hw) cudaFree(d_hw);
+        if (d_scr) cudaFree(d_scr);
+        c2c_plan_destroy(p);
+        return code;
+    };
+    if ((rc = upload(h.chirp, &p->d_chirp)) != AA_OK) return fail(rc);
+    if ((rc = upload(h.hw, &d_hw)) != AA_OK) return fail(rc);
+    if (cudaMalloc(&p->d_H, sizeof(float2) * P) != cudaSuccess) {
+        set_error("cudaMalloc failed building Bluestein tables for length %d", M);
+        return fail(AA_ERR_CUDA);
+    }
+    size_t scr = c2c_scratch_elems(p->inner, 1);
+    if (scr && cudaMalloc(&d_scr, sizeof(float2) * scr) != cudaSuccess) {
+        set_error("cudaMalloc failed building Bluestein tables for length %d", M);
+        return fail(AA_ERR_CUDA);
+    }
+    rc = c2c_exec(p->inner, make_src_complex(d_hw, (long long)P, (int)P, 0),
+                  make_dst_complex(p->d_H, (long long)P, (int)P, 0, 1.0f), 1, d_scr, 0);
+    if (rc != AA_OK) return fail(rc);
+    if (cudaStreamSynchronize(0) != cudaSuccess) {
+        set_error("Bluestein table transform failed");
+        return fail(AA_ERR_CUDA);
+    }
+    cudaFree(d_hw);
+    if (d_scr) cudaFree(d_scr);
+    *out = p;
+    return AA_OK;
+}
+
+size_t c2c_scratch_elems(const C2CPlan* p, long long units) {
+    if (!p->bluestein) return p->M1 > 1 ? (size_t)units * (size_t)p->M : 0;
+    size_t P = (size_t)p->inner->M;
+    return (size_t)units * P + c2c_scratch_elems(p->inner, units);
+}
+
+int c2c_exec(const C2CPlan* p, SrcDesc src, DstDesc dst, long long units, float2* scratch, cudaStream_t stream) {
+    if (!p->bluestein) return exec_direct(p, src, dst, units, scratch, stream);
+    const int P = p->inner->M;
+    float2* mid = scratch;
+    float2* inner_scratch = scratch + (size_t)units * (size_t)P;
+    // A = FFT_P(x * w, zero padded); mid = A * H
+    SrcDesc s1 = src;
+    s1.chirp = p->d_chirp;
+    s1.chirp_len = p->M;
+    DstDesc d1{};
+    d1.mode = DST_MUL_TABLE;
+    d1.base = mid;
+    d1.unit_stride = P;
+    d1.n_valid = P;
+    d1.scale1 = 1.0f;
+    d1.scale2 = 1.0f;
+    d1.table = p->d_H;
+    int rc = c2c_exec(p->inner, s1, d1, units, inner_scratch, stream);
+    if (rc != AA_OK) return rc;
+    // X = w * IFFT_P(mid), first M outputs; then the caller's conj / scale
+    SrcDesc s2 = make_src_complex(mid, P, P, 1);
+    DstDesc d2 = dst;
+    d2.conj1 = 1;
+    d2.scale1 = 1.0f / (float)P;
+    d2.chirp = p->d_chirp;
+    d2.conj2 = dst.conj1;
+    d2.scale2 = dst.scale1 * dst.scale2;
+    d2.n_valid = dst.n_valid < p->M ? dst.n_valid : p->M;
+    return c2c_exec(p->inner, s2, d2, units, inner_scratch, stream);
+}
+
+}  // namespace aa

@@ -1,0 +1,168 @@
+// Host-side FFT planning: factorisation, two-pass split, twiddle / chirp tables.
+// No CUDA runtime calls here - fft.cu uploads these tables; the CPU model check
+// (tests/csrc/fft_model_check.cu) uses them directly.
+#pragma once
+
+#include <math.h>
+#include <string.h>
+
+#include <vector>
+
+#include "fft_core.cuh"
+
+namespace aa {
+
+constexpr int kMaxSubLen = 4096;      // longest in-CTA transform
+constexpr int kSinglePassMax = 2048;  // M <= this: one pass
+constexpr int kTwoLevelShift = 10;
+
+struct HostSubPlan {
+    int L = 1;
+    int nst = 0;
+    int radix[kMaxStages] = {0};
+    std::vector<float2> tw;  // exp(-2 pi i m / L)
+};
+
+struct HostTwoLevel {
+    int shift = kTwoLevelShift;
+    std::vector<float2> hi, lo;
+};
+
+struct HostC2C {
+    int M = 0;
+    bool bluestein = false;
+    int M1 = 1, M2 = 1;
+    HostSubPlan s1, s2;
+    HostTwoLevel twM;
+    // Bluestein
+    int P = 0;
+    std::vector<float2> chirp;  // exp(-i pi n^2 / M)
+    std::vector<float2> hw;     // wrapped conj chirp, length P (its FFT is the table H)
+};
+
+inline bool is_smooth_host(long long n) {
+    if (n < 1) return false;
+    for (int p : {2, 3, 5, 7, 11, 13})
+        while (n % p == 0) n /= p;
+    return n == 1;
+}
+
+inline bool factor_radices(int L, int* radix, int* nst) {
+    int n = 0;
+    int rem = L;
+    int twos = 0;
+    while (rem % 2 == 0) {
+        rem /= 2;
+        ++twos;
+    }
+    // as many radix-8 stages as possible, the rest as radix 4 / 2 (2^4 -> 4,4)
+    while (twos >= 3 && twos != 4) {
+        radix[n++] = 8;
+        twos -= 3;
+    }
+    while (twos >= 2) {
+        radix[n++] = 4;
+        twos -= 2;
+    }
+    if (twos == 1) radix[n++] = 2;
+    for (int p : {3, 5, 7, 11, 13}) {
+        while (rem % p == 0) {
+            if (n >= kMaxStages) return false;
+            radix[n++] = p;
+            rem /= p;
+        }
+    }
+    if (rem != 1) return false;
+    *nst = n;
+    return true;
+}
+
+inline bool host_subplan(int L, HostSubPlan* sp) {
+    sp->L = L;
+    memset(sp->radix, 0, sizeof(sp->radix));
+    if (!factor_radices(L, sp->radix, &sp->nst)) return false;
+    sp->tw.resize((size_t)L);
+    for (int m = 0; m < L; ++m) {
+        double a = -2.0 * M_PI * (double)m / (double)L;
+        sp->tw[(size_t)m] = make_float2((float)cos(a), (float)sin(a));
+    }
+    return true;
+}
+
+inline void host_two_level(long long len, HostTwoLevel* t) {
+    const int R = 1 << t->shift;
+    long long nhi = (len + R - 1) / R + 1;
+    t->hi.resize((size_t)nhi);
+    t->lo.resize((size_t)R);
+    for (long long a = 0; a < nhi; ++a) {
+        double ang = -2.0 * M_PI * (double)((a * R) % len) / (double)len;
+        t->hi[(size_t)a] = make_float2((float)cos(ang), (float)sin(ang));
+    }
+    for (int b = 0; b < R; ++b) {
+        double ang = -2.0 * M_PI * (double)(b % len) / (double)len;
+        t->lo[(size_t)b] = make_float2((float)cos(ang), (float)sin(ang));
+    }
+}
+
+// true if a direct (mixed radix, <= 2 pass) plan exists for M
+inline bool direct_plan_possible(int M) {
+    if (!is_smooth_host(M)) return false;
+    if (M <= kSinglePassMax) return true;
+    for (int d = 1; (long long)d * d <= M; ++d)
+        if (M % d == 0 && M / d <= kMaxSubLen) return true;
+    return false;
+}
+
+inline bool host_direct_plan(int M, HostC2C* p) {
+    p->M = M;
+    p->bluestein = false;
+    int best1 = -1;
+    if (M <= kSinglePassMax) {
+        best1 = 1;
+    } else {
+        int best_cost = 1 << 30;
+        for (int d = 1; (long long)d * d <= M; ++d) {
+            if (M % d) continue;
+            int e = M / d;  // d <= e; rows (pass 2, contiguous) get the longer side
+            if (e > kMaxSubLen) continue;
+            if (e < best_cost) {
+                best_cost = e;
+                best1 = d;
+            }
+        }
+        if (best1 < 0) return false;
+    }
+    p->M1 = best1;
+    p->M2 = M / best1;
+    if (p->M1 > 1) {
+        if (!host_subplan(p->M1, &p->s1)) return false;
+        host_two_level(M, &p->twM);
+    }
+    return host_subplan(p->M2, &p->s2);
+}
+
+inline long long bluestein_length(int M) {
+    long long P = 1;
+    while (P < 2LL * M - 1) P <<= 1;
+    return P;
+}
+
+// Bluestein tables: X[k] = w[k] * sum_n (x[n] w[n]) conj(w)[k-n],  w[n] = exp(-i pi n^2 / M)
+inline void host_bluestein_tables(int M, HostC2C* p) {
+    p->M = M;
+    p->bluestein = true;
+    p->P = (int)bluestein_length(M);
+    p->chirp.resize((size_t)M);
+    p->hw.assign((size_t)p->P, make_float2(0.f, 0.f));
+    const unsigned long long twoM = 2ULL * (unsigned long long)M;
+    for (int n = 0; n < M; ++n) {
+        unsigned long long q = ((unsigned long long)n * (unsigned long long)n) % twoM;
+        double ang = -M_PI * (double)q / (double)M;
+        p->chirp[(size_t)n] = make_float2((float)cos(ang), (float)sin(ang));
+        float2 c = make_float2((float)cos(ang), (float)(-sin(ang)));
+        p->hw[(size_t)n] = c;
+        if (n > 0) p->hw[(size_t)(p->P - n)] = c;
+    }
+}
+
+}  // namespace aa

@@ -1,0 +1,34 @@
+// Internal launchers shared between translation units.
+#pragma once
+
+#include "aa_common.cuh"
+
+namespace aa {
+
+int launch_edc(const float* d_x, long long row_stride, const int* d_lengths, int uniform_len, int max_len, int n_rows,
+               const aa_decay_params* p, const int* d_start_in, int start_div, int min_samples, float* d_edc_out,
+               long long edc_stride, int* d_start_out, double* d_fits_out, double* d_rt60_out, double* d_early10_out,
+               int* d_status_out, cudaStream_t stream);
+
+int launch_peak(const float* d_x, long long row_stride, const int* d_lengths, int uniform_len, int n_rows, int* d_out,
+                cudaStream_t stream);
+
+int launch_csd(const float* d_x, long long row_stride, const int* d_lengths, int uniform_len, int n_rows,
+               const int* d_start_idx, const int* d_frame_idx, const int* d_n_slices, int max_slices,
+               const aa_csd_params* p, float* d_out, cudaStream_t stream);
+
+int launch_pcm16(const int16_t* d_pcm, long long pcm_stride, int n_files, int n_frames, int n_channels, int mode,
+                 float* d_out, long long out_stride, cudaStream_t stream);
+
+}  // namespace aa
+
+namespace aa {
+
+int launch_curve_fits(const float* d_curve, long long stride, const int* d_lengths, int uniform_len,
+                      const int* d_offsets, int n_rows, const aa_decay_params* p, double* d_fits_out,
+                      double* d_rt60_out, double* d_early10_out, cudaStream_t stream);
+
+int launch_box_smooth(const float* d_in, float* d_out, long long stride, const int* d_lengths, int uniform_len,
+                      const int* d_offsets, int n_rows, int window, double floor_db, cudaStream_t stream);
+
+}  // namespace aa

@@ -1,0 +1,439 @@
+"""Batched device engine: torch tensors as buffers, the C ABI for all arithmetic.
+
+Everything here is plumbing (allocation, host<->device copies, stream handles,
+plan / workspace caches).  The analysis itself happens in
+libaudio_analysis_b200.so; there is no torch arithmetic and no CPU path.
+
+Rows = analysed channels (the reference's 1-D `samples`).  A `Rows` object is a
+device tensor [B, stride] of float32 with per-row lengths; stride % 4 == 0 so
+every row starts 16-byte aligned.
+"""
+
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass
+from typing import Dict, List, Optional, Sequence, Tuple, Union
+
+import numpy as np
+import torch
+
+from . import _native as nat
+
+ArrayLike = Union[np.ndarray, torch.Tensor, Sequence[np.ndarray]]
+
+
+def _device(device=None) -> torch.device:
+    nat.require_device()
+    if device is None:
+        return torch.device("cuda", torch.cuda.current_device())
+    return torch.device(device)
+
+
+def _stream_ptr() -> C.c_void_p:
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _ptr(t: Optional[torch.Tensor]) -> C.c_void_p:
+    return C.c_void_p(0 if t is None else t.data_ptr())
+
+
+def round_up4(n: int) -> int:
+    return (int(n) + 3) & ~3
+
+
+@dataclass
+class Rows:
+    """Device-resident batch of channels."""
+
+    x: torch.Tensor                  # [B, stride] float32, cuda
+    lengths: Optional[torch.Tensor]  # [B] int32 cuda, or None when every row has `n` samples
+    n: int                           # maximum row length
+    host_lengths: np.ndarray         # [B] int64 (host copy)
+
+    @property
+    def n_rows(self) -> int:
+        return int(self.x.shape[0])
+
+    @property
+    def stride(self) -> int:
+        return int(self.x.stride(0))
+
+    @property
+    def uniform(self) -> bool:
+        return self.lengths is None
+
+
+def make_rows(data: ArrayLike, device=None, lengths: Optional[Sequence[int]] = None) -> Rows:
+    """Stage channels on the device.
+
+    Accepts a 2-D float32 numpy array / torch tensor [B, N] (CPU, ideally pinned, or
+    CUDA) or a list of 1-D arrays of different lengths (zero padded to a common pitch).
+    Inputs are never modified.
+    """
+    dev = _device(device)
+    if isinstance(data, torch.Tensor):
+        t = data
+        if t.dim() == 1:
+            t = t.unsqueeze(0)
+        if t.dim() != 2:
+            raise ValueError("expected [rows, samples]")
+        if t.dtype != torch.float32:
+            t = t.float()
+        b, n = int(t.shape[0]), int(t.shape[1])
+        if t.is_cuda:
+            dev = t.device
+            ok = t.stride(1) == 1 and t.stride(0) % 4 == 0 and t.stride(0) >= n and t.data_ptr() % 16 == 0
+            if ok:
+                x = t
+            else:
+                x = torch.zeros((b, max(4, round_up4(n))), dtype=torch.float32, device=dev)
+                x[:, :n].copy_(t)
+        else:
+            stride = max(4, round_up4(n))
+            if stride == n and t.is_contiguous():
+                x = t.to(dev, non_blocking=True)
+            else:
+                x = torch.zeros((b, stride), dtype=torch.float32, device=dev)
+                x[:, :n].copy_(t, non_blocking=True)
+        hl = np.full(b, n, dtype=np.int64) if lengths is None else np.asarray(lengths, dtype=np.int64)
+        return _finish_rows(x, n, hl, dev)
+    if isinstance(data, np.ndarray) and data.ndim == 2:
+        arr = np.ascontiguousarray(data, dtype=np.float32)
+        b, n = arr.shape
+        stride = max(4, round_up4(n))
+        if stride == n:
+            x = torch.from_numpy(arr).to(dev, non_blocking=False)
+        else:
+            x = torch.zeros((b, stride), dtype=torch.float32, device=dev)
+            x[:, :n].copy_(torch.from_numpy(arr))
+        hl = np.full(b, n, dtype=np.int64) if lengths is None else np.asarray(lengths, dtype=np.int64)
+        return _finish_rows(x, n, hl, dev)
+    # ragged list of 1-D arrays
+    chans = [np.asarray(c, dtype=np.float32) for c in data]
+    for c in chans:
+        if c.ndim != 1:
+            raise ValueError("expects 1D mono arrays")
+    b = len(chans)
+    n = max((c.size for c in chans), default=0)
+    stride = max(4, round_up4(n))
+    host = torch.zeros((b, stride), dtype=torch.float32)
+    hv = host.numpy()
+    for i, c in enumerate(chans):
+        hv[i, : c.size] = c
+    x = host.to(dev)
+    hl = np.array([c.size for c in chans], dtype=np.int64)
+    return _finish_rows(x, n, hl, dev)
+
+
+def _finish_rows(x: torch.Tensor, n: int, hl: np.ndarray, dev: torch.device) -> Rows:
+    if n > nat.AA_MAX_ROW_SAMPLES:
+        raise ValueError(f"rows longer than {nat.AA_MAX_ROW_SAMPLES} samples are not supported")
+    if hl.size and int(hl.max(initial=0)) > n:
+        raise ValueError("a row length exceeds the buffer width")
+    uniform = bool(hl.size == 0 or np.all(hl == n))
+    lengths = None if uniform else torch.from_numpy(hl.astype(np.int32)).to(x.device)
+    return Rows(x=x, lengths=lengths, n=int(n), host_lengths=hl)
+
+
+# --------------------------------------------------------------------------------------
+# decay
+# --------------------------------------------------------------------------------------
+
+
+@dataclass
+class DecayOut:
+    start: torch.Tensor          # [B] int32
+    fits: torch.Tensor           # [B, 3, 8] float64 (rows follow `fit_ranges` order)
+    early10: torch.Tensor        # [B] float64, NaN = None
+    status: torch.Tensor         # [B] int32
+    edc_db: Optional[torch.Tensor]  # [B, stride] float32, entry j = curve at absolute sample j (valid j >= start)
+
+
+def decay_params(sample_rate_hz: int, trim_to_peak: bool, ignore_leading_seconds: float, edc_floor_db: float,
+                 edc_epsilon: float, fit_lower_limit_db: float, fit_ranges: Sequence[Tuple[float, float]],
+                 want_early10: bool = True) -> nat.DecayParams:
+    if len(fit_ranges) > nat.AA_MAX_FITS:
+        raise ValueError("at most 3 fit ranges")
+    p = nat.DecayParams()
+    p.sample_rate_hz = int(sample_rate_hz)
+    p.trim_to_peak = 1 if trim_to_peak else 0
+    ign = 0
+    if ignore_leading_seconds > 0.0:  # analyse/decay.py:140-141
+        ign = max(0, int(round(float(ignore_leading_seconds) * float(sample_rate_hz))))
+    p.ignore_leading_samples = min(ign, nat.AA_MAX_ROW_SAMPLES)
+    p.smoothing_window = 0
+    p.edc_floor_db = float(edc_floor_db)
+    p.edc_epsilon = float(edc_epsilon)
+    p.fit_lower_limit_db = float(fit_lower_limit_db)
+    p.n_fits = len(fit_ranges)
+    p.want_early10 = 1 if want_early10 else 0
+    for i, (hi, lo) in enumerate(fit_ranges):
+        hi, lo = float(hi), float(lo)
+        if lo > hi:  # analyse/decay.py:216-217
+            raise ValueError("range_db should be (higher_db, lower_db), e.g. (-5, -25).")
+        p.fit_hi_db[i] = hi
+        p.fit_lo_db[i] = lo
+    return p
+
+
+def decay(rows: Rows, params: nat.DecayParams, want_edc: bool = True,
+          start_in: Optional[torch.Tensor] = None) -> DecayOut:
+    lib = nat.load()
+    dev = rows.x.device
+    b = rows.n_rows
+    start = torch.empty(b, dtype=torch.int32, device=dev)
+    fits = torch.empty((b, nat.AA_MAX_FITS, nat.AA_FIT_COLS), dtype=torch.float64, device=dev)
+    early = torch.empty(b, dtype=torch.float64, device=dev)
+    status = torch.empty(b, dtype=torch.int32, device=dev)
+    edc = torch.empty((b, rows.stride), dtype=torch.float32, device=dev) if want_edc else None
+    with torch.cuda.device(dev):
+        nat.check(lib.aa_decay_batch(
+            _ptr(rows.x), rows.stride, _ptr(rows.lengths), rows.n, b, C.byref(params), _ptr(start_in), _ptr(edc),
+            rows.stride if want_edc else 0, _ptr(start), _ptr(fits), _ptr(early), _ptr(status), _stream_ptr()))
+    return DecayOut(start=start, fits=fits, early10=early, status=status, edc_db=edc)
+
+
+def curve_fits(curve: torch.Tensor, lengths: Optional[torch.Tensor], uniform_len: int,
+               offsets: Optional[torch.Tensor], params: nat.DecayParams) -> Tuple[torch.Tensor, torch.Tensor]:
+    """Crossings + fits on caller-supplied dB curves [B, stride] -> (fits [B,3,8], early10 [B])."""
+    lib = nat.load()
+    dev = curve.device
+    b = int(curve.shape[0])
+    fits = torch.empty((b, nat.AA_MAX_FITS, nat.AA_FIT_COLS), dtype=torch.float64, device=dev)
+    early = torch.empty(b, dtype=torch.float64, device=dev)
+    with torch.cuda.device(dev):
+        nat.check(lib.aa_curve_fits_batch(_ptr(curve), int(curve.stride(0)), _ptr(lengths), int(uniform_len),
+                                          _ptr(offsets), b, C.byref(params), _ptr(fits), _ptr(early), _stream_ptr()))
+    return fits, early
+
+
+def box_smooth_db(curve: torch.Tensor, lengths: Optional[torch.Tensor], uniform_len: int,
+                  offsets: Optional[torch.Tensor], window: int, floor_db: float) -> torch.Tensor:
+    """np.convolve(curve, ones(w)/w, "same") then the floor, per row (analyse/decay.py:161-167)."""
+    lib = nat.load()
+    dev = curve.device
+    out = torch.empty_like(curve)
+    with torch.cuda.device(dev):
+        nat.check(lib.aa_box_smooth_db_batch(_ptr(curve), _ptr(out), int(curve.stride(0)), _ptr(lengths),
+                                             int(uniform_len), _ptr(offsets), int(curve.shape[0]), int(window),
+                                             float(floor_db), _stream_ptr()))
+    return out
+
+
+def decay_smoothed(rows: Rows, params: nat.DecayParams, window: int) -> DecayOut:
+    """decay() with edc_smoothing_window_samples > 1: raw dB curve -> box filter -> generic fits."""
+    raw = nat.DecayParams()
+    C.memmove(C.byref(raw), C.byref(params), C.sizeof(nat.DecayParams))
+    raw.n_fits = 0
+    raw.want_early10 = 0
+    raw.edc_floor_db = float("-inf")
+    first = decay(rows, raw, want_edc=True)
+    smooth = box_smooth_db(first.edc_db, rows.lengths, rows.n, first.start, window, params.edc_floor_db)
+    fits, early = curve_fits(smooth, rows.lengths, rows.n, first.start, params)
+    return DecayOut(start=first.start, fits=fits, early10=early, status=first.status, edc_db=smooth)
+
+
+def peak_index(rows: Rows) -> torch.Tensor:
+    lib = nat.load()
+    dev = rows.x.device
+    out = torch.empty(rows.n_rows, dtype=torch.int32, device=dev)
+    lengths = rows.lengths
+    if lengths is None:
+        lengths = torch.full((rows.n_rows,), rows.n, dtype=torch.int32, device=dev)
+    with torch.cuda.device(dev):
+        nat.check(lib.aa_peak_index_batch(_ptr(rows.x), rows.stride, _ptr(lengths), rows.n_rows, _ptr(out),
+                                          _stream_ptr()))
+    return out
+
+
+# --------------------------------------------------------------------------------------
+# rt60bands
+# --------------------------------------------------------------------------------------
+
+
+class _BandsPlan:
+    def __init__(self, n: int):
+        lib = nat.load()
+        h = C.c_void_p()
+        nat.check(lib.aa_bands_plan_create(int(n), C.byref(h)))
+        self.handle = h
+        self.n = int(n)
+        self.kind = int(lib.aa_bands_plan_kind(h))
+
+    def close(self):
+        if self.handle:
+            nat.load().aa_bands_plan_destroy(self.handle)
+            self.handle = None
+
+
+_bands_plans: Dict[Tuple[int, int], _BandsPlan] = {}
+_workspaces: Dict[int, torch.Tensor] = {}
+DEFAULT_WORKSPACE_BYTES = 6 << 30
+
+
+def bands_plan(n: int, dev: torch.device) -> _BandsPlan:
+    key = (dev.index if dev.index is not None else torch.cuda.current_device(), int(n))
+    plan = _bands_plans.get(key)
+    if plan is None:
+        with torch.cuda.device(dev):
+            plan = _BandsPlan(n)
+        _bands_plans[key] = plan
+    return plan
+
+
+def workspace(nbytes: int, dev: torch.device) -> torch.Tensor:
+    key = dev.index if dev.index is not None else torch.cuda.current_device()
+    ws = _workspaces.get(key)
+    if ws is None or ws.numel() < nbytes:
+        _workspaces[key] = None  # release before growing
+        ws = torch.empty(int(nbytes), dtype=torch.uint8, device=dev)
+        _workspaces[key] = ws
+    return ws
+
+
+def release_caches() -> None:
+    for p in _bands_plans.values():
+        p.close()
+    _bands_plans.clear()
+    for p in _deconv_plans.values():
+        p.close()
+    _deconv_plans.clear()
+    _workspaces.clear()
+
+
+def band_array(bands: Sequence[Tuple[int, Optional[float], Optional[float]]]):
+    """(kind, low_edge, high_edge) triples -> ctypes aa_band array."""
+    if not 1 <= len(bands) <= nat.AA_MAX_BANDS:
+        raise ValueError(f"between 1 and {nat.AA_MAX_BANDS} bands")
+    arr = (nat.Band * len(bands))()
+    for i, (kind, lo, hi) in enumerate(bands):
+        arr[i].kind = int(kind)
+        arr[i].low_edge_hz = 0.0 if lo is None else float(lo)
+        arr[i].high_edge_hz = 0.0 if hi is None else float(hi)
+    return arr
+
+
+def rt60bands(rows: Rows, start_idx: torch.Tensor, bands: Sequence[Tuple[int, Optional[float], Optional[float]]],
+              transition_width_octaves: float, params: nat.DecayParams, want_band_signals: bool = False,
+              workspace_bytes: Optional[int] = None):
+    """RT60 table [B, n_bands, 3] (float64, NaN = None; columns follow params' fit order)."""
+    if not rows.uniform:
+        raise ValueError("rt60bands needs rows of equal length (group channels by length)")
+    lib = nat.load()
+    dev = rows.x.device
+    b, nb = rows.n_rows, len(bands)
+    plan = bands_plan(rows.n, dev)
+    one = int(lib.aa_bands_workspace_bytes(plan.handle, 1, nb))
+    budget = int(workspace_bytes or DEFAULT_WORKSPACE_BYTES)
+    if budget < one:
+        budget = one
+    allrows = int(lib.aa_bands_workspace_bytes(plan.handle, b, nb))
+    ws = workspace(min(budget, allrows), dev)
+    metrics = torch.empty((b, nb, nat.AA_MAX_FITS), dtype=torch.float64, device=dev)
+    sig = torch.empty((b, nb, rows.n), dtype=torch.float32, device=dev) if want_band_signals else None
+    barr = band_array(bands)
+    with torch.cuda.device(dev):
+        nat.check(lib.aa_rt60bands_batch(
+            plan.handle, _ptr(rows.x), rows.stride, b, _ptr(start_idx), barr, nb, float(transition_width_octaves),
+            C.byref(params), _ptr(metrics), _ptr(sig), _ptr(ws), ws.numel(), _stream_ptr()))
+    return metrics, sig
+
+
+# --------------------------------------------------------------------------------------
+# waterfall / CSD
+# --------------------------------------------------------------------------------------
+
+
+def csd_params(n_fft: int, hop_length: int, use_hann_window: bool, bin_lo: int, n_bins: int, db_reference: str,
+               floor_db: float, dynamic_range_db: float) -> nat.CsdParams:
+    p = nat.CsdParams()
+    p.n_fft = int(n_fft)
+    p.hop_length = int(hop_length)
+    p.use_hann_window = 1 if use_hann_window else 0
+    p.bin_lo = int(bin_lo)
+    p.n_bins = int(n_bins)
+    ref = str(db_reference).lower()
+    p.db_reference = {"slice_max": nat.AA_DBREF_SLICE_MAX, "none": nat.AA_DBREF_NONE}.get(ref, nat.AA_DBREF_GLOBAL_MAX)
+    p.floor_db = float(floor_db)
+    p.dynamic_range_db = float(max(10.0, dynamic_range_db))  # analyse/waterfall.py:338
+    return p
+
+
+def csd(rows: Rows, start_idx: torch.Tensor, frame_idx: torch.Tensor, n_slices: torch.Tensor,
+        params: nat.CsdParams) -> torch.Tensor:
+    """Relative-dB slices [B, max_slices, n_bins] float32."""
+    lib = nat.load()
+    dev = rows.x.device
+    b = rows.n_rows
+    max_slices = int(frame_idx.shape[1])
+    out = torch.zeros((b, max_slices, int(params.n_bins)), dtype=torch.float32, device=dev)
+    with torch.cuda.device(dev):
+        nat.check(lib.aa_csd_batch(_ptr(rows.x), rows.stride, _ptr(rows.lengths), rows.n, b, _ptr(start_idx),
+                                   _ptr(frame_idx), _ptr(n_slices), max_slices, C.byref(params), _ptr(out),
+                                   _stream_ptr()))
+    return out
+
+
+# --------------------------------------------------------------------------------------
+# PCM16 decode and deconvolution
+# --------------------------------------------------------------------------------------
+
+
+def pcm16_to_rows(pcm: torch.Tensor, n_frames: int, n_channels: int, mono_downmix: bool) -> Rows:
+    """pcm: [files, n_frames*n_channels] int16 on the device -> float32 rows (io.py:46-95)."""
+    lib = nat.load()
+    dev = pcm.device
+    files = int(pcm.shape[0])
+    per_file = 1 if (mono_downmix or n_channels == 1) else n_channels
+    stride = round_up4(n_frames)
+    out = torch.zeros((files * per_file, stride), dtype=torch.float32, device=dev)
+    with torch.cuda.device(dev):
+        nat.check(lib.aa_pcm16_to_float_batch(_ptr(pcm), int(pcm.stride(0)), files, int(n_frames), int(n_channels),
+                                              1 if (mono_downmix and n_channels == 2) else 0, _ptr(out), stride,
+                                              _stream_ptr()))
+    hl = np.full(files * per_file, n_frames, dtype=np.int64)
+    return _finish_rows(out, int(n_frames), hl, dev)
+
+
+class _DeconvPlan:
+    def __init__(self, n_fft: int):
+        lib = nat.load()
+        h = C.c_void_p()
+        nat.check(lib.aa_deconv_plan_create(int(n_fft), C.byref(h)))
+        self.handle = h
+        self.n_fft = int(n_fft)
+
+    def close(self):
+        if self.handle:
+            nat.load().aa_deconv_plan_destroy(self.handle)
+            self.handle = None
+
+
+_deconv_plans: Dict[Tuple[int, int], _DeconvPlan] = {}
+
+
+def deconvolve(rec: Rows, sweep: torch.Tensor, n_fft: int, regularization_relative: float, remove_dc: bool,
+               target_peak: float, norm_group: int, n_out: int) -> torch.Tensor:
+    """Impulse responses [B, round_up4(n_out)] float32 (analyse/deconvolve.py:124-193)."""
+    if not rec.uniform:
+        raise ValueError("deconvolve needs recordings of equal length")
+    lib = nat.load()
+    dev = rec.x.device
+    key = (dev.index if dev.index is not None else torch.cuda.current_device(), int(n_fft))
+    plan = _deconv_plans.get(key)
+    if plan is None:
+        with torch.cuda.device(dev):
+            plan = _DeconvPlan(n_fft)
+        _deconv_plans[key] = plan
+    b = rec.n_rows
+    ws = workspace(int(lib.aa_deconv_workspace_bytes(plan.handle, b)), dev)
+    stride = round_up4(n_out)
+    out = torch.zeros((b, stride), dtype=torch.float32, device=dev)
+    sweep = sweep.to(dev, dtype=torch.float32).contiguous()
+    with torch.cuda.device(dev):
+        nat.check(lib.aa_deconvolve_batch(plan.handle, _ptr(sweep), int(sweep.numel()), _ptr(rec.x), rec.stride,
+                                          rec.n, b, float(regularization_relative), 1 if remove_dc else 0,
+                                          float(target_peak), int(norm_group), int(n_out), _ptr(out), stride,
+                                          _ptr(ws), ws.numel(), _stream_ptr()))
+    return out

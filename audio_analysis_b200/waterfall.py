@@ -1,0 +1,469 @@
+"""Waterfall / cumulative spectral decay slices on the B200 path.
+
+Drop-in mirror of the reference's `analyse/waterfall.py` API.  Host side: which
+STFT frames become slices (a function of the frame count and the settings only,
+reference waterfall.py:233-286) and which rfft bins are kept (:300-308).  Device
+side (`aa_csd_batch`): windowed real FFT of the selected frames, magnitude in dB,
+crop, reference level and clip (reference :188-230, :309, :328-339).  The
+reference computes every frame and keeps <= num_slices of them; the result is
+the same because normalisation only looks at the selected slices (:335).
+"""
+
+from __future__ import annotations
+
+from dataclasses import dataclass
+from pathlib import Path
+from typing import Dict, List, Optional, Sequence, Tuple
+
+import numpy as np
+
+from . import engine
+from . import _native as nat
+from .io import get_analysis_channels, load_wav_file
+
+
+@dataclass(frozen=True)
+class WaterfallAnalysisSettings:
+    use_mono_downmix_for_stereo: bool = False
+    trim_to_peak: bool = True
+    ignore_leading_seconds: float = 0.0
+    analysis_duration_seconds: Optional[float] = None
+    n_fft: int = 4096
+    hop_length: int = 512
+    use_hann_window: bool = True
+    f_min_hz: float = 20.0
+    f_max_hz: float = 20000.0
+    slice_mode: str = "auto"  # "auto" | "uniform_time" | "uniform_frames"
+    num_slices: int = 18
+    slice_spacing_seconds: float = 0.05
+    start_time_seconds: float = 0.0
+    end_time_seconds: Optional[float] = None
+    db_reference: str = "global_max"  # "global_max" | "slice_max"
+    smoothing_log_bins: int = 0
+    log_bins_per_octave: int = 96
+    dynamic_range_db: float = 80.0
+    floor_db: float = -120.0
+
+
+@dataclass(frozen=True)
+class WaterfallPlotSettings:
+    style: str = "3d"  # "3d" | "2d"
+    secondary_channel_alpha: float = 0.7
+    elev_deg: float = 30.0
+    azim_deg: float = -60.0
+    ridge_offset_db: float = 6.0
+    zlim_db: Optional[Tuple[float, float]] = None
+
+
+@dataclass(frozen=True)
+class ChannelWaterfallResult:
+    channel_name: str
+    sample_rate_hz: int
+    analysis_start_sample_index: int
+    analysis_length_samples: int
+    slice_times_seconds: np.ndarray      # (S,)
+    frequency_hz: np.ndarray             # (F,)
+    slice_magnitude_rel_db: np.ndarray   # (S, F) in [-dynamic_range_db, 0]
+
+
+_TOO_SHORT = "Not enough samples after trimming/selection for waterfall (need at least n_fft)."
+_TOO_FEW_SLICES = "Not enough slices selected for waterfall (increase duration or num_slices)."
+
+
+# --------------------------------------------------------------------------------------
+# host-side selection logic
+# --------------------------------------------------------------------------------------
+
+
+def frame_times_seconds(num_frames: int, hop_length: int, sample_rate_hz: int) -> np.ndarray:
+    """Window-start time of every STFT frame, float32 like the reference (waterfall.py:229)."""
+    return (np.arange(int(num_frames), dtype=np.float32) * float(hop_length) / float(sample_rate_hz)).astype(np.float32)
+
+
+def _select_slice_frame_indices(frame_times: np.ndarray, settings: WaterfallAnalysisSettings) -> np.ndarray:
+    """Frame index of every slice, ordered and unique (reference waterfall.py:233-286)."""
+    if frame_times.size == 0:
+        return np.zeros((0,), dtype=np.int32)
+    t_begin = float(max(0.0, settings.start_time_seconds))
+    last = float(frame_times[-1])
+    t_end = last if settings.end_time_seconds is None else float(settings.end_time_seconds)
+    if t_end <= t_begin:
+        t_end = last
+    usable = np.nonzero((frame_times >= t_begin) & (frame_times <= t_end))[0]
+    if usable.size == 0:
+        return np.zeros((0,), dtype=np.int32)
+    first, final = int(usable[0]), int(usable[-1])
+    mode = str(settings.slice_mode).lower()
+    if mode == "uniform_frames":
+        return np.unique(np.linspace(first, final, int(max(1, settings.num_slices)), dtype=np.int32))
+    if mode == "uniform_time":
+        spacing = float(max(1e-4, settings.slice_spacing_seconds))
+        wanted = np.arange(t_begin, t_end + 1e-9, spacing, dtype=np.float64)
+    else:
+        wanted = np.linspace(t_begin, t_end, int(max(2, settings.num_slices)), dtype=np.float64)
+    nearest = [int(np.argmin(np.abs(frame_times - float(t)))) for t in wanted]
+    picked = [j for j in nearest if first <= j <= final]
+    if mode == "uniform_time" and not picked:
+        picked = [first, final]
+    return np.unique(np.array(picked, dtype=np.int32))
+
+
+def frequency_selection(settings: WaterfallAnalysisSettings, sample_rate_hz: int) -> Tuple[int, np.ndarray]:
+    """(first kept rfft bin, kept frequencies float32) - reference waterfall.py:213, :300-308."""
+    freq = np.fft.rfftfreq(int(settings.n_fft), d=1.0 / float(sample_rate_hz)).astype(np.float32)
+    nyquist = float(freq[-1]) if freq.size else 0.0
+    lo = float(np.clip(settings.f_min_hz, 1.0, nyquist))
+    hi = float(np.clip(settings.f_max_hz, lo, nyquist))
+    keep = np.nonzero((freq >= lo) & (freq <= hi))[0]
+    if keep.size == 0:
+        raise ValueError("Waterfall frequency selection is empty (check f_min_hz/f_max_hz).")
+    return int(keep[0]), freq[keep[0]: keep[-1] + 1].astype(np.float32)
+
+
+def analysed_span(length: int, peak: int, settings: WaterfallAnalysisSettings, sample_rate_hz: int) -> Tuple[int, int]:
+    """(start index, analysed length) after trim / ignore / duration (reference waterfall.py:355-372)."""
+    start = int(peak) if settings.trim_to_peak else 0
+    remaining = int(length) - start
+    if settings.ignore_leading_seconds > 0.0:
+        skip = int(round(float(settings.ignore_leading_seconds) * float(sample_rate_hz)))
+        skip = max(0, min(skip, remaining))
+        start += skip
+        remaining -= skip
+    if settings.analysis_duration_seconds is not None:
+        keep = int(round(float(settings.analysis_duration_seconds) * float(sample_rate_hz)))
+        remaining = max(0, min(keep, remaining))
+    return start, remaining
+
+
+# --------------------------------------------------------------------------------------
+# optional log-frequency smoothing of finished slices (reference waterfall.py:132-185); off by
+# default.  It post-processes the S x F dB table (<= 18 x 1705 values per channel), so it runs on
+# the host on the kernel's raw dB output and the normalisation is redone afterwards.
+# --------------------------------------------------------------------------------------
+
+
+def _moving_average_1d(values: np.ndarray, window: int) -> np.ndarray:
+    if window <= 1:
+        return values.astype(np.float32, copy=False)
+    taps = np.full(int(window), 1.0 / float(int(window)), dtype=np.float64)
+    return np.convolve(values.astype(np.float64), taps, mode="same").astype(np.float32)
+
+
+def _smooth_mag_db_log_frequency(frequency_hz: np.ndarray, magnitude_db: np.ndarray, f_min_hz: float, f_max_hz: float,
+                                 smoothing_log_bins: int, log_bins_per_octave: int) -> np.ndarray:
+    if smoothing_log_bins <= 1:
+        return magnitude_db.astype(np.float32, copy=False)
+    f = frequency_hz.astype(np.float64, copy=False)
+    m = magnitude_db.astype(np.float64, copy=False)
+    lo = float(max(1.0, f_min_hz))
+    hi = float(max(lo, f_max_hz))
+    inside = (f >= lo) & (f <= hi)
+    if not np.any(inside):
+        return magnitude_db.astype(np.float32, copy=False)
+    f_in, m_in = f[inside], m[inside]
+    a, b = float(np.log2(f_in[0])), float(np.log2(f_in[-1]))
+    per_octave = int(max(16, log_bins_per_octave))
+    count = int(max(8, np.ceil((b - a) * per_octave))) + 1
+    grid = 2.0 ** np.linspace(a, b, count, dtype=np.float64)
+    on_grid = np.interp(grid, f_in, m_in)
+    on_grid = _moving_average_1d(on_grid.astype(np.float32), int(smoothing_log_bins)).astype(np.float64)
+    result = magnitude_db.astype(np.float32, copy=True)
+    result[inside] = np.interp(f_in, grid, on_grid).astype(np.float32)
+    return result
+
+
+def _normalise_slices(raw_db: np.ndarray, settings: WaterfallAnalysisSettings) -> np.ndarray:
+    """Reference level and clip on the host (only used after the optional smoothing), waterfall.py:328-339."""
+    if str(settings.db_reference).lower() == "slice_max":
+        rel = raw_db - np.max(raw_db, axis=1, keepdims=True)
+    else:
+        rel = raw_db - float(np.max(raw_db))
+    dyn = float(max(10.0, settings.dynamic_range_db))
+    return np.clip(rel, -dyn, 0.0).astype(np.float32)
+
+
+# --------------------------------------------------------------------------------------
+# batched analysis
+# --------------------------------------------------------------------------------------
+
+
+@dataclass
+class WaterfallPlan:
+    """Per-row selection for a batch: analysis start / length and the slice frames."""
+
+    start: np.ndarray        # [B] int32
+    length: np.ndarray       # [B] int64 analysed samples
+    frames: np.ndarray       # [B, S_max] int32
+    n_slices: np.ndarray     # [B] int32
+    bin_lo: int
+    freq: np.ndarray         # [F] float32
+    hop_length: int
+    sample_rate_hz: int
+
+    def slice_times(self, row: int) -> np.ndarray:
+        """Window-start times of the row's slices, float32 like the reference (waterfall.py:229, :400)."""
+        idx = self.frames[row, : int(self.n_slices[row])]
+        return (idx.astype(np.float32) * float(self.hop_length) / float(self.sample_rate_hz)).astype(np.float32)
+
+
+_slice_tables: Dict[tuple, Tuple[np.ndarray, np.ndarray]] = {}
+
+
+def slice_table(settings: WaterfallAnalysisSettings, sample_rate_hz: int, max_frames: int):
+    """frames[t] / counts[t] for every possible frame count t in [0, max_frames].
+
+    The selected slices depend only on the number of STFT frames and the settings
+    (reference waterfall.py:233-286), so the whole mapping is tabulated once per
+    (settings, sample rate) and looked up per row - on the device for batches.
+    """
+    key = (settings.slice_mode, int(settings.num_slices), float(settings.slice_spacing_seconds),
+           float(settings.start_time_seconds), settings.end_time_seconds, int(settings.hop_length),
+           int(sample_rate_hz))
+    have = _slice_tables.get(key)
+    if have is not None and have[0].shape[0] > max_frames:
+        return have
+    rows: List[np.ndarray] = [np.zeros((0,), dtype=np.int32)]
+    for t in range(1, int(max_frames) + 1):
+        rows.append(_select_slice_frame_indices(frame_times_seconds(t, settings.hop_length, sample_rate_hz), settings))
+    width = max(1, max(int(r.size) for r in rows))
+    if width > nat.AA_MAX_SLICES:
+        raise ValueError(f"more than {nat.AA_MAX_SLICES} slices selected")
+    frames = np.zeros((len(rows), width), dtype=np.int32)
+    counts = np.zeros(len(rows), dtype=np.int32)
+    for t, r in enumerate(rows):
+        frames[t, : r.size] = r
+        counts[t] = r.size
+    _slice_tables[key] = (frames, counts)
+    return frames, counts
+
+
+def run_waterfall(rows: engine.Rows, sample_rate_hz: int, settings: WaterfallAnalysisSettings, peaks=None,
+                  validate: bool = True):
+    """Device-level call: returns (slices tensor [B, S_max, F], WaterfallPlan).
+
+    `peaks` (device int32 [B]) may be supplied when the peak index is already known from the decay
+    kernel, which saves the 4 B/sample arg-max pass.  Start / span / slice lookup are
+    integer bookkeeping on the device, so the CSD kernel is enqueued without a host round trip; the
+    host copy of the plan (and the reference's ValueErrors) follows after the launch.
+    """
+    import torch
+
+    n_fft, hop = int(settings.n_fft), int(settings.hop_length)
+    if n_fft <= 0 or hop <= 0:
+        raise ValueError("n_fft and hop_length must be positive.")
+    bin_lo, freq = frequency_selection(settings, sample_rate_hz)
+    dev = rows.x.device
+    b = rows.n_rows
+    lengths = rows.lengths if rows.lengths is not None else torch.full((b,), rows.n, dtype=torch.int32, device=dev)
+    if settings.trim_to_peak:
+        start = (peaks if peaks is not None else engine.peak_index(rows)).to(torch.int32)
+    else:
+        start = torch.zeros(b, dtype=torch.int32, device=dev)
+    remaining = lengths - start
+    if settings.ignore_leading_seconds > 0.0:  # reference waterfall.py:363-367
+        skip = int(round(float(settings.ignore_leading_seconds) * float(sample_rate_hz)))
+        skip_t = torch.clamp(torch.full_like(remaining, max(0, skip)), max=remaining)
+        start = start + skip_t
+        remaining = remaining - skip_t
+    if settings.analysis_duration_seconds is not None:  # reference waterfall.py:369-372
+        keep = int(round(float(settings.analysis_duration_seconds) * float(sample_rate_hz)))
+        remaining = torch.clamp(torch.full_like(remaining, max(0, keep)), max=remaining)
+    max_frames = max(0, 1 + (rows.n - n_fft) // hop)
+    table, counts = slice_table(settings, sample_rate_hz, max_frames)
+    n_frames = torch.where(remaining >= n_fft, 1 + torch.div(remaining - n_fft, hop, rounding_mode="floor"),
+                           torch.zeros_like(remaining)).to(torch.int64)
+    table_d = torch.from_numpy(table).to(dev)
+    counts_d = torch.from_numpy(counts).to(dev)
+    frames_d = table_d[n_frames].contiguous()
+    nslices_d = counts_d[n_frames].contiguous()
+    smoothing = int(settings.smoothing_log_bins or 0) > 1
+    params = engine.csd_params(n_fft, hop, settings.use_hann_window, bin_lo, int(freq.size),
+                               "none" if smoothing else settings.db_reference, settings.floor_db,
+                               settings.dynamic_range_db)
+    start = start.contiguous()
+    slices = engine.csd(rows, start, frames_d, nslices_d, params)
+    plan = WaterfallPlan(start=start.cpu().numpy().astype(np.int32), length=remaining.cpu().numpy().astype(np.int64),
+                         frames=frames_d.cpu().numpy(), n_slices=nslices_d.cpu().numpy(), bin_lo=bin_lo, freq=freq,
+                         hop_length=hop, sample_rate_hz=int(sample_rate_hz))
+    if validate:
+        if np.any(plan.length < n_fft):
+            raise ValueError(_TOO_SHORT)
+        if np.any(plan.n_slices < 2):
+            raise ValueError(_TOO_FEW_SLICES)
+    return slices, plan
+
+
+def analyse_waterfall_batch(channels, sample_rate_hz: int, channel_names: Optional[Sequence[str]] = None,
+                            settings: Optional[WaterfallAnalysisSettings] = None, device=None,
+                            peaks=None) -> List[ChannelWaterfallResult]:
+    settings = settings or WaterfallAnalysisSettings()
+    rows = channels if isinstance(channels, engine.Rows) else engine.make_rows(channels, device)
+    names = list(channel_names) if channel_names is not None else [f"ch{i}" for i in range(rows.n_rows)]
+    slices, plan = run_waterfall(rows, sample_rate_hz, settings, peaks)
+    table = slices.cpu().numpy()
+    smoothing = int(settings.smoothing_log_bins or 0) > 1
+    nyquist = float(np.fft.rfftfreq(int(settings.n_fft), d=1.0 / float(sample_rate_hz)).astype(np.float32)[-1])
+    f_lo = float(np.clip(settings.f_min_hz, 1.0, nyquist))
+    f_hi = float(np.clip(settings.f_max_hz, f_lo, nyquist))
+    results = []
+    for b in range(rows.n_rows):
+        s = int(plan.n_slices[b])
+        rel = np.array(table[b, :s, :], dtype=np.float32)
+        if smoothing:
+            rel = np.stack([
+                _smooth_mag_db_log_frequency(plan.freq, row, f_lo, f_hi, int(settings.smoothing_log_bins),
+                                             int(settings.log_bins_per_octave)) for row in rel
+            ], axis=0).astype(np.float32)
+            rel = _normalise_slices(rel, settings)
+        results.append(ChannelWaterfallResult(
+            channel_name=str(names[b]),
+            sample_rate_hz=int(sample_rate_hz),
+            analysis_start_sample_index=int(plan.start[b]),
+            analysis_length_samples=int(plan.length[b]),
+            slice_times_seconds=plan.slice_times(b),
+            frequency_hz=plan.freq,
+            slice_magnitude_rel_db=rel,
+        ))
+    return results
+
+
+def analyse_waterfall_for_channel(
+    samples: np.ndarray,
+    sample_rate_hz: int,
+    channel_name: str,
+    settings: WaterfallAnalysisSettings,
+) -> ChannelWaterfallResult:
+    """One channel (reference waterfall.py:349-410)."""
+    samples = np.asarray(samples, dtype=np.float32)
+    if samples.ndim != 1:
+        raise ValueError("_compute_stft_magnitude_db expects a 1D mono array.")
+    if samples.size < int(settings.n_fft):
+        raise ValueError(_TOO_SHORT)
+    return analyse_waterfall_batch(samples[None, :], sample_rate_hz, [channel_name], settings)[0]
+
+
+def analyse_waterfall_from_wav_file(
+    input_wav_file_path: str | Path,
+    settings: Optional[WaterfallAnalysisSettings] = None,
+) -> List[ChannelWaterfallResult]:
+    """Reference waterfall.py:413-441; the channels of one file share a batch."""
+    settings = settings or WaterfallAnalysisSettings()
+    audio = load_wav_file(input_wav_file_path, expected_channel_mode="mono_or_stereo",
+                          allow_mono_and_upmix_to_stereo=False)
+    chans = get_analysis_channels(audio, use_mono_downmix_for_stereo=settings.use_mono_downmix_for_stereo)
+    data = np.stack([c for _, c in chans], axis=0)
+    return analyse_waterfall_batch(data, audio.sample_rate_hz, [n for n, _ in chans], settings)
+
+
+# --------------------------------------------------------------------------------------
+# figures (optional) and text
+# --------------------------------------------------------------------------------------
+
+_TICKS_HZ = (20, 50, 100, 200, 500, 1000, 2000, 5000, 10000, 20000)
+
+
+def _hz_major_ticks_for_audio(f_min_hz: float, f_max_hz: float) -> List[float]:
+    inside = [float(t) for t in _TICKS_HZ if float(f_min_hz) <= float(t) <= float(f_max_hz)]
+    return inside or [float(max(1.0, f_min_hz)), float(f_max_hz)]
+
+
+def _hz_tick_formatter(x, pos) -> str:
+    return f"{int(round(x / 1000.0))}k" if x >= 1000.0 else f"{int(round(x))}"
+
+
+def plot_waterfall_figure(
+    result: ChannelWaterfallResult,
+    analysis_settings: WaterfallAnalysisSettings,
+    plot_settings: WaterfallPlotSettings,
+    title: Optional[str] = None,
+):
+    """3-D surface over log10(f) (default) or 2-D stacked ridges (same content as reference :458-560)."""
+    from .plotting import DEFAULT_DPI, DEFAULT_FIGURE_SIZE, create_figure_and_axis, pyplot
+
+    plt = pyplot(optional=False)
+    import matplotlib.ticker as mticker
+
+    nyquist = 0.5 * float(result.sample_rate_hz)
+    f_lo = float(np.clip(analysis_settings.f_min_hz, 1.0, nyquist))
+    f_hi = float(np.clip(analysis_settings.f_max_hz, f_lo, nyquist))
+    dyn = float(max(10.0, analysis_settings.dynamic_range_db))
+    ticks = _hz_major_ticks_for_audio(f_lo, f_hi)
+    if str(plot_settings.style).lower() == "2d":
+        figure, axis = create_figure_and_axis(title=title)
+        axis.set_xlabel("Frequency (Hz)")
+        axis.set_ylabel("Magnitude (dB, offset by time slice)")
+        axis.set_xscale("log")
+        axis.set_xlim(f_lo, f_hi)
+        axis.set_xticks(ticks)
+        axis.xaxis.set_major_formatter(mticker.FuncFormatter(_hz_tick_formatter))
+        axis.xaxis.set_minor_formatter(mticker.NullFormatter())
+        step = float(max(0.0, plot_settings.ridge_offset_db))
+        count = int(result.slice_times_seconds.size)
+        for i in range(count):
+            axis.plot(result.frequency_hz, result.slice_magnitude_rel_db[i] - float(i) * step, alpha=0.9, label=None)
+        for i in (0, count // 2, count - 1):
+            axis.text(float(result.frequency_hz[0]), -float(i) * step, f"{float(result.slice_times_seconds[i]):.2f}s",
+                      fontsize=9, verticalalignment="bottom")
+        axis.grid(True, which="both", linestyle=":", linewidth=0.5)
+        if plot_settings.zlim_db is not None:
+            axis.set_ylim(*plot_settings.zlim_db)
+        else:
+            axis.set_ylim(-float(count - 1) * step - dyn, 2.0)
+        return figure
+    from mpl_toolkits.mplot3d import Axes3D  # noqa: F401  (registers the 3d projection)
+
+    figure = plt.figure(figsize=DEFAULT_FIGURE_SIZE, dpi=DEFAULT_DPI)
+    axis = figure.add_subplot(111, projection="3d")
+    if title:
+        axis.set_title(title)
+    gx, gy = np.meshgrid(np.log10(result.frequency_hz.astype(np.float64)), result.slice_times_seconds.astype(np.float64))
+    axis.plot_surface(gx, gy, result.slice_magnitude_rel_db.astype(np.float64), cmap="viridis", alpha=0.8,
+                      antialiased=True, edgecolor="none", linewidth=0)
+    axis.set_xlabel("Frequency (Hz)")
+    axis.set_ylabel("Time (s)")
+    axis.set_zlabel("Magnitude (dB rel)")
+    axis.invert_yaxis()
+    axis.set_xlim(np.log10(f_lo), np.log10(f_hi))
+    axis.set_xticks([np.log10(t) for t in ticks])
+    axis.set_xticklabels([_hz_tick_formatter(t, None) for t in ticks])
+    if plot_settings.zlim_db is not None:
+        axis.set_zlim(*plot_settings.zlim_db)
+    else:
+        axis.set_zlim(-dyn, 2.0)
+    axis.view_init(elev=float(plot_settings.elev_deg), azim=float(plot_settings.azim_deg))
+    return figure
+
+
+def plot_waterfall_from_wav_file(
+    input_wav_file_path: str | Path,
+    analysis_settings: Optional[WaterfallAnalysisSettings] = None,
+    plot_settings: Optional[WaterfallPlotSettings] = None,
+    output_basename: Optional[str | Path] = None,
+    show_interactive: bool = True,
+) -> List[ChannelWaterfallResult]:
+    """Analyse, then one `<basename>_waterfall_<CH>.png` per channel when matplotlib is available (:563-607)."""
+    from .plotting import finalize_and_show_or_save, pyplot
+
+    analysis_settings = analysis_settings or WaterfallAnalysisSettings()
+    plot_settings = plot_settings or WaterfallPlotSettings()
+    results = analyse_waterfall_from_wav_file(input_wav_file_path, analysis_settings)
+    if (output_basename is not None or show_interactive) and pyplot() is not None:
+        for r in results:
+            figure = plot_waterfall_figure(r, analysis_settings, plot_settings,
+                                           title=f"Waterfall — {input_wav_file_path} — {r.channel_name}")
+            target = None
+            if output_basename is not None:
+                base = Path(output_basename)
+                target = base.with_name(f"{base.stem}_waterfall_{r.channel_name}.png").with_suffix(".png")
+            finalize_and_show_or_save(figure, output_path=target, show_interactive=show_interactive)
+    return results
+
+
+def summarise_waterfall_results_text(results: List[ChannelWaterfallResult]) -> str:
+    """`[ch] start_sample= dur= slices= f_bins=` per channel (reference waterfall.py:615-623)."""
+    return "\n".join(
+        f"[{r.channel_name}] start_sample={r.analysis_start_sample_index}  "
+        f"dur={float(r.analysis_length_samples) / float(r.sample_rate_hz):.3f}s  "
+        f"slices={int(r.slice_times_seconds.size)}  f_bins={int(r.frequency_hz.size)}"
+        for r in results
+    )

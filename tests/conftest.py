@@ -41,3 +41,12 @@ def golden(request):
     d = load_golden(request.param)
     d["name"] = request.param
     return d
+
+
+def pytest_sessionfinish(session, exitstatus):
+    try:
+        from _parity import dump_observed
+
+        dump_observed()
+    except Exception:
+        pass

@@ -1,0 +1,367 @@
+// CPU check of the FFT engine's index arithmetic.
+//
+// Runs the SAME host/device functions the CUDA kernels use (fft_core.cuh butterflies,
+// fft_access.cuh accessors, fft_plan_host.hpp planner) in a serial emulation of
+// fft_pass1_kernel / fft_pass2_kernel / the Bluestein sequence, and compares with
+// direct DFT sums in double precision.  No GPU is needed: nvcc compiles this as a
+// host program.  Exit code 0 = all checks passed.
+#include <math.h>
+#include <stdio.h>
+#include <stdlib.h>
+
+#include <complex>
+#include <vector>
+
+#include "../../audio_analysis_b200/csrc/fft_access.cuh"
+#include "../../audio_analysis_b200/csrc/fft_plan_host.hpp"
+
+using namespace aa;
+typedef std::complex<double> cd;
+
+static unsigned long long rng_state = 0x9E3779B97F4A7C15ULL;
+static double urand() {
+    rng_state ^= rng_state << 13;
+    rng_state ^= rng_state >> 7;
+    rng_state ^= rng_state << 17;
+    return (double)(rng_state >> 11) / 9007199254740992.0 * 2.0 - 1.0;
+}
+
+static TwoLevelTwiddle dev_view(const HostTwoLevel& t) {
+    TwoLevelTwiddle d;
+    d.hi = t.hi.data();
+    d.lo = t.lo.data();
+    d.shift = t.shift;
+    return d;
+}
+
+static void emu_stages(const HostSubPlan& sp, std::vector<float2>& a, std::vector<float2>& b) {
+    int Ns = 1;
+    for (int s = 0; s < sp.nst; ++s) {
+        int R = sp.radix[s];
+        for (int j = 0; j < sp.L / R; ++j) stockham_butterfly(R, j, sp.L, Ns, a.data(), b.data(), sp.tw.data());
+        a.swap(b);
+        Ns *= R;
+    }
+}
+
+static void emu_direct(const HostC2C& p, const SrcDesc& src, const DstDesc& dst, long long units) {
+    std::vector<float2> scratch;
+    for (long long u = 0; u < units; ++u) {
+        SrcDesc src2 = src;
+        long long u2 = u;
+        if (p.M1 > 1) {
+            scratch.assign((size_t)p.M, make_float2(0, 0));
+            TwoLevelTwiddle tw = dev_view(p.twM);
+            std::vector<float2> a((size_t)p.M1), b((size_t)p.M1);
+            for (int col = 0; col < p.M2; ++col) {
+                for (int i = 0; i < p.M1; ++i) a[(size_t)i] = src_get(src, u, (int)pass1_src_index(p.M2, col, i));
+                emu_stages(p.s1, a, b);
+                for (int i = 0; i < p.M1; ++i)
+                    scratch[(size_t)pass1_dst_index(p.M2, col, i)] = cmul(a[(size_t)i], twiddle2(tw, (long long)col * i));
+            }
+            src2 = SrcDesc{};
+            src2.mode = SRC_COMPLEX;
+            src2.base = scratch.data();
+            src2.unit_stride = 0;
+            src2.n_valid = p.M;
+            u2 = 0;
+        }
+        std::vector<float2> a((size_t)p.M2), b((size_t)p.M2);
+        for (int row = 0; row < p.M1; ++row) {
+            for (int i = 0; i < p.M2; ++i) a[(size_t)i] = src_get(src2, u2, (int)pass2_src_index(p.M2, row, i));
+            emu_stages(p.s2, a, b);
+            for (int i = 0; i < p.M2; ++i) dst_put(dst, u, (int)pass2_dst_index(p.M1, row, i), a[(size_t)i]);
+        }
+    }
+}
+
+struct EmuPlan {
+    HostC2C top;
+    HostC2C inner;  // Bluestein: length P
+    std::vector<float2> H;
+};
+
+static SrcDesc src_complex(const float2* base, long long stride, int n_valid, int conj) {
+    SrcDesc s{};
+    s.mode = SRC_COMPLEX;
+    s.base = base;
+    s.unit_stride = stride;
+    s.n_valid = n_valid;
+    s.conj = conj;
+    return s;
+}
+static DstDesc dst_complex(float2* base, long long stride, int n_valid, int conj, float scale) {
+    DstDesc d{};
+    d.mode = DST_COMPLEX;
+    d.base = base;
+    d.unit_stride = stride;
+    d.n_valid = n_valid;
+    d.conj1 = conj;
+    d.scale1 = scale;
+    d.scale2 = 1.0f;
+    return d;
+}
+
+static bool emu_plan(int M, EmuPlan* ep) {
+    if (direct_plan_possible(M)) return host_direct_plan(M, &ep->top);
+    host_bluestein_tables(M, &ep->top);
+    if (!host_direct_plan(ep->top.P, &ep->inner)) return false;
+    ep->H.assign((size_t)ep->top.P, make_float2(0, 0));
+    emu_direct(ep->inner, src_complex(ep->top.hw.data(), ep->top.P, ep->top.P, 0),
+               dst_complex(ep->H.data(), ep->top.P, ep->top.P, 0, 1.0f), 1);
+    return true;
+}
+
+// mirrors c2c_exec in fft.cu
+static void emu_exec(const EmuPlan& ep, SrcDesc src, DstDesc dst, long long units) {
+    if (!ep.top.bluestein) {
+        emu_direct(ep.top, src, dst, units);
+        return;
+    }
+    const int P = ep.top.P;
+    std::vector<float2> mid((size_t)units * P);
+    SrcDesc s1 = src;
+    s1.chirp = ep.top.chirp.data();
+    s1.chirp_len = ep.top.M;
+    DstDesc d1{};
+    d1.mode = DST_MUL_TABLE;
+    d1.base = mid.data();
+    d1.unit_stride = P;
+    d1.n_valid = P;
+    d1.scale1 = 1.0f;
+    d1.scale2 = 1.0f;
+    d1.table = ep.H.data();
+    emu_direct(ep.inner, s1, d1, units);
+    SrcDesc s2 = src_complex(mid.data(), P, P, 1);
+    DstDesc d2 = dst;
+    d2.conj1 = 1;
+    d2.scale1 = 1.0f / (float)P;
+    d2.chirp = ep.top.chirp.data();
+    d2.conj2 = dst.conj1;
+    d2.scale2 = dst.scale1 * dst.scale2;
+    d2.n_valid = dst.n_valid < ep.top.M ? dst.n_valid : ep.top.M;
+    emu_direct(ep.inner, s2, d2, units);
+}
+
+static int failures = 0;
+static void report(const char* what, int n, double err, double tol) {
+    bool ok = err <= tol;
+    printf("%-34s n=%-8d rel_err=%.3e  %s\n", what, n, err, ok ? "ok" : "FAIL");
+    if (!ok) ++failures;
+}
+
+// ---- 1. complex transforms ---------------------------------------------------------------
+static void check_c2c(int M) {
+    EmuPlan ep;
+    if (!emu_plan(M, &ep)) {
+        printf("plan failed for %d\n", M);
+        ++failures;
+        return;
+    }
+    const int units = 2;
+    std::vector<float2> x((size_t)units * M), X((size_t)units * M);
+    double norm = 0;
+    for (auto& v : x) {
+        v = make_float2((float)urand(), (float)urand());
+        norm += (double)v.x * v.x + (double)v.y * v.y;
+    }
+    norm = sqrt(norm / units);
+    emu_exec(ep, src_complex(x.data(), M, M, 0), dst_complex(X.data(), M, M, 0, 1.0f), units);
+    // spot check bins by direct summation
+    int nchk = M <= 512 ? M : 48;
+    double worst = 0;
+    for (int c = 0; c < nchk; ++c) {
+        int k = M <= 512 ? c : (int)((urand() * 0.5 + 0.5) * (M - 1));
+        for (int u = 0; u < units; ++u) {
+            cd acc = 0;
+            for (int n = 0; n < M; ++n) {
+                double ang = -2.0 * M_PI * (double)(((long long)n * k) % M) / M;
+                acc += cd(x[(size_t)u * M + n].x, x[(size_t)u * M + n].y) * cd(cos(ang), sin(ang));
+            }
+            double e = std::abs(acc - cd(X[(size_t)u * M + k].x, X[(size_t)u * M + k].y)) / norm;
+            if (e > worst) worst = e;
+        }
+    }
+    char name[64];
+    snprintf(name, sizeof(name), "c2c %s M1=%d M2=%d", ep.top.bluestein ? "bluestein" : "direct",
+             ep.top.bluestein ? ep.inner.M1 : ep.top.M1, ep.top.bluestein ? ep.inner.M2 : ep.top.M2);
+    report(name, M, worst, ep.top.bluestein ? 3e-5 : 5e-6);
+    // inverse through the conj trick must return the input
+    std::vector<float2> back((size_t)units * M);
+    emu_exec(ep, src_complex(X.data(), M, M, 1), dst_complex(back.data(), M, M, 1, 1.0f / M), units);
+    double e2 = 0;
+    for (size_t i = 0; i < back.size(); ++i) {
+        double d = hypot((double)back[i].x - x[i].x, (double)back[i].y - x[i].y);
+        if (d > e2) e2 = d;
+    }
+    report("  round trip", M, e2, ep.top.bluestein ? 1e-4 : 2e-5);
+}
+
+// ---- 2. real forward + band-masked real inverse (the rt60bands filter) -------------------
+static BandDev make_bandpass(double low, double high, double tw_oct, double nyq, double freq_scale, int nbins) {
+    BandDev b{};
+    b.kind = AA_BAND_BANDPASS;
+    double fac = pow(2.0, tw_oct);
+    double hp_pass = low, hp_stop = fmax(1.0, low / fac);
+    double lp_pass = high, lp_stop = fmin(nyq, high * fac);
+    b.hp_stop = (float)hp_stop;
+    b.hp_pass = (float)hp_pass;
+    b.hp_span = (float)(hp_pass - hp_stop);
+    b.lp_pass = (float)lp_pass;
+    b.lp_stop = (float)lp_stop;
+    b.lp_span = (float)(lp_stop - lp_pass);
+    b.k_first = nbins;
+    b.k_last = -1;
+    BandDev open = b;
+    open.k_first = 0;
+    open.k_last = nbins - 1;
+    for (int k = 0; k < nbins; ++k) {
+        float f = (float)((double)k * freq_scale);
+        if (band_mask_value(open, f) != 0.0f) {
+            if (k < b.k_first) b.k_first = k;
+            b.k_last = k;
+        }
+    }
+    return b;
+}
+
+static void check_real_band(int N) {
+    const double sr = 48000.0;
+    const double freq_scale = 1.0 / ((double)N * (1.0 / sr));
+    const int half = N / 2;
+    std::vector<float> x((size_t)N);
+    double norm = 0;
+    for (int n = 0; n < N; ++n) {
+        x[(size_t)n] = (float)(urand() * exp(-6.0 * n / N));
+        norm += (double)x[(size_t)n] * x[(size_t)n];
+    }
+    norm = sqrt(norm);
+    std::vector<float2> X;  // half spectrum, k in [0, N/2]
+    long long X_stride;
+    HostTwoLevel twN;
+    host_two_level(N, &twN);
+    EmuPlan ep;
+    const bool even = (N % 2) == 0;
+    const int M = even ? N / 2 : N;
+    if (!emu_plan(M, &ep)) {
+        ++failures;
+        return;
+    }
+    if (even) {
+        std::vector<float2> Z((size_t)M);
+        SrcDesc s{};
+        s.mode = SRC_REAL_PACKED;
+        s.base = x.data();
+        s.unit_stride = N;
+        s.n_valid = N;
+        emu_exec(ep, s, dst_complex(Z.data(), M, M, 0, 1.0f), 1);
+        X.resize((size_t)M + 1);
+        TwoLevelTwiddle t = dev_view(twN);
+        for (int k = 0; k <= M; ++k)
+            X[(size_t)k] = untangle_half_spectrum(Z[(size_t)(k % M)], Z[(size_t)((M - k) % M)], twiddle2(t, k));
+        X_stride = M + 1;
+    } else {
+        X.resize((size_t)N);
+        SrcDesc s{};
+        s.mode = SRC_REAL_AS_COMPLEX;
+        s.base = x.data();
+        s.unit_stride = N;
+        s.n_valid = N;
+        emu_exec(ep, s, dst_complex(X.data(), N, N, 0, 1.0f), 1);
+        X_stride = N;
+    }
+    // forward check on a few bins
+    double worst = 0;
+    for (int c = 0; c < 24; ++c) {
+        int k = (c == 0) ? 0 : (c == 1 ? half : (int)((urand() * 0.5 + 0.5) * half));
+        cd acc = 0;
+        for (int n = 0; n < N; ++n) {
+            double ang = -2.0 * M_PI * (double)(((long long)n * k) % N) / N;
+            acc += (double)x[(size_t)n] * cd(cos(ang), sin(ang));
+        }
+        double e = std::abs(acc - cd(X[(size_t)k].x, X[(size_t)k].y)) / norm;
+        if (e > worst) worst = e;
+    }
+    char name[64];
+    snprintf(name, sizeof(name), "rfft %s%s", even ? "packed" : "odd", ep.top.bluestein ? "+bluestein" : "");
+    report(name, N, worst, ep.top.bluestein ? 3e-5 : 5e-6);
+
+    // two bands in one batch (unit = row*n_bands + band)
+    std::vector<BandDev> bands;
+    bands.push_back(make_bandpass(890.9, 1122.5, 1.0 / 6.0, 24000.0, freq_scale, half + 1));
+    bands.push_back(make_bandpass(55.7, 70.2, 1.0 / 6.0, 24000.0, freq_scale, half + 1));
+    const int nb = (int)bands.size();
+    std::vector<float> y((size_t)nb * N, 0.f);
+    SrcDesc s{};
+    s.mode = even ? SRC_BAND_PACKED : SRC_BAND_FULL;
+    s.base = X.data();
+    s.unit_stride = X_stride;
+    s.n_valid = M;
+    s.conj = 1;
+    s.n_bands = nb;
+    s.bands = bands.data();
+    s.freq_scale = freq_scale;
+    s.N = N;
+    s.M = even ? M : 0;
+    s.twN = dev_view(twN);
+    DstDesc d{};
+    if (even) {
+        d = dst_complex((float2*)y.data(), M, M, 1, 1.0f / (float)M);
+    } else {
+        d.mode = DST_REAL_PART;
+        d.base = y.data();
+        d.unit_stride = N;
+        d.n_valid = N;
+        d.conj1 = 1;
+        d.scale1 = 1.0f / (float)N;
+        d.scale2 = 1.0f;
+    }
+    emu_exec(ep, s, d, nb);
+    // direct evaluation of irfft(X * mask) at a few samples, from the double-precision spectrum of x
+    for (int bi = 0; bi < nb; ++bi) {
+        BandDev open = bands[(size_t)bi];
+        std::vector<cd> Y;
+        std::vector<int> ks;
+        double ynorm = 0;
+        for (int k = open.k_first; k <= open.k_last; ++k) {
+            float f = (float)((double)k * freq_scale);
+            double m = band_mask_value(open, f);
+            if (m == 0.0) continue;
+            cd acc = 0;
+            for (int n = 0; n < N; ++n) {
+                double ang = -2.0 * M_PI * (double)(((long long)n * k) % N) / N;
+                acc += (double)x[(size_t)n] * cd(cos(ang), sin(ang));
+            }
+            Y.push_back(acc * m);
+            ks.push_back(k);
+            ynorm += std::norm(acc * m);
+        }
+        ynorm = sqrt(2.0 * ynorm / N);  // rms-ish scale of the band signal times sqrt(N)
+        double w2 = 0;
+        for (int c = 0; c < 40; ++c) {
+            int n = (int)((urand() * 0.5 + 0.5) * (N - 1));
+            double acc = 0;
+            for (size_t q = 0; q < ks.size(); ++q) {
+                int k = ks[q];
+                double ang = 2.0 * M_PI * (double)(((long long)n * k) % N) / N;
+                double wgt = (k == 0 || (even && k == half)) ? 1.0 : 2.0;
+                acc += wgt * (Y[q] * cd(cos(ang), sin(ang))).real();
+            }
+            acc /= N;
+            double e = fabs(acc - (double)y[(size_t)bi * N + n]) / (ynorm / sqrt((double)N) + 1e-30);
+            if (e > w2) w2 = e;
+        }
+        snprintf(name, sizeof(name), "  band %d inverse (%d bins)", bi, (int)ks.size());
+        report(name, N, w2, ep.top.bluestein ? 2e-3 : 2e-4);
+    }
+}
+
+int main() {
+    const int sizes[] = {1, 2, 3, 4, 5, 6, 7, 8, 11, 13, 16, 30, 64, 77, 143, 360, 1001, 2048,
+                         2304, 4096, 24000, 30000, 31200, 65536, 17, 397, 4099, 25011, 45001};
+    for (int M : sizes) check_c2c(M);
+    const int real_sizes[] = {48000, 60000, 62400, 50022, 45001, 4410, 64, 1155};
+    for (int N : real_sizes) check_real_band(N);
+    printf("%s (%d failures)\n", failures ? "FAILED" : "ALL OK", failures);
+    return failures ? 1 : 0;
+}
