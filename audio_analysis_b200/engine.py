@@ -38,6 +38,10 @@ def _ptr(t: Optional[torch.Tensor]) -> C.c_void_p:
     return C.c_void_p(0 if t is None else t.data_ptr())
 
 
+def _pitch(t: torch.Tensor) -> int:
+    return int(t.stride(0)) if t.shape[0] > 1 else int(t.shape[1])
+
+
 def round_up4(n: int) -> int:
     return (int(n) + 3) & ~3
 
@@ -57,7 +61,8 @@ class Rows:
 
     @property
     def stride(self) -> int:
-        return int(self.x.stride(0))
+        # torch reports arbitrary strides for size-1 dimensions: a single row's pitch is its width
+        return int(self.x.stride(0)) if self.x.shape[0] > 1 else int(self.x.shape[1])
 
     @property
     def uniform(self) -> bool:
@@ -203,7 +208,7 @@ def curve_fits(curve: torch.Tensor, lengths: Optional[torch.Tensor], uniform_len
     fits = torch.empty((b, nat.AA_MAX_FITS, nat.AA_FIT_COLS), dtype=torch.float64, device=dev)
     early = torch.empty(b, dtype=torch.float64, device=dev)
     with torch.cuda.device(dev):
-        nat.check(lib.aa_curve_fits_batch(_ptr(curve), int(curve.stride(0)), _ptr(lengths), int(uniform_len),
+        nat.check(lib.aa_curve_fits_batch(_ptr(curve), _pitch(curve), _ptr(lengths), int(uniform_len),
                                           _ptr(offsets), b, C.byref(params), _ptr(fits), _ptr(early), _stream_ptr()))
     return fits, early
 
@@ -215,7 +220,7 @@ def box_smooth_db(curve: torch.Tensor, lengths: Optional[torch.Tensor], uniform_
     dev = curve.device
     out = torch.empty_like(curve)
     with torch.cuda.device(dev):
-        nat.check(lib.aa_box_smooth_db_batch(_ptr(curve), _ptr(out), int(curve.stride(0)), _ptr(lengths),
+        nat.check(lib.aa_box_smooth_db_batch(_ptr(curve), _ptr(out), _pitch(curve), _ptr(lengths),
                                              int(uniform_len), _ptr(offsets), int(curve.shape[0]), int(window),
                                              float(floor_db), _stream_ptr()))
     return out
@@ -389,7 +394,7 @@ def pcm16_to_rows(pcm: torch.Tensor, n_frames: int, n_channels: int, mono_downmi
     stride = round_up4(n_frames)
     out = torch.zeros((files * per_file, stride), dtype=torch.float32, device=dev)
     with torch.cuda.device(dev):
-        nat.check(lib.aa_pcm16_to_float_batch(_ptr(pcm), int(pcm.stride(0)), files, int(n_frames), int(n_channels),
+        nat.check(lib.aa_pcm16_to_float_batch(_ptr(pcm), _pitch(pcm), files, int(n_frames), int(n_channels),
                                               1 if (mono_downmix and n_channels == 2) else 0, _ptr(out), stride,
                                               _stream_ptr()))
     hl = np.full(files * per_file, n_frames, dtype=np.int64)

@@ -1,0 +1,406 @@
+#!/usr/bin/env python
+"""Benchmark of the IR decay / spectral-decay hot path (BASELINE.json metric).
+
+    python bench.py --gpus N --steps K --warmup W            # this build (CUDA path)
+    python bench.py --impl reference --gpus N --steps K ...   # the reference algorithm on the host cores
+
+Metric: IR-seconds analysed per second for third-octave RT60 + broadband EDC + CSD waterfall.
+Workload: config 5 of BASELINE.json (6 s @ 48 kHz mono IRs, 288,000 samples), sharded by IR:
+each GPU analyses `--rows` IRs per step (default 8192 = the 8-GPU shard of the 65,536-IR config),
+so N GPUs analyse N * rows IRs per step (weak scaling, no data-path collective; one NCCL gather of
+the metric tables per step).
+
+One step = decay (EDC curve + EDT/T20/T30 fits + early-decay time) + rt60bands (third-octave, T30) +
+waterfall (18 slices x 1705 bins) over the whole batch.  `value` is timed with the inputs resident in
+HBM; `e2e` through the public batch API from pinned host memory with the result tables copied back.
+"""
+
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+from pathlib import Path
+
+ROOT = Path(__file__).resolve().parent
+if str(ROOT) not in sys.path:
+    sys.path.insert(0, str(ROOT))
+
+SR = 48000
+N_SAMPLES = 288000
+METRIC = "ir_seconds_analysed_per_second"
+UNIT = "IR-s/s"
+
+
+# ----------------------------------------------------------------------------------------------
+# CPU side (oracle port of the reference algorithm) - used by cpu_baseline and --impl reference
+# ----------------------------------------------------------------------------------------------
+
+
+def _cpu_one_row(row):
+    """The reference's three analyses on one channel (oracle/ref_port.py restates analyse/*.py)."""
+    import oracle
+
+    d = oracle.decay_metrics(row, SR, oracle.DecayParams(compute_edt=True))
+    b = oracle.band_metrics(row, SR, oracle.BandParams(band_mode="third"))
+    # the reference computes every STFT frame (waterfall.py:220); time it the way the reference runs
+    w = oracle.waterfall(row, SR, oracle.CsdParams(), only_selected_frames=False)
+    return d["start"], len(b["metrics"]), w["rel_db"].shape
+
+
+def _cpu_init():
+    for var in ("OMP_NUM_THREADS", "MKL_NUM_THREADS", "OPENBLAS_NUM_THREADS"):
+        os.environ[var] = "1"
+
+
+def cpu_throughput(rows_np, cores, repeats=1, start_method="spawn"):
+    """IR-seconds per wall second of the CPU path on `cores` worker processes.
+
+    spawn, not fork: the calling process holds a CUDA context."""
+    import multiprocessing as mp
+
+    ctx = mp.get_context(start_method)
+    with ctx.Pool(processes=cores, initializer=_cpu_init) as pool:
+        pool.map(_cpu_one_row, [rows_np[0]] * cores)  # warm the workers (imports, FFT plans)
+        best = None
+        for _ in range(repeats):
+            t0 = time.perf_counter()
+            pool.map(_cpu_one_row, list(rows_np), chunksize=1)
+            dt = time.perf_counter() - t0
+            best = dt if best is None else min(best, dt)
+    return rows_np.shape[0] * (N_SAMPLES / SR) / best, best
+
+
+def host_cores() -> int:
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except AttributeError:
+        return max(1, os.cpu_count() or 1)
+
+
+# ----------------------------------------------------------------------------------------------
+# clocks
+# ----------------------------------------------------------------------------------------------
+
+
+class ClockSampler:
+    FIELDS = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+              "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.gpu = gpu_index
+        self.proc = None
+        self.lines = []
+        self.thread = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--id={self.gpu}", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits",
+                 "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except OSError:
+            self.proc = None
+            return
+        self.thread = threading.Thread(target=self._pump, daemon=True)
+        self.thread.start()
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        sm, smax, power, reasons = [], [], [], set()
+        names = ("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap")
+        for line in self.lines:
+            parts = [p.strip() for p in line.split(",")]
+            if len(parts) < 9:
+                continue
+            try:
+                sm.append(float(parts[1]))
+                smax.append(float(parts[2]))
+                power.append(float(parts[3]))
+            except ValueError:
+                continue
+            for name, val in zip(names, parts[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        return {"sm_mhz": statistics.median(sm), "sm_max_mhz": max(smax), "power_w_max": max(power),
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# ----------------------------------------------------------------------------------------------
+# this build
+# ----------------------------------------------------------------------------------------------
+
+
+def measured_peak_gbs():
+    path = ROOT / "MEASURED_PEAKS.json"
+    if path.exists():
+        try:
+            return float(json.loads(path.read_text())["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+def run_ours(args):
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+
+    from audio_analysis_b200 import _native as nat
+    from audio_analysis_b200 import decay, distributed, engine, rt60bands, waterfall
+    from audio_analysis_b200.pipeline import run_hot_path
+    from audio_analysis_b200.synth import synth_batch_torch
+
+    rank, world, local = distributed.init_from_env("nccl")
+    if world != args.gpus and rank == 0:
+        print(f"note: --gpus {args.gpus} but WORLD_SIZE={world}", file=sys.stderr)
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    lib = nat.load()
+    rows_n = int(args.rows)
+    n = int(args.samples)
+
+    ds = decay.DecayAnalysisSettings(compute_edt=True)
+    bs = rt60bands.Rt60BandsAnalysisSettings(band_mode="third", decay_settings=ds)
+    ws = waterfall.WaterfallAnalysisSettings()
+
+    # synthetic input, generated on the device; rank r owns IR indices [r*rows, (r+1)*rows)
+    x_dev = synth_batch_torch(rows_n, n, SR, first_index=rank * rows_n, device=dev)
+    rows = engine.make_rows(x_dev)
+    torch.cuda.synchronize()
+
+    def step_device():
+        return run_hot_path(rows, SR, ds, bs, ws, want_edc=True)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(3, args.warmup)):
+        out = step_device()
+    barrier()
+    launches0 = lib.aa_kernel_launch_count()
+    sampler = ClockSampler(local)
+    sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for _ in range(args.steps):
+        out = step_device()
+    e1.record()
+    barrier()
+    clocks = sampler.stop()
+    ms_total = e0.elapsed_time(e1)
+    launches = (lib.aa_kernel_launch_count() - launches0) // max(1, args.steps)
+    t = torch.tensor([ms_total], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_total = float(t.item())
+    ms_step = ms_total / args.steps
+    ir_seconds_per_step = world * rows_n * (n / SR)
+    value = ir_seconds_per_step / (ms_step / 1e3)
+
+    # ---- per-kernel timings for the roofline objects (CUDA events on the launching stream)
+    def time_call(fn, reps=5):
+        fn()
+        torch.cuda.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(reps):
+            fn()
+        b.record()
+        torch.cuda.synchronize()
+        return a.elapsed_time(b) / reps
+
+    peak, peak_src = measured_peak_gbs()
+    ms_decay = time_call(lambda: decay.run_decay(rows, SR, ds, want_edc=True))
+    start_idx = out.decay.start
+    ms_bands = time_call(lambda: rt60bands.run_rt60_bands(rows, SR, bs, start_idx=start_idx), reps=2)
+    ms_csd = time_call(lambda: waterfall.run_waterfall(rows, SR, ws, peaks=start_idx, validate=False))
+    n_bins = int(out.csd.shape[2])
+    bytes_decay = 8.0 * rows_n * n                                   # read x + write edc_db
+    bytes_bands = 4.0 * rows_n * n                                   # read x once; outputs negligible
+    bytes_csd = rows_n * (18 * 4096 * 4.0 + 18 * n_bins * 4.0)       # selected frames in, slices out
+    def roof(nbytes, ms):
+        gbs = nbytes / (ms / 1e3) / 1e9
+        return {"achieved": round(gbs, 1), "frac": round(gbs / peak, 4), "ms": round(ms, 4)}
+    roofline = {"bound": "hbm", "kernel": "edc_kernel<true> (aa_decay_batch: fused EDC + crossings + fits)",
+                **roof(bytes_decay, ms_decay), "peak": peak, "peak_source": peak_src, "unit": "GB/s",
+                "algorithmic_bytes_per_launch": bytes_decay, "traffic": None,
+                "share_of_step": round(ms_decay / ms_step, 4)}
+    by_kernel = {
+        "decay_edc_fits": {**roof(bytes_decay, ms_decay), "bound": "hbm", "share_of_step": round(ms_decay / ms_step, 4)},
+        "rt60bands_third_octave": {**roof(bytes_bands, ms_bands), "bound": "fp32 ALU / L2 (SURVEY D7), not HBM",
+                                   "share_of_step": round(ms_bands / ms_step, 4)},
+        "csd_waterfall": {**roof(bytes_csd, ms_csd), "bound": "hbm", "share_of_step": round(ms_csd / ms_step, 4)},
+    }
+
+    # ---- end to end through the public batch API: pinned host input -> H2D -> kernels -> tables D2H
+    e2e = None
+    try:
+        x_host = torch.empty((rows_n, n), dtype=torch.float32, pin_memory=True)
+        x_host.copy_(x_dev)
+        torch.cuda.synchronize()
+        keep = {}
+
+        def step_e2e():
+            r = engine.make_rows(x_host, device=dev)             # H2D from pinned memory
+            o = run_hot_path(r, SR, ds, bs, ws, want_edc=True)
+            res = {"start": o.decay.start, "fits": o.decay.fits, "early10": o.decay.early10,
+                   "status": o.decay.status, "band_rt60": o.band_metrics, "csd": o.csd}
+            nbytes = 0
+            for k, v in res.items():
+                if k not in keep:
+                    keep[k] = torch.empty(v.shape, dtype=v.dtype, pin_memory=True)
+                keep[k].copy_(v, non_blocking=True)               # D2H of the result tables + CSD slices
+                nbytes += v.numel() * v.element_size()
+            return nbytes
+
+        d2h = step_e2e()
+        barrier()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        steps_e2e = max(1, min(args.steps, 3))
+        a.record()
+        for _ in range(steps_e2e):
+            d2h = step_e2e()
+        b.record()
+        barrier()
+        t2 = torch.tensor([a.elapsed_time(b)], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t2, op=dist.ReduceOp.MAX)
+        ms_e2e = float(t2.item()) / steps_e2e
+        e2e = {"value": round(ir_seconds_per_step / (ms_e2e / 1e3), 1), "unit": UNIT, "ms_per_step": round(ms_e2e, 3),
+               "h2d_bytes_per_step": int(rows_n * n * 4), "d2h_bytes_per_step": int(d2h),
+               "note": "EDC curves stay in HBM (plot data on demand); metric tables and CSD slices are copied back"}
+        del x_host
+    except Exception as exc:  # pinned allocation can fail on small hosts
+        e2e = {"value": None, "unit": UNIT, "error": str(exc)[:200]}
+
+    # ---- the one collective: gather the metric tables to rank 0 (timed, not part of `value`)
+    gather_ms = None
+    if world > 1:
+        tables = {"band_rt60": out.band_metrics, "fits": out.decay.fits, "early10": out.decay.early10,
+                  "start": out.decay.start}
+        barrier()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        distributed.gather_tables(tables, world * rows_n)
+        b.record()
+        barrier()
+        gather_ms = a.elapsed_time(b)
+
+    # ---- CPU baseline: the oracle port on the host cores, bounded sample (rank 0, single GPU run only)
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        cores = host_cores()
+        sample = max(8, min(cores, 64))
+        sample_rows = x_dev[:sample].cpu().numpy()
+        v, wall = cpu_throughput(sample_rows, cores=min(cores, sample))
+        cpu = {"value": round(v, 2), "unit": UNIT, "cores": min(cores, sample), "kind": "port",
+               "sample": f"{sample} of the same IRs ({sample * n / SR:.0f} IR-s), one process per core, "
+                         f"{wall:.2f} s wall; decay + third-octave rt60bands + waterfall of oracle/ref_port.py"}
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": round(value, 1), "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": max(3, args.warmup), "ms_per_step": round(ms_step, 3), "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32 (f64 carries and regression sums)",
+            "data": "synthetic exponentially-decaying gaussian noise IRs, 0.25-0.5 s leading silence, -90 dB floor",
+            "config": {"workload": f"config5 shard: {rows_n} x {n / SR:.0f} s @48 kHz mono IRs per GPU "
+                                   f"(third-octave RT60 + broadband EDC/EDT/T20/T30 + CSD 18x{n_bins})",
+                       "rows_per_gpu": rows_n, "samples_per_row": n, "bands": 26,
+                       "l2": "inputs (rows*samples*4 B per GPU) are larger than L2; no flush needed"},
+            "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
+            "roofline": roofline, "roofline_by_kernel": by_kernel, "cpu_baseline": cpu,
+            "gather_ms": gather_ms,
+        }
+        print(json.dumps(line))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+# ----------------------------------------------------------------------------------------------
+# reference arm: the reference's own CPU algorithm (oracle port; /root/reference is not on the GPU box)
+# ----------------------------------------------------------------------------------------------
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import numpy as np
+
+    from audio_analysis_b200.synth import synth_batch_numpy
+
+    cores = host_cores()
+    sample = max(8, min(cores, 64))
+    rows = synth_batch_numpy(sample, int(args.samples), SR)
+    import multiprocessing as mp
+
+    workers = min(cores, sample)
+    ctx = mp.get_context("fork")
+    times = []
+    with ctx.Pool(processes=workers, initializer=_cpu_init) as pool:
+        for _ in range(max(1, args.warmup)):
+            pool.map(_cpu_one_row, list(rows[:workers]), chunksize=1)
+        for _ in range(args.steps):
+            t0 = time.perf_counter()
+            pool.map(_cpu_one_row, list(rows), chunksize=1)
+            times.append(time.perf_counter() - t0)
+    total = sum(times)
+    value = args.steps * sample * (int(args.samples) / SR) / total
+    line = {
+        "impl": "reference", "metric": METRIC, "value": round(value, 2), "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": max(1, args.warmup), "ms_per_step": round(1e3 * total / args.steps, 2),
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64 (numpy)",
+        "data": "synthetic exponentially-decaying gaussian noise IRs, 0.25-0.5 s leading silence, -90 dB floor",
+        "config": {"workload": f"config5 rows: {sample} x {int(args.samples) / SR:.0f} s @48 kHz mono IRs per step "
+                               "(third-octave RT60 + broadband EDC/EDT/T20/T30 + CSD), bounded sample of the GPU arm's "
+                               "workload", "samples_per_row": int(args.samples), "bands": 26},
+        "cpu_baseline": {"value": round(value, 2), "unit": UNIT, "cores": workers, "kind": "port",
+                         "sample": f"{sample} IRs per step, one process per core; oracle/ref_port.py restates "
+                                   "analyse/decay.py, rt60bands.py, waterfall.py (pinned bit-exact to the reference by "
+                                   "tests/golden)"},
+        "e2e": {"value": round(value, 2), "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
+    ap.add_argument("--rows", type=int, default=int(os.environ.get("AA_BENCH_ROWS", "8192")),
+                    help="IRs per GPU per step (default 8192: config 5 sharded over 8 GPUs)")
+    ap.add_argument("--samples", type=int, default=N_SAMPLES)
+    ap.add_argument("--no-cpu-baseline", dest="no_cpu_baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

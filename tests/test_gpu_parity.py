@@ -83,7 +83,12 @@ def test_decay_ragged_batch_equals_single_rows(dec):
     # batch result == batch-size-1 result, bit for bit (the kernel is deterministic)
     single = dec.analyse_decay_for_channel(chans[1], SR, "x", s)
     assert np.array_equal(single.edc_db, batch[1].edc_db)
-    assert single.fits == {k: v for k, v in batch[1].fits.items()}
+    # the float64 regression sums are reduced in a different order when the tile -> warp split changes
+    for k, f in single.fits.items():
+        g = batch[1].fits[k]
+        assert f.start_time_seconds == g.start_time_seconds and f.end_time_seconds == g.end_time_seconds
+        assert f.rt60_seconds == pytest.approx(g.rt60_seconds, rel=1e-12)
+        assert f.r_squared == pytest.approx(g.r_squared, abs=1e-12)
 
 
 def test_decay_analytic_exponential(dec):
