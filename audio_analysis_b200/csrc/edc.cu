@@ -41,6 +41,7 @@ constexpr int kWarps = kThreads / 32;
 constexpr int kTile = 128;  // samples per warp tile: one float4 per lane
 constexpr int kMaxTargets = 2 + 2 * AA_MAX_FITS;
 constexpr int kMaxCluster = 8;
+constexpr int kUnroll = 4;  // tiles loaded ahead per warp (memory-level parallelism)
 
 struct EdcArgs {
     const float* x;
@@ -134,7 +135,7 @@ __device__ __forceinline__ float to_db(double e, double eps, double inv_e0, floa
 }
 
 template <bool kWriteDb>
-__global__ void __launch_bounds__(kThreads) edc_kernel(EdcArgs a) {
+__global__ void __launch_bounds__(kThreads, 2) edc_kernel(EdcArgs a) {
     cg::cluster_group cluster = cg::this_cluster();
     const int T = (int)cluster.num_blocks();
     const int rank = (int)cluster.block_rank();
@@ -166,22 +167,32 @@ __global__ void __launch_bounds__(kThreads) edc_kernel(EdcArgs a) {
     int aidx = 0x7fffffff;
     {
         const int k_skip = (start_known >= 0) ? start_known / kTile : 0;
-        for (int k = my_tile0; k < my_tile0 + tpw; ++k) {
-            float tsum = 0.f;
-            if (k < my_tile1 && k >= k_skip) {
-                float4 v = load_tile(x, k, lane, len);
-                if (find_peak) {
-                    const int i0 = k * kTile + lane * 4;
-                    float m;
-                    m = fabsf(v.x); if (m > amax) { amax = m; aidx = i0; }
-                    m = fabsf(v.y); if (m > amax) { amax = m; aidx = i0 + 1; }
-                    m = fabsf(v.z); if (m > amax) { amax = m; aidx = i0 + 2; }
-                    m = fabsf(v.w); if (m > amax) { amax = m; aidx = i0 + 3; }
-                }
-                TileScan t = tile_scan(v);
-                tsum = __fadd_rn(t.excl, t.s[0]);  // lane 0: whole-tile sum, same ops as phase 2
+        for (int kb = my_tile0; kb < my_tile0 + tpw; kb += kUnroll) {
+            float4 v[kUnroll];
+#pragma unroll
+            for (int u = 0; u < kUnroll; ++u) {  // all loads first: kUnroll x 512 B in flight per warp
+                const int k = kb + u;
+                v[u] = (k < my_tile1 && k >= k_skip) ? load_tile(x, k, lane, len) : make_float4(0.f, 0.f, 0.f, 0.f);
             }
-            if (lane == 0) tile_sum[k - cta_tile0] = tsum;
+#pragma unroll
+            for (int u = 0; u < kUnroll; ++u) {
+                const int k = kb + u;
+                if (k >= my_tile0 + tpw) break;
+                float tsum = 0.f;
+                if (k < my_tile1 && k >= k_skip) {
+                    if (find_peak) {
+                        const int i0 = k * kTile + lane * 4;
+                        float m;
+                        m = fabsf(v[u].x); if (m > amax) { amax = m; aidx = i0; }
+                        m = fabsf(v[u].y); if (m > amax) { amax = m; aidx = i0 + 1; }
+                        m = fabsf(v[u].z); if (m > amax) { amax = m; aidx = i0 + 2; }
+                        m = fabsf(v[u].w); if (m > amax) { amax = m; aidx = i0 + 3; }
+                    }
+                    TileScan t = tile_scan(v[u]);
+                    tsum = __fadd_rn(t.excl, t.s[0]);  // lane 0: whole-tile sum, same ops as phase 2
+                }
+                if (lane == 0) tile_sum[k - cta_tile0] = tsum;
+            }
         }
     }
     if (find_peak) {
@@ -420,30 +431,40 @@ __global__ void __launch_bounds__(kThreads) edc_kernel(EdcArgs a) {
     }
     float* __restrict__ out = kWriteDb ? a.edc_out + (long long)row * a.edc_stride : nullptr;
 
-    for (int k = max(my_tile0, start_tile); k < my_tile1; ++k) {
-        const int t_lo = k * kTile, t_hi = t_lo + kTile - 1;
-        bool fit_here = false;
+    for (int kb = max(my_tile0, start_tile); kb < my_tile1; kb += kUnroll) {
+        float4 v[kUnroll];
+        bool need[kUnroll];
 #pragma unroll
-        for (int f = 0; f < AA_MAX_FITS; ++f) fit_here |= (ffirst[f] <= t_hi && flast[f] >= t_lo);
-        if (!kWriteDb && !fit_here) continue;
-        float4 v = load_tile(x, k, lane, len);
-        TileScan t = tile_scan(v);
-        const double base = carry[k - cta_tile0] + cta_carry;
-        float db[4];
+        for (int u = 0; u < kUnroll; ++u) {
+            const int k = kb + u;
+            const int t_lo = k * kTile, t_hi = t_lo + kTile - 1;
+            bool fit_here = false;
 #pragma unroll
-        for (int j = 0; j < 4; ++j)
-            db[j] = to_db(base + (double)__fadd_rn(t.excl, t.s[j]), a.eps, inv_e0, a.floor_db);
-        const int i0 = t_lo + lane * 4;
-        if (kWriteDb) {
-            if (i0 >= start && i0 + 3 < len) {
-                st_cs_f4(out + i0, make_float4(db[0], db[1], db[2], db[3]));
-            } else {
-#pragma unroll
-                for (int j = 0; j < 4; ++j)
-                    if (i0 + j >= start && i0 + j < len) out[i0 + j] = db[j];
-            }
+            for (int f = 0; f < AA_MAX_FITS; ++f) fit_here |= (ffirst[f] <= t_hi && flast[f] >= t_lo);
+            need[u] = (k < my_tile1) && (kWriteDb || fit_here);
+            v[u] = need[u] ? load_tile(x, k, lane, len) : make_float4(0.f, 0.f, 0.f, 0.f);
         }
-        if (fit_here) {
+#pragma unroll
+        for (int u = 0; u < kUnroll; ++u) {
+            if (!need[u]) continue;  // warp-uniform
+            const int k = kb + u;
+            const int t_lo = k * kTile, t_hi = t_lo + kTile - 1;
+            TileScan t = tile_scan(v[u]);
+            const double base = carry[k - cta_tile0] + cta_carry;
+            float db[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+                db[j] = to_db(base + (double)__fadd_rn(t.excl, t.s[j]), a.eps, inv_e0, a.floor_db);
+            const int i0 = t_lo + lane * 4;
+            if (kWriteDb) {
+                if (i0 >= start && i0 + 3 < len) {
+                    st_cs_f4(out + i0, make_float4(db[0], db[1], db[2], db[3]));
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 4; ++j)
+                        if (i0 + j >= start && i0 + j < len) out[i0 + j] = db[j];
+                }
+            }
 #pragma unroll
             for (int f = 0; f < AA_MAX_FITS; ++f) {
                 if (ffirst[f] <= t_hi && flast[f] >= t_lo) {
@@ -451,10 +472,10 @@ __global__ void __launch_bounds__(kThreads) edc_kernel(EdcArgs a) {
                     for (int j = 0; j < 4; ++j) {
                         const int idx = i0 + j;
                         if (idx >= ffirst[f] && idx <= flast[f]) {
-                            const double u = (double)(idx - ffirst[f]);
+                            const double u2 = (double)(idx - ffirst[f]);
                             const double yc = (double)db[j] - ymid[f];
                             acc[f * 3 + 0] += yc;
-                            acc[f * 3 + 1] = fma(u, yc, acc[f * 3 + 1]);
+                            acc[f * 3 + 1] = fma(u2, yc, acc[f * 3 + 1]);
                             acc[f * 3 + 2] = fma(yc, yc, acc[f * 3 + 2]);
                         }
                     }

@@ -19,7 +19,7 @@ namespace aa {
 namespace {
 
 constexpr int kPassThreads = 256;
-constexpr size_t kSmemSoft = 96 * 1024;  // aim for 2 CTAs per SM
+constexpr size_t kSmemSoft = 56 * 1024;  // per CTA: aim for 4 CTAs (32 warps) per SM
 constexpr size_t kSmemHard = 200 * 1024;
 
 int upload(const std::vector<float2>& h, float2** d) {
@@ -33,6 +33,7 @@ int upload_subplan(const HostSubPlan& h, SubPlan* sp) {
     sp->dev.L = h.L;
     sp->dev.nst = h.nst;
     memcpy(sp->dev.radix, h.radix, sizeof(h.radix));
+    fill_stage_constants(&sp->dev);
     int rc = upload(h.tw, &sp->d_tw);
     if (rc != AA_OK) return rc;
     sp->dev.tw = sp->d_tw;
@@ -53,13 +54,16 @@ int upload_two_level(const HostTwoLevel& h, TwoLevelTable* out) {
 void choose_group(int L, int* G, int* Lp, size_t* smem) {
     int lp = L | 1;  // odd row pitch: column-major accesses hit distinct banks
     size_t per = 2 * sizeof(float2) * (size_t)lp;
-    int g = (int)(kSmemSoft / per);
-    if (g < 4) g = (int)(kSmemHard / per);
-    if (g > 16) g = 16;
+    size_t twb = sizeof(float2) * (size_t)L;  // stage twiddles live in shared memory too
+    int g = (int)((kSmemSoft - (twb < kSmemSoft ? twb : 0)) / per);
+    if (g < 4) g = (int)((kSmemHard - twb) / per);
+    if (g >= 16) g = 16;
+    else if (g >= 8) g = 8;
+    else if (g >= 4) g = 4;
     if (g < 1) g = 1;
     *G = g;
     *Lp = lp;
-    *smem = per * (size_t)g;
+    *smem = per * (size_t)g + twb;
 }
 
 // ------------------------------------------------------------------------------------
@@ -69,33 +73,88 @@ void choose_group(int L, int* G, int* Lp, size_t* smem) {
 struct PassArgs {
     SubPlanDev sp;
     int G, Lp;
+    unsigned G_rcp;
     int M1, M2;
     int groups;  // CTAs per unit
     TwoLevelTwiddle twM;
 };
 
-__device__ __forceinline__ void run_stages(const SubPlanDev& sp, int G, int Lp, float2*& a, float2*& b) {
-    const int L = sp.L;
-    int Ns = 1;
+template <int R>
+__device__ __forceinline__ void stage_loop(const SubPlanDev& sp, int s, int G, int Lp, const float2* __restrict__ a,
+                                           float2* __restrict__ b, const float2* __restrict__ tw) {
+    const int L = sp.L, Ns = sp.Ns[s], nb = sp.nb[s], tmul = sp.tmul[s];
+    const unsigned nb_rcp = sp.nb_rcp[s], ns_rcp = sp.ns_rcp[s];
+    const int total = G * nb;
+    for (int e = threadIdx.x; e < total; e += kPassThreads) {
+        const int g = (int)fast_div((unsigned)e, nb_rcp);
+        const int j = e - g * nb;
+        const int k = j - (int)fast_div((unsigned)j, ns_rcp) * Ns;
+        stockham_butterfly_pre<R>(j, k, k * tmul, nb, L, Ns, a + g * Lp, b + g * Lp, tw);
+    }
+}
+
+__device__ __forceinline__ void run_stages(const SubPlanDev& sp, int G, int Lp, float2*& a, float2*& b,
+                                           const float2* tw) {
     for (int s = 0; s < sp.nst; ++s) {
-        const int R = sp.radix[s];
-        const int nb = L / R;
-        const int total = G * nb;
-        for (int e = threadIdx.x; e < total; e += blockDim.x) {
-            const int g = e / nb;
-            const int j = e - g * nb;
-            stockham_butterfly(R, j, L, Ns, a + g * Lp, b + g * Lp, sp.tw);
+        switch (sp.radix[s]) {  // one branch per stage, not per butterfly
+            case 2: stage_loop<2>(sp, s, G, Lp, a, b, tw); break;
+            case 3: stage_loop<3>(sp, s, G, Lp, a, b, tw); break;
+            case 4: stage_loop<4>(sp, s, G, Lp, a, b, tw); break;
+            case 5: stage_loop<5>(sp, s, G, Lp, a, b, tw); break;
+            case 7: stage_loop<7>(sp, s, G, Lp, a, b, tw); break;
+            case 8: stage_loop<8>(sp, s, G, Lp, a, b, tw); break;
+            case 11: stage_loop<11>(sp, s, G, Lp, a, b, tw); break;
+            case 13: stage_loop<13>(sp, s, G, Lp, a, b, tw); break;
+            default: break;
         }
         __syncthreads();
         float2* t = a;
         a = b;
         b = t;
-        Ns *= R;
+    }
+}
+
+__device__ __forceinline__ void load_stage_twiddles(const SubPlanDev& sp, float2* tw_s) {
+    for (int m = threadIdx.x; m < sp.L; m += kPassThreads) tw_s[m] = __ldg(sp.tw + m);
+}
+
+// Source fast paths: kSrc = SRC_COMPLEX / SRC_REAL_PACKED / SRC_BAND_PACKED are inlined without the mode
+// switch and the Bluestein wrapper; kSrc = -1 is the generic accessor.
+template <int kSrc>
+__device__ __forceinline__ float2 fetch(const SrcDesc& s, long long unit, int idx) {
+    if (kSrc == SRC_COMPLEX) {
+        float2 v = (idx < s.n_valid) ? __ldg((const float2*)s.base + unit * s.unit_stride + idx) : make_float2(0.f, 0.f);
+        return s.conj ? cconj(v) : v;
+    } else if (kSrc == SRC_REAL_PACKED) {
+        const float* p = (const float*)s.base + unit * s.unit_stride;
+        const int i0 = 2 * idx;
+        float2 v;
+        if (i0 + 1 < s.n_valid) v = __ldg((const float2*)(p + i0));
+        else v = make_float2(i0 < s.n_valid ? __ldg(p + i0) : 0.f, 0.f);
+        if (s.clip) {
+            v.x = fminf(fmaxf(v.x, -1.f), 1.f);
+            v.y = fminf(fmaxf(v.y, -1.f), 1.f);
+        }
+        return v;
+    } else if (kSrc == SRC_BAND_PACKED) {
+        const long long row = unit / s.n_bands;
+        const BandDev& b = s.bands[unit - row * s.n_bands];
+        const int mk = s.M - idx;
+        const bool in_k = (idx >= b.k_first && idx <= b.k_last), in_m = (mk >= b.k_first && mk <= b.k_last);
+        if (!in_k && !in_m) return make_float2(0.f, 0.f);
+        const float2* X = (const float2*)s.base + row * s.unit_stride;
+        float2 yk = band_Y(s, X, b, idx);
+        float2 ym = band_Y(s, X, b, mk);
+        float2 v = pack_half_spectrum(yk, ym, twiddle2(s.twN, idx));
+        return s.conj ? cconj(v) : v;
+    } else {
+        return src_get(s, unit, idx);
     }
 }
 
 // pass 1: columns.  CTA = G adjacent columns n2 of one unit; M1-point FFT over n1; twiddle; store [k1*M2 + n2].
-__global__ void __launch_bounds__(kPassThreads) fft_pass1_kernel(PassArgs pa, SrcDesc src, float2* scratch,
+template <int kSrc>
+__global__ void __launch_bounds__(kPassThreads, 4) fft_pass1_kernel(PassArgs pa, SrcDesc src, float2* __restrict__ scratch,
                                                                  long long scratch_stride) {
     extern __shared__ float2 smem[];
     const long long unit = blockIdx.x / pa.groups;
@@ -104,31 +163,37 @@ __global__ void __launch_bounds__(kPassThreads) fft_pass1_kernel(PassArgs pa, Sr
     const int L = pa.sp.L, G = pa.G, Lp = pa.Lp;
     float2* a = smem;
     float2* b = smem + (size_t)G * Lp;
-    for (int e = threadIdx.x; e < G * L; e += blockDim.x) {
-        const int i = e / G;
+    float2* tw_s = b + (size_t)G * Lp;
+    load_stage_twiddles(pa.sp, tw_s);
+    const int total = G * L;
+#pragma unroll 4
+    for (int e = threadIdx.x; e < total; e += kPassThreads) {
+        const int i = (int)fast_div((unsigned)e, pa.G_rcp);
         const int g = e - i * G;
         const int col = col0 + g;
         float2 v = make_float2(0.f, 0.f);
-        if (col < pa.M2) v = src_get(src, unit, (int)pass1_src_index(pa.M2, col, i));
+        if (col < pa.M2) v = fetch<kSrc>(src, unit, i * pa.M2 + col);
         a[g * Lp + i] = v;
     }
     __syncthreads();
-    run_stages(pa.sp, G, Lp, a, b);
-    float2* out = scratch + unit * scratch_stride;
-    for (int e = threadIdx.x; e < G * L; e += blockDim.x) {
-        const int i = e / G;
+    run_stages(pa.sp, G, Lp, a, b, tw_s);
+    float2* __restrict__ out = scratch + unit * scratch_stride;
+#pragma unroll 4
+    for (int e = threadIdx.x; e < total; e += kPassThreads) {
+        const int i = (int)fast_div((unsigned)e, pa.G_rcp);
         const int g = e - i * G;
         const int col = col0 + g;
         if (col < pa.M2) {
-            float2 v = a[g * Lp + i];
-            v = cmul(v, twiddle2(pa.twM, (long long)col * i));
-            out[pass1_dst_index(pa.M2, col, i)] = v;
+            float2 v = cmul(a[g * Lp + i], twiddle2(pa.twM, (long long)col * i));
+            out[(long long)i * pa.M2 + col] = v;
         }
     }
 }
 
 // pass 2: rows.  CTA = G adjacent rows k1 of one unit; M2-point FFT over n2; store [k1 + M1*k2].
-__global__ void __launch_bounds__(kPassThreads) fft_pass2_kernel(PassArgs pa, SrcDesc src, DstDesc dst) {
+// kDst = DST_COMPLEX inlines the plain conj/scale store; -1 is the generic sink.
+template <int kSrc, int kDst>
+__global__ void __launch_bounds__(kPassThreads, 4) fft_pass2_kernel(PassArgs pa, SrcDesc src, DstDesc dst) {
     extern __shared__ float2 smem[];
     const long long unit = blockIdx.x / pa.groups;
     const int rg = blockIdx.x - (int)(unit * pa.groups);
@@ -136,31 +201,64 @@ __global__ void __launch_bounds__(kPassThreads) fft_pass2_kernel(PassArgs pa, Sr
     const int L = pa.sp.L, G = pa.G, Lp = pa.Lp;
     float2* a = smem;
     float2* b = smem + (size_t)G * Lp;
-    for (int e = threadIdx.x; e < G * L; e += blockDim.x) {
-        const int g = e / L;
+    float2* tw_s = b + (size_t)G * Lp;
+    load_stage_twiddles(pa.sp, tw_s);
+    const int total = G * L;
+#pragma unroll 4
+    for (int e = threadIdx.x; e < total; e += kPassThreads) {
+        const int g = (int)fast_div((unsigned)e, pa.sp.L_rcp);
         const int i = e - g * L;
         const int row = row0 + g;
         float2 v = make_float2(0.f, 0.f);
-        if (row < pa.M1) v = src_get(src, unit, (int)pass2_src_index(pa.M2, row, i));
+        if (row < pa.M1) v = fetch<kSrc>(src, unit, row * pa.M2 + i);
         a[g * Lp + i] = v;
     }
     __syncthreads();
-    run_stages(pa.sp, G, Lp, a, b);
-    for (int e = threadIdx.x; e < G * L; e += blockDim.x) {
-        const int i = e / G;
+    run_stages(pa.sp, G, Lp, a, b, tw_s);
+#pragma unroll 4
+    for (int e = threadIdx.x; e < total; e += kPassThreads) {
+        const int i = (int)fast_div((unsigned)e, pa.G_rcp);
         const int g = e - i * G;
         const int row = row0 + g;
-        if (row < pa.M1) dst_put(dst, unit, (int)pass2_dst_index(pa.M1, row, i), a[g * Lp + i]);
+        if (row < pa.M1) {
+            const int idx = i * pa.M1 + row;
+            float2 v = a[g * Lp + i];
+            if (kDst == DST_COMPLEX) {
+                if (idx < dst.n_valid) {
+                    if (dst.conj1) v = cconj(v);
+                    ((float2*)dst.base)[unit * dst.unit_stride + idx] = cscale(v, dst.scale1);
+                }
+            } else {
+                dst_put(dst, unit, idx, v);
+            }
+        }
     }
+}
+
+template <typename K>
+int set_smem(K kernel) {
+    AA_CUDA_TRY(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemHard));
+    return AA_OK;
 }
 
 int configure_kernels_once() {
     static bool done = false;
     if (done) return AA_OK;
-    AA_CUDA_TRY(cudaFuncSetAttribute(fft_pass1_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemHard));
-    AA_CUDA_TRY(cudaFuncSetAttribute(fft_pass2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemHard));
+    int rc;
+    if ((rc = set_smem(fft_pass1_kernel<SRC_COMPLEX>)) != AA_OK) return rc;
+    if ((rc = set_smem(fft_pass1_kernel<SRC_REAL_PACKED>)) != AA_OK) return rc;
+    if ((rc = set_smem(fft_pass1_kernel<SRC_BAND_PACKED>)) != AA_OK) return rc;
+    if ((rc = set_smem(fft_pass1_kernel<-1>)) != AA_OK) return rc;
+    if ((rc = set_smem(fft_pass2_kernel<SRC_COMPLEX, DST_COMPLEX>)) != AA_OK) return rc;
+    if ((rc = set_smem(fft_pass2_kernel<SRC_COMPLEX, -1>)) != AA_OK) return rc;
+    if ((rc = set_smem(fft_pass2_kernel<-1, DST_COMPLEX>)) != AA_OK) return rc;
+    if ((rc = set_smem(fft_pass2_kernel<-1, -1>)) != AA_OK) return rc;
     done = true;
     return AA_OK;
+}
+
+bool plain_complex_dst(const DstDesc& d) {
+    return d.mode == DST_COMPLEX && d.chirp == nullptr && d.conj2 == 0 && d.scale2 == 1.0f;
 }
 
 int exec_direct(const C2CPlan* p, const SrcDesc& src, const DstDesc& dst, long long units, float2* scratch,
@@ -173,26 +271,47 @@ int exec_direct(const C2CPlan* p, const SrcDesc& src, const DstDesc& dst, long l
     pa.M2 = p->M2;
     pa.twM = p->twM.dev;
     SrcDesc src2 = src;
+    const bool fast_src = (src.chirp == nullptr);
     if (p->M1 > 1) {
         AA_REQUIRE(scratch != nullptr, AA_ERR_WORKSPACE, "fft scratch missing");
         pa.sp = p->s1.dev;
         pa.G = p->G1;
+        pa.G_rcp = fast_rcp((unsigned)p->G1);
         pa.Lp = p->Lp1;
         pa.groups = (p->M2 + p->G1 - 1) / p->G1;
         long long grid = units * pa.groups;
         AA_REQUIRE(grid < 2147483647LL, AA_ERR_INVALID_ARGUMENT, "fft grid too large");
-        fft_pass1_kernel<<<(unsigned)grid, kPassThreads, p->smem1, stream>>>(pa, src, scratch, (long long)p->M);
+        const unsigned g = (unsigned)grid;
+        if (fast_src && src.mode == SRC_COMPLEX)
+            fft_pass1_kernel<SRC_COMPLEX><<<g, kPassThreads, p->smem1, stream>>>(pa, src, scratch, (long long)p->M);
+        else if (fast_src && src.mode == SRC_REAL_PACKED)
+            fft_pass1_kernel<SRC_REAL_PACKED><<<g, kPassThreads, p->smem1, stream>>>(pa, src, scratch, (long long)p->M);
+        else if (fast_src && src.mode == SRC_BAND_PACKED)
+            fft_pass1_kernel<SRC_BAND_PACKED><<<g, kPassThreads, p->smem1, stream>>>(pa, src, scratch, (long long)p->M);
+        else
+            fft_pass1_kernel<-1><<<g, kPassThreads, p->smem1, stream>>>(pa, src, scratch, (long long)p->M);
         rc = launch_check("fft_pass1_kernel");
         if (rc != AA_OK) return rc;
         src2 = make_src_complex(scratch, p->M, p->M, 0);
     }
     pa.sp = p->s2.dev;
     pa.G = p->G2;
+    pa.G_rcp = fast_rcp((unsigned)p->G2);
     pa.Lp = p->Lp2;
     pa.groups = (p->M1 + p->G2 - 1) / p->G2;
     long long grid = units * pa.groups;
     AA_REQUIRE(grid < 2147483647LL, AA_ERR_INVALID_ARGUMENT, "fft grid too large");
-    fft_pass2_kernel<<<(unsigned)grid, kPassThreads, p->smem2, stream>>>(pa, src2, dst);
+    const unsigned g = (unsigned)grid;
+    const bool src_plain = (src2.mode == SRC_COMPLEX && src2.chirp == nullptr);
+    const bool dst_plain = plain_complex_dst(dst);
+    if (src_plain && dst_plain)
+        fft_pass2_kernel<SRC_COMPLEX, DST_COMPLEX><<<g, kPassThreads, p->smem2, stream>>>(pa, src2, dst);
+    else if (src_plain)
+        fft_pass2_kernel<SRC_COMPLEX, -1><<<g, kPassThreads, p->smem2, stream>>>(pa, src2, dst);
+    else if (dst_plain)
+        fft_pass2_kernel<-1, DST_COMPLEX><<<g, kPassThreads, p->smem2, stream>>>(pa, src2, dst);
+    else
+        fft_pass2_kernel<-1, -1><<<g, kPassThreads, p->smem2, stream>>>(pa, src2, dst);
     return launch_check("fft_pass2_kernel");
 }
 

@@ -19,7 +19,39 @@ struct SubPlanDev {
     int nst;                 // number of stages
     int radix[kMaxStages];   // each in {2,3,4,5,7,8,11,13}
     const float2* tw;        // exp(-2*pi*i*m/L), m in [0, L)
+    // per stage, filled by fill_stage_constants(): Ns = product of earlier radices, nb = L / radix,
+    // tmul = L / (Ns * radix), and multiply-high reciprocals for the two divisions in the butterfly loop
+    int Ns[kMaxStages];
+    int nb[kMaxStages];
+    int tmul[kMaxStages];
+    unsigned nb_rcp[kMaxStages];
+    unsigned ns_rcp[kMaxStages];
+    unsigned L_rcp;
 };
+
+// q = n / d through one multiply-high: rcp = ceil(2^32 / d), exact while n * d < 2^32; d == 1 -> rcp = 0
+AA_HD unsigned fast_rcp(unsigned d) { return d <= 1 ? 0u : (unsigned)((0x100000000ULL + d - 1) / d); }
+AA_HD unsigned fast_div(unsigned n, unsigned rcp) {
+#ifdef __CUDA_ARCH__
+    return rcp ? __umulhi(n, rcp) : n;
+#else
+    return rcp ? (unsigned)(((unsigned long long)n * rcp) >> 32) : n;
+#endif
+}
+
+inline void fill_stage_constants(SubPlanDev* sp) {
+    int Ns = 1;
+    for (int s = 0; s < sp->nst; ++s) {
+        const int R = sp->radix[s];
+        sp->Ns[s] = Ns;
+        sp->nb[s] = sp->L / R;
+        sp->tmul[s] = sp->L / (Ns * R);
+        sp->nb_rcp[s] = fast_rcp((unsigned)(sp->L / R));
+        sp->ns_rcp[s] = fast_rcp((unsigned)Ns);
+        Ns *= R;
+    }
+    sp->L_rcp = fast_rcp((unsigned)sp->L);
+}
 
 AA_HD float2 cmul(float2 a, float2 b) { return make_float2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x); }
 AA_HD float2 cmulc(float2 a, float2 b) { return make_float2(a.x * b.x + a.y * b.y, a.y * b.x - a.x * b.y); }  // a*conj(b)
@@ -119,6 +151,27 @@ AA_HD void stockham_butterfly_fixed(int j, int L, int Ns, const float2* src, flo
     const int T = L / R;
     const int k = j % Ns;
     const int tstep = k * (L / (Ns * R));  // twiddle exp(-2 pi i r k / (Ns R)) = tw[r * tstep]
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+        float2 x = src[j + r * T];
+        v[r] = (r == 0 || tstep == 0) ? x : cmul(x, tw[r * tstep]);
+    }
+    if (R == 2) dft2(v);
+    else if (R == 3) dft3(v);
+    else if (R == 4) dft4(v);
+    else if (R == 5) dft5(v);
+    else if (R == 8) dft8(v);
+    else dft_generic(v, R, tw, L);
+    const int base = (j - k) * R + k;
+#pragma unroll
+    for (int r = 0; r < R; ++r) dst[base + r * Ns] = v[r];
+}
+
+// Same butterfly with k = j % Ns and the twiddle step supplied by the caller (no division here).
+template <int R>
+AA_HD void stockham_butterfly_pre(int j, int k, int tstep, int T, int L, int Ns, const float2* src, float2* dst,
+                                  const float2* tw) {
+    float2 v[R];
 #pragma unroll
     for (int r = 0; r < R; ++r) {
         float2 x = src[j + r * T];

@@ -34,13 +34,44 @@ static TwoLevelTwiddle dev_view(const HostTwoLevel& t) {
     return d;
 }
 
+template <int R>
+static void emu_stage(const SubPlanDev& d, int s, const float2* a, float2* b) {
+    // mirrors stage_loop<R> in fft.cu: multiply-high division, precomputed twiddle step
+    for (int e = 0; e < d.nb[s]; ++e) {
+        const int g = (int)fast_div((unsigned)e, d.nb_rcp[s]);
+        const int j = e - g * d.nb[s];
+        const int k = j - (int)fast_div((unsigned)j, d.ns_rcp[s]) * d.Ns[s];
+        if (g != 0) { printf("fast_div broke at e=%d\n", e); exit(2); }
+        stockham_butterfly_pre<R>(j, k, k * d.tmul[s], d.nb[s], d.L, d.Ns[s], a, b, d.tw);
+    }
+}
+
 static void emu_stages(const HostSubPlan& sp, std::vector<float2>& a, std::vector<float2>& b) {
-    int Ns = 1;
+    SubPlanDev d{};
+    d.L = sp.L;
+    d.nst = sp.nst;
+    for (int s = 0; s < sp.nst; ++s) d.radix[s] = sp.radix[s];
+    d.tw = sp.tw.data();
+    fill_stage_constants(&d);
     for (int s = 0; s < sp.nst; ++s) {
-        int R = sp.radix[s];
-        for (int j = 0; j < sp.L / R; ++j) stockham_butterfly(R, j, sp.L, Ns, a.data(), b.data(), sp.tw.data());
+        switch (sp.radix[s]) {
+            case 2: emu_stage<2>(d, s, a.data(), b.data()); break;
+            case 3: emu_stage<3>(d, s, a.data(), b.data()); break;
+            case 4: emu_stage<4>(d, s, a.data(), b.data()); break;
+            case 5: emu_stage<5>(d, s, a.data(), b.data()); break;
+            case 7: emu_stage<7>(d, s, a.data(), b.data()); break;
+            case 8: emu_stage<8>(d, s, a.data(), b.data()); break;
+            case 11: emu_stage<11>(d, s, a.data(), b.data()); break;
+            case 13: emu_stage<13>(d, s, a.data(), b.data()); break;
+            default: printf("bad radix\n"); exit(2);
+        }
         a.swap(b);
-        Ns *= R;
+    }
+    // exhaustive check of the multiply-high division for every index the kernels can form
+    for (unsigned dd = 1; dd <= 4096; dd += (dd < 64 ? 1 : 37)) {
+        unsigned r = fast_rcp(dd);
+        for (unsigned n = 0; n < 70000; n += 13)
+            if (fast_div(n, r) != n / dd) { printf("fast_div(%u,%u) wrong\n", n, dd); exit(2); }
     }
 }
 
