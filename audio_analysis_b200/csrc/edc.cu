@@ -26,6 +26,7 @@
 // the curve is monotone across tile boundaries.
 #include <cooperative_groups.h>
 #include <math.h>
+#include <stdlib.h>
 
 #include "aa_common.cuh"
 #include "fit_math.cuh"
@@ -575,10 +576,26 @@ __global__ void __launch_bounds__(256) peak_kernel(const float* __restrict__ xs,
 }
 
 int pick_cluster(int max_len) {
+    if (const char* env = getenv("AA_EDC_CLUSTER")) {  // tuning override: 1, 2, 4 or 8 CTAs per row
+        int t = atoi(env);
+        if (t == 1 || t == 2 || t == 4 || t == 8) return t;
+    }
     if (max_len <= 16384) return 1;
     if (max_len <= 65536) return 2;
     if (max_len <= 131072) return 4;
     return kMaxCluster;
+}
+
+// Many rows: one CTA per row keeps every SM streaming (no cluster barriers on the critical path);
+// few rows: split each row over a cluster so the whole chip works on them and the row stays in L2.
+int pick_cluster_for_batch(int max_len, int n_rows) {
+    if (getenv("AA_EDC_CLUSTER")) return pick_cluster(max_len);
+    const int t = pick_cluster(max_len);
+    if (n_rows >= 2 * 148) {
+        const size_t dyn1 = (size_t)((max_len + kTile - 1) / kTile + kWarps) * (sizeof(double) + sizeof(float));
+        if (dyn1 <= 100 * 1024) return 1;
+    }
+    return t;
 }
 
 }  // namespace
@@ -637,7 +654,7 @@ int launch_edc(const float* d_x, long long row_stride, const int* d_lengths, int
         a.target[3 + 2 * f] = lo > p->fit_lower_limit_db ? lo : p->fit_lower_limit_db;  // decay.py:219
     }
 
-    const int T = pick_cluster(max_len);
+    const int T = pick_cluster_for_batch(max_len, n_rows);
     const int nt_max = (max_len + kTile - 1) / kTile;
     int tpw = (nt_max + T * kWarps - 1) / (T * kWarps);
     if (tpw < 1) tpw = 1;

@@ -235,6 +235,147 @@ __global__ void __launch_bounds__(kPassThreads, 4) fft_pass2_kernel(PassArgs pa,
     }
 }
 
+// ------------------------------------------------------------------------------------
+// compile-time specialised passes for the hot lengths (everything else uses the kernels above)
+// ------------------------------------------------------------------------------------
+
+template <int L, int G, int Lp, int Ns>
+__device__ __forceinline__ void spec_stages(float2*& a, float2*& b, const float2* tw) {}
+
+template <int L, int G, int Lp, int Ns, int R, int... Rest>
+__device__ __forceinline__ void spec_stages(float2*& a, float2*& b, const float2* __restrict__ tw) {
+    constexpr int nb = L / R, tmul = L / (Ns * R), total = G * nb;
+#pragma unroll 2
+    for (int e = threadIdx.x; e < total; e += kPassThreads) {
+        const int g = e / nb;  // constant divisors: multiply-shift
+        const int j = e - g * nb;
+        const int k = j % Ns;
+        stockham_butterfly_pre<R>(j, k, k * tmul, nb, L, Ns, a + g * Lp, b + g * Lp, tw);
+    }
+    __syncthreads();
+    float2* t = a;
+    a = b;
+    b = t;
+    spec_stages<L, G, Lp, Ns * R, Rest...>(a, b, tw);
+}
+
+template <int L, int G>
+constexpr size_t spec_smem() { return sizeof(float2) * ((size_t)2 * G * (L | 1) + L); }
+
+template <int kSrc, int M1, int M2, int G, int... Rs>
+__global__ void __launch_bounds__(kPassThreads, 4) fft_pass1_spec(SrcDesc src, float2* __restrict__ scratch,
+                                                                   TwoLevelTwiddle twM, const float2* __restrict__ tw_g) {
+    constexpr int L = M1, Lp = L | 1, groups = (M2 + G - 1) / G, total = G * L;
+    extern __shared__ float2 smem[];
+    const int unit = blockIdx.x / groups;
+    const int col0 = (blockIdx.x - unit * groups) * G;
+    float2* a = smem;
+    float2* b = smem + G * Lp;
+    float2* tw_s = b + G * Lp;
+    for (int m = threadIdx.x; m < L; m += kPassThreads) tw_s[m] = __ldg(tw_g + m);
+#pragma unroll 4
+    for (int e = threadIdx.x; e < total; e += kPassThreads) {
+        const int i = e / G, g = e % G;
+        const int col = col0 + g;
+        float2 v = make_float2(0.f, 0.f);
+        if (M2 % G == 0 || col < M2) v = fetch<kSrc>(src, unit, i * M2 + col);
+        a[g * Lp + i] = v;
+    }
+    __syncthreads();
+    spec_stages<L, G, Lp, 1, Rs...>(a, b, tw_s);
+    float2* __restrict__ out = scratch + (size_t)unit * ((size_t)M1 * M2);
+#pragma unroll 4
+    for (int e = threadIdx.x; e < total; e += kPassThreads) {
+        const int i = e / G, g = e % G;
+        const int col = col0 + g;
+        if (M2 % G == 0 || col < M2) out[i * M2 + col] = cmul(a[g * Lp + i], twiddle2(twM, (long long)(col * i)));
+    }
+}
+
+template <int M1, int M2, int G, int... Rs>
+__global__ void __launch_bounds__(kPassThreads, 4) fft_pass2_spec(const float2* __restrict__ scratch,
+                                                                   float2* __restrict__ out, long long out_stride,
+                                                                   int n_valid, int conj, float scale,
+                                                                   const float2* __restrict__ tw_g) {
+    constexpr int L = M2, Lp = L | 1, groups = (M1 + G - 1) / G, total = G * L;
+    extern __shared__ float2 smem[];
+    const int unit = blockIdx.x / groups;
+    const int row0 = (blockIdx.x - unit * groups) * G;
+    float2* a = smem;
+    float2* b = smem + G * Lp;
+    float2* tw_s = b + G * Lp;
+    for (int m = threadIdx.x; m < L; m += kPassThreads) tw_s[m] = __ldg(tw_g + m);
+    const float2* __restrict__ in = scratch + (size_t)unit * ((size_t)M1 * M2);
+#pragma unroll 4
+    for (int e = threadIdx.x; e < total; e += kPassThreads) {
+        const int g = e / L, i = e % L;
+        const int row = row0 + g;
+        float2 v = make_float2(0.f, 0.f);
+        if (M1 % G == 0 || row < M1) v = __ldg(in + row * M2 + i);
+        a[g * Lp + i] = v;
+    }
+    __syncthreads();
+    spec_stages<L, G, Lp, 1, Rs...>(a, b, tw_s);
+    float2* __restrict__ o = out + (size_t)unit * out_stride;
+#pragma unroll 4
+    for (int e = threadIdx.x; e < total; e += kPassThreads) {
+        const int i = e / G, g = e % G;
+        const int row = row0 + g;
+        const int idx = i * M1 + row;
+        if ((M1 % G == 0 || row < M1) && idx < n_valid) {
+            float2 v = a[g * Lp + i];
+            if (conj) v.y = -v.y;
+            o[idx] = cscale(v, scale);
+        }
+    }
+}
+
+// (M1, M2) pairs with specialised kernels.  Radix chains start with an odd radix where there is one:
+// a first stage of radix 8 writes shared memory with stride 8 (an 8-way bank conflict).
+#define AA_SPEC_LIST(X)                      \
+    X(375, 384, 8, (3, 5, 5, 5), (3, 8, 4, 4)) /* N = 288000 */ \
+    X(300, 320, 8, (3, 5, 5, 4), (5, 8, 8))    /* N = 192000 */
+
+#define AA_UNPACK(...) __VA_ARGS__
+
+template <int kSrc>
+bool launch_pass1_spec(const C2CPlan* p, const SrcDesc& src, float2* scratch, long long units, cudaStream_t stream) {
+#define X(m1, m2, g, r1, r2)                                                                                   \
+    if (p->M1 == m1 && p->M2 == m2) {                                                                          \
+        auto k = fft_pass1_spec<kSrc, m1, m2, g, AA_UNPACK r1>;                                               \
+        static bool once = false;                                                                              \
+        if (!once) {                                                                                           \
+            cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)spec_smem<m1, g>());   \
+            once = true;                                                                                       \
+        }                                                                                                      \
+        k<<<(unsigned)(units * ((m2 + g - 1) / g)), kPassThreads, spec_smem<m1, g>(), stream>>>(               \
+            src, scratch, p->twM.dev, p->s1.dev.tw);                                                           \
+        return true;                                                                                           \
+    }
+    AA_SPEC_LIST(X)
+#undef X
+    return false;
+}
+
+bool launch_pass2_spec(const C2CPlan* p, const float2* scratch, const DstDesc& dst, long long units,
+                       cudaStream_t stream) {
+#define X(m1, m2, g, r1, r2)                                                                                   \
+    if (p->M1 == m1 && p->M2 == m2) {                                                                          \
+        auto k = fft_pass2_spec<m1, m2, g, AA_UNPACK r2>;                                                     \
+        static bool once = false;                                                                              \
+        if (!once) {                                                                                           \
+            cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)spec_smem<m2, g>());   \
+            once = true;                                                                                       \
+        }                                                                                                      \
+        k<<<(unsigned)(units * ((m1 + g - 1) / g)), kPassThreads, spec_smem<m2, g>(), stream>>>(               \
+            scratch, (float2*)dst.base, dst.unit_stride, dst.n_valid, dst.conj1, dst.scale1, p->s2.dev.tw);    \
+        return true;                                                                                           \
+    }
+    AA_SPEC_LIST(X)
+#undef X
+    return false;
+}
+
 template <typename K>
 int set_smem(K kernel) {
     AA_CUDA_TRY(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemHard));
@@ -282,7 +423,12 @@ int exec_direct(const C2CPlan* p, const SrcDesc& src, const DstDesc& dst, long l
         long long grid = units * pa.groups;
         AA_REQUIRE(grid < 2147483647LL, AA_ERR_INVALID_ARGUMENT, "fft grid too large");
         const unsigned g = (unsigned)grid;
-        if (fast_src && src.mode == SRC_COMPLEX)
+        const bool use_spec = getenv("AA_FFT_GENERIC") == nullptr && units * (long long)p->M < 2147483647LL;
+        if (use_spec && fast_src && src.mode == SRC_BAND_PACKED &&
+            launch_pass1_spec<SRC_BAND_PACKED>(p, src, scratch, units, stream)) {
+        } else if (use_spec && fast_src && src.mode == SRC_REAL_PACKED &&
+                   launch_pass1_spec<SRC_REAL_PACKED>(p, src, scratch, units, stream)) {
+        } else if (fast_src && src.mode == SRC_COMPLEX)
             fft_pass1_kernel<SRC_COMPLEX><<<g, kPassThreads, p->smem1, stream>>>(pa, src, scratch, (long long)p->M);
         else if (fast_src && src.mode == SRC_REAL_PACKED)
             fft_pass1_kernel<SRC_REAL_PACKED><<<g, kPassThreads, p->smem1, stream>>>(pa, src, scratch, (long long)p->M);
@@ -304,7 +450,11 @@ int exec_direct(const C2CPlan* p, const SrcDesc& src, const DstDesc& dst, long l
     const unsigned g = (unsigned)grid;
     const bool src_plain = (src2.mode == SRC_COMPLEX && src2.chirp == nullptr);
     const bool dst_plain = plain_complex_dst(dst);
-    if (src_plain && dst_plain)
+    const bool spec2 = getenv("AA_FFT_GENERIC") == nullptr && p->M1 > 1 && src_plain && dst_plain &&
+                       units * (long long)p->M < 2147483647LL &&
+                       launch_pass2_spec(p, scratch, dst, units, stream);
+    if (spec2) {
+    } else if (src_plain && dst_plain)
         fft_pass2_kernel<SRC_COMPLEX, DST_COMPLEX><<<g, kPassThreads, p->smem2, stream>>>(pa, src2, dst);
     else if (src_plain)
         fft_pass2_kernel<SRC_COMPLEX, -1><<<g, kPassThreads, p->smem2, stream>>>(pa, src2, dst);

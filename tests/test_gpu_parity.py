@@ -218,6 +218,32 @@ def test_rt60bands_batch_third_octave_matches_oracle():
         check_band_table(f"synth{i}", have, want)
 
 
+@pytest.mark.parametrize("n", [288000, 192000])
+def test_rt60bands_specialised_fft_lengths_match_oracle(n):
+    """Config-5 (288,000) and config-3 (192,000) row lengths run the compile-time specialised FFT passes."""
+    from audio_analysis_b200 import engine, rt60bands as rb
+    from audio_analysis_b200.synth import synth_batch_numpy
+    x = synth_batch_numpy(2, n, SR, first_index=40)
+    s = rb.Rt60BandsAnalysisSettings(band_mode="third", include_t20=True, include_edt=True)
+    rows = engine.make_rows(x)
+    metrics, bands, plan, start, sig = rb.run_rt60_bands(rows, SR, s, want_band_signals=True)
+    got = metrics.cpu().numpy()
+    sig = sig.cpu().numpy()
+    p = oracle.BandParams(band_mode="third", include_t20=True, include_edt=True)
+    freqs = np.fft.rfftfreq(n, d=1.0 / SR).astype(np.float32)
+    for i in range(2):
+        w = oracle.band_metrics(x[i], SR, p)
+        names = [b["name"] for b in w["bands"]]
+        want = np.array([[np.nan if v is None else v for v in w["metrics"][nm]] for nm in names])
+        check_band_table(f"n{n}/{i}", got[i], want)
+        spec = np.fft.rfft(x[i].astype(np.float64))
+        for k in (0, 12, 25):
+            ref = oracle.band_filter(x[i], oracle.band_mask(freqs, w["bands"][k], 1.0 / 6.0, 0.5 * SR), spec)
+            err = float(np.max(np.abs(sig[i, k] - ref))) / (float(np.max(np.abs(ref))) + 1e-30)
+            note(f"band_signal_max_err_rel_to_peak[n{n}]", err)
+            assert err < 2e-5
+
+
 def test_rt60bands_smoothing_and_ignore_match_oracle():
     from audio_analysis_b200 import decay, rt60bands as rb
     g = load_golden("smooth_60000")
