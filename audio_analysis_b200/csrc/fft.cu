@@ -13,6 +13,7 @@
 
 #include "fft.cuh"
 #include "fft_plan_host.hpp"
+#include "fft_spec.cuh"
 
 namespace aa {
 
@@ -82,14 +83,15 @@ struct PassArgs {
 template <int R>
 __device__ __forceinline__ void stage_loop(const SubPlanDev& sp, int s, int G, int Lp, const float2* __restrict__ a,
                                            float2* __restrict__ b, const float2* __restrict__ tw) {
-    const int L = sp.L, Ns = sp.Ns[s], nb = sp.nb[s], tmul = sp.tmul[s];
+    const int L = sp.L, Ns = sp.Ns[s], nb = sp.nb[s];
     const unsigned nb_rcp = sp.nb_rcp[s], ns_rcp = sp.ns_rcp[s];
     const int total = G * nb;
+    const float2* twc = tw + compact_twiddle_offset(Ns);
     for (int e = threadIdx.x; e < total; e += kPassThreads) {
         const int g = (int)fast_div((unsigned)e, nb_rcp);
         const int j = e - g * nb;
         const int k = j - (int)fast_div((unsigned)j, ns_rcp) * Ns;
-        stockham_butterfly_pre<R>(j, k, k * tmul, nb, L, Ns, a + g * Lp, b + g * Lp, tw);
+        stockham_butterfly_compact<R, 0>(j, k, nb, L, Ns, a + g * Lp, b + g * Lp, twc, sp.tw);
     }
 }
 
@@ -101,6 +103,7 @@ __device__ __forceinline__ void run_stages(const SubPlanDev& sp, int G, int Lp, 
             case 3: stage_loop<3>(sp, s, G, Lp, a, b, tw); break;
             case 4: stage_loop<4>(sp, s, G, Lp, a, b, tw); break;
             case 5: stage_loop<5>(sp, s, G, Lp, a, b, tw); break;
+            case 6: stage_loop<6>(sp, s, G, Lp, a, b, tw); break;
             case 7: stage_loop<7>(sp, s, G, Lp, a, b, tw); break;
             case 8: stage_loop<8>(sp, s, G, Lp, a, b, tw); break;
             case 11: stage_loop<11>(sp, s, G, Lp, a, b, tw); break;
@@ -114,8 +117,18 @@ __device__ __forceinline__ void run_stages(const SubPlanDev& sp, int G, int Lp, 
     }
 }
 
+// compact per-stage twiddles: stage with Ns earlier points holds w_{Ns R}^{r k} at [Ns - 1 + (r - 1) Ns + k]
 __device__ __forceinline__ void load_stage_twiddles(const SubPlanDev& sp, float2* tw_s) {
-    for (int m = threadIdx.x; m < sp.L; m += kPassThreads) tw_s[m] = __ldg(sp.tw + m);
+    for (int s = 0; s < sp.nst; ++s) {
+        const int Ns = sp.Ns[s], R = sp.radix[s], tmul = sp.tmul[s];
+        const unsigned ns_rcp = sp.ns_rcp[s];
+        float2* t = tw_s + compact_twiddle_offset(Ns);
+        for (int m = threadIdx.x; m < Ns * (R - 1); m += kPassThreads) {
+            const int r1 = (int)fast_div((unsigned)m, ns_rcp);
+            const int k = m - r1 * Ns;
+            t[m] = __ldg(sp.tw + (r1 + 1) * k * tmul);
+        }
+    }
 }
 
 // Source fast paths: kSrc = SRC_COMPLEX / SRC_REAL_PACKED / SRC_BAND_PACKED are inlined without the mode
@@ -239,26 +252,6 @@ __global__ void __launch_bounds__(kPassThreads, 4) fft_pass2_kernel(PassArgs pa,
 // compile-time specialised passes for the hot lengths (everything else uses the kernels above)
 // ------------------------------------------------------------------------------------
 
-template <int L, int G, int Lp, int Ns>
-__device__ __forceinline__ void spec_stages(float2*& a, float2*& b, const float2* tw) {}
-
-template <int L, int G, int Lp, int Ns, int R, int... Rest>
-__device__ __forceinline__ void spec_stages(float2*& a, float2*& b, const float2* __restrict__ tw) {
-    constexpr int nb = L / R, tmul = L / (Ns * R), total = G * nb;
-#pragma unroll 2
-    for (int e = threadIdx.x; e < total; e += kPassThreads) {
-        const int g = e / nb;  // constant divisors: multiply-shift
-        const int j = e - g * nb;
-        const int k = j % Ns;
-        stockham_butterfly_pre<R>(j, k, k * tmul, nb, L, Ns, a + g * Lp, b + g * Lp, tw);
-    }
-    __syncthreads();
-    float2* t = a;
-    a = b;
-    b = t;
-    spec_stages<L, G, Lp, Ns * R, Rest...>(a, b, tw);
-}
-
 template <int L, int G>
 constexpr size_t spec_smem() { return sizeof(float2) * ((size_t)2 * G * (L | 1) + L); }
 
@@ -272,7 +265,7 @@ __global__ void __launch_bounds__(kPassThreads, 4) fft_pass1_spec(SrcDesc src, f
     float2* a = smem;
     float2* b = smem + G * Lp;
     float2* tw_s = b + G * Lp;
-    for (int m = threadIdx.x; m < L; m += kPassThreads) tw_s[m] = __ldg(tw_g + m);
+    spec_twiddles<L, 1, Rs...>(tw_s, tw_g);
 #pragma unroll 4
     for (int e = threadIdx.x; e < total; e += kPassThreads) {
         const int i = e / G, g = e % G;
@@ -282,7 +275,7 @@ __global__ void __launch_bounds__(kPassThreads, 4) fft_pass1_spec(SrcDesc src, f
         a[g * Lp + i] = v;
     }
     __syncthreads();
-    spec_stages<L, G, Lp, 1, Rs...>(a, b, tw_s);
+    spec_stages<kPassThreads, 0, L, G, Lp, 1, Rs...>(a, b, tw_s, tw_g);
     float2* __restrict__ out = scratch + (size_t)unit * ((size_t)M1 * M2);
 #pragma unroll 4
     for (int e = threadIdx.x; e < total; e += kPassThreads) {
@@ -304,7 +297,7 @@ __global__ void __launch_bounds__(kPassThreads, 4) fft_pass2_spec(const float2* 
     float2* a = smem;
     float2* b = smem + G * Lp;
     float2* tw_s = b + G * Lp;
-    for (int m = threadIdx.x; m < L; m += kPassThreads) tw_s[m] = __ldg(tw_g + m);
+    spec_twiddles<L, 1, Rs...>(tw_s, tw_g);
     const float2* __restrict__ in = scratch + (size_t)unit * ((size_t)M1 * M2);
 #pragma unroll 4
     for (int e = threadIdx.x; e < total; e += kPassThreads) {
@@ -315,7 +308,7 @@ __global__ void __launch_bounds__(kPassThreads, 4) fft_pass2_spec(const float2* 
         a[g * Lp + i] = v;
     }
     __syncthreads();
-    spec_stages<L, G, Lp, 1, Rs...>(a, b, tw_s);
+    spec_stages<kPassThreads, 0, L, G, Lp, 1, Rs...>(a, b, tw_s, tw_g);
     float2* __restrict__ o = out + (size_t)unit * out_stride;
 #pragma unroll 4
     for (int e = threadIdx.x; e < total; e += kPassThreads) {
@@ -333,7 +326,7 @@ __global__ void __launch_bounds__(kPassThreads, 4) fft_pass2_spec(const float2* 
 // (M1, M2) pairs with specialised kernels.  Radix chains start with an odd radix where there is one:
 // a first stage of radix 8 writes shared memory with stride 8 (an 8-way bank conflict).
 #define AA_SPEC_LIST(X)                      \
-    X(375, 384, 8, (3, 5, 5, 5), (3, 8, 4, 4)) /* N = 288000 */ \
+    X(375, 384, 8, (3, 5, 5, 5), (8, 8, 6)) /* N = 288000 */ \
     X(300, 320, 8, (3, 5, 5, 4), (5, 8, 8))    /* N = 192000 */
 
 #define AA_UNPACK(...) __VA_ARGS__

@@ -107,6 +107,23 @@ AA_HD void dft5(float2* v) {
     v[3] = csub(p2, r);
 }
 
+AA_HD void dft6(float2* v) {
+    // 6 = 2 x 3 (Good-Thomas free form): two 3-point DFTs on even / odd inputs, twiddle, 2-point combine
+    float2 e[3] = {v[0], v[2], v[4]};
+    float2 o[3] = {v[1], v[3], v[5]};
+    dft3(e);
+    dft3(o);
+    const float h = 0.8660254037844386f;
+    float2 o1 = make_float2(0.5f * o[1].x + h * o[1].y, 0.5f * o[1].y - h * o[1].x);    // * exp(-i pi/3)
+    float2 o2 = make_float2(-0.5f * o[2].x + h * o[2].y, -0.5f * o[2].y - h * o[2].x);  // * exp(-2i pi/3)
+    v[0] = cadd(e[0], o[0]);
+    v[3] = csub(e[0], o[0]);
+    v[1] = cadd(e[1], o1);
+    v[4] = csub(e[1], o1);
+    v[2] = cadd(e[2], o2);
+    v[5] = csub(e[2], o2);
+}
+
 AA_HD void dft8(float2* v) {
     const float h = 0.7071067811865476f;
     float2 e[4] = {v[0], v[2], v[4], v[6]};
@@ -165,6 +182,38 @@ AA_HD void stockham_butterfly_fixed(int j, int L, int Ns, const float2* src, flo
     const int base = (j - k) * R + k;
 #pragma unroll
     for (int r = 0; r < R; ++r) dst[base + r * Ns] = v[r];
+}
+
+// Shared-memory index padding: one float2 of padding every 2^kPad elements (0 = none).
+template <int kPad>
+AA_HD int pad_index(int i) { return kPad ? i + (i >> kPad) : i; }
+
+// Offset of stage-s twiddles in the compact table: stages are stored back to back, stage with Ns earlier points
+// starts at Ns - 1 (sum over earlier stages of Ns' * (R' - 1) telescopes), r-major: [(r - 1) * Ns + k] so that
+// consecutive k (consecutive threads) read consecutive words - no bank conflicts for any radix.
+AA_HD int compact_twiddle_offset(int Ns) { return Ns - 1; }
+
+// Butterfly with compact stage twiddles: twc = table + compact_twiddle_offset(Ns); full = exp(-2 pi i m / L) table
+// (only the generic prime radices read it, for their roots of unity).
+template <int R, int kPad>
+AA_HD void stockham_butterfly_compact(int j, int k, int T, int L, int Ns, const float2* src, float2* dst,
+                                      const float2* twc, const float2* full) {
+    float2 v[R];
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+        float2 x = src[pad_index<kPad>(j + r * T)];
+        v[r] = (r == 0 || Ns == 1) ? x : cmul(x, twc[(r - 1) * Ns + k]);
+    }
+    if (R == 2) dft2(v);
+    else if (R == 3) dft3(v);
+    else if (R == 4) dft4(v);
+    else if (R == 5) dft5(v);
+    else if (R == 6) dft6(v);
+    else if (R == 8) dft8(v);
+    else dft_generic(v, R, full, L);
+    const int base = (j - k) * R + k;
+#pragma unroll
+    for (int r = 0; r < R; ++r) dst[pad_index<kPad>(base + r * Ns)] = v[r];
 }
 
 // Same butterfly with k = j % Ns and the twiddle step supplied by the caller (no division here).

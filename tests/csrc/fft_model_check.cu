@@ -34,15 +34,52 @@ static TwoLevelTwiddle dev_view(const HostTwoLevel& t) {
     return d;
 }
 
-template <int R>
-static void emu_stage(const SubPlanDev& d, int s, const float2* a, float2* b) {
-    // mirrors stage_loop<R> in fft.cu: multiply-high division, precomputed twiddle step
+// compact per-stage twiddles exactly as load_stage_twiddles / spec_twiddles build them on the device
+static std::vector<float2> compact_table(int L, const int* radix, int nst, const float2* tw) {
+    std::vector<float2> t((size_t)L + 1, make_float2(0, 0));
+    int Ns = 1;
+    for (int s = 0; s < nst; ++s) {
+        const int R = radix[s], tmul = L / (Ns * R);
+        for (int m = 0; m < Ns * (R - 1); ++m) {
+            const int r1 = m / Ns, k = m % Ns;
+            t[(size_t)compact_twiddle_offset(Ns) + m] = tw[(r1 + 1) * k * tmul];
+        }
+        Ns *= R;
+    }
+    return t;
+}
+
+template <int R, int kPad>
+static void emu_stage(const SubPlanDev& d, int s, const float2* a, float2* b, const float2* compact) {
+    // mirrors stage_loop<R> in fft.cu: multiply-high division, compact twiddles
     for (int e = 0; e < d.nb[s]; ++e) {
         const int g = (int)fast_div((unsigned)e, d.nb_rcp[s]);
         const int j = e - g * d.nb[s];
         const int k = j - (int)fast_div((unsigned)j, d.ns_rcp[s]) * d.Ns[s];
         if (g != 0) { printf("fast_div broke at e=%d\n", e); exit(2); }
-        stockham_butterfly_pre<R>(j, k, k * d.tmul[s], d.nb[s], d.L, d.Ns[s], a, b, d.tw);
+        stockham_butterfly_compact<R, kPad>(j, k, d.nb[s], d.L, d.Ns[s], a, b, compact + compact_twiddle_offset(d.Ns[s]),
+                                            d.tw);
+    }
+}
+
+template <int kPad>
+static void emu_chain(SubPlanDev& d, std::vector<float2>& a, std::vector<float2>& b) {
+    fill_stage_constants(&d);
+    std::vector<float2> compact = compact_table(d.L, d.radix, d.nst, d.tw);
+    for (int s = 0; s < d.nst; ++s) {
+        switch (d.radix[s]) {
+            case 2: emu_stage<2, kPad>(d, s, a.data(), b.data(), compact.data()); break;
+            case 3: emu_stage<3, kPad>(d, s, a.data(), b.data(), compact.data()); break;
+            case 4: emu_stage<4, kPad>(d, s, a.data(), b.data(), compact.data()); break;
+            case 5: emu_stage<5, kPad>(d, s, a.data(), b.data(), compact.data()); break;
+            case 6: emu_stage<6, kPad>(d, s, a.data(), b.data(), compact.data()); break;
+            case 7: emu_stage<7, kPad>(d, s, a.data(), b.data(), compact.data()); break;
+            case 8: emu_stage<8, kPad>(d, s, a.data(), b.data(), compact.data()); break;
+            case 11: emu_stage<11, kPad>(d, s, a.data(), b.data(), compact.data()); break;
+            case 13: emu_stage<13, kPad>(d, s, a.data(), b.data(), compact.data()); break;
+            default: printf("bad radix\n"); exit(2);
+        }
+        a.swap(b);
     }
 }
 
@@ -52,26 +89,15 @@ static void emu_stages(const HostSubPlan& sp, std::vector<float2>& a, std::vecto
     d.nst = sp.nst;
     for (int s = 0; s < sp.nst; ++s) d.radix[s] = sp.radix[s];
     d.tw = sp.tw.data();
-    fill_stage_constants(&d);
-    for (int s = 0; s < sp.nst; ++s) {
-        switch (sp.radix[s]) {
-            case 2: emu_stage<2>(d, s, a.data(), b.data()); break;
-            case 3: emu_stage<3>(d, s, a.data(), b.data()); break;
-            case 4: emu_stage<4>(d, s, a.data(), b.data()); break;
-            case 5: emu_stage<5>(d, s, a.data(), b.data()); break;
-            case 7: emu_stage<7>(d, s, a.data(), b.data()); break;
-            case 8: emu_stage<8>(d, s, a.data(), b.data()); break;
-            case 11: emu_stage<11>(d, s, a.data(), b.data()); break;
-            case 13: emu_stage<13>(d, s, a.data(), b.data()); break;
-            default: printf("bad radix\n"); exit(2);
+    emu_chain<0>(d, a, b);
+    static bool div_checked = false;
+    if (!div_checked) {  // exhaustive check of the multiply-high division for every index the kernels can form
+        div_checked = true;
+        for (unsigned dd = 1; dd <= 4096; dd += (dd < 64 ? 1 : 37)) {
+            unsigned r = fast_rcp(dd);
+            for (unsigned n = 0; n < 70000; n += 13)
+                if (fast_div(n, r) != n / dd) { printf("fast_div(%u,%u) wrong\n", n, dd); exit(2); }
         }
-        a.swap(b);
-    }
-    // exhaustive check of the multiply-high division for every index the kernels can form
-    for (unsigned dd = 1; dd <= 4096; dd += (dd < 64 ? 1 : 37)) {
-        unsigned r = fast_rcp(dd);
-        for (unsigned n = 0; n < 70000; n += 13)
-            if (fast_div(n, r) != n / dd) { printf("fast_div(%u,%u) wrong\n", n, dd); exit(2); }
     }
 }
 
@@ -387,7 +413,50 @@ static void check_real_band(int N) {
     }
 }
 
+// the compile-time chains of fft.cu's AA_SPEC_LIST and csd.cu (radix 6, padded shared-memory layout)
+template <int kPad>
+static void check_chain(int L, std::vector<int> radices) {
+    HostSubPlan hp;
+    host_subplan(L, &hp);  // only its twiddle table is used
+    SubPlanDev d{};
+    d.L = L;
+    d.nst = (int)radices.size();
+    for (int s = 0; s < d.nst; ++s) d.radix[s] = radices[(size_t)s];
+    d.tw = hp.tw.data();
+    const size_t padded = (size_t)pad_index<kPad>(L - 1) + 1;
+    std::vector<float2> x((size_t)L), a(padded, make_float2(0, 0)), b(padded, make_float2(0, 0));
+    double norm = 0;
+    for (int i = 0; i < L; ++i) {
+        x[(size_t)i] = make_float2((float)urand(), (float)urand());
+        a[(size_t)pad_index<kPad>(i)] = x[(size_t)i];
+        norm += (double)x[(size_t)i].x * x[(size_t)i].x + (double)x[(size_t)i].y * x[(size_t)i].y;
+    }
+    norm = sqrt(norm);
+    emu_chain<kPad>(d, a, b);
+    double worst = 0;
+    for (int k = 0; k < L; k += (L > 512 ? 17 : 1)) {
+        cd acc = 0;
+        for (int n = 0; n < L; ++n) {
+            double ang = -2.0 * M_PI * (double)(((long long)n * k) % L) / L;
+            acc += cd(x[(size_t)n].x, x[(size_t)n].y) * cd(cos(ang), sin(ang));
+        }
+        float2 got = a[(size_t)pad_index<kPad>(k)];
+        worst = fmax(worst, std::abs(acc - cd(got.x, got.y)) / norm);
+    }
+    char name[64];
+    snprintf(name, sizeof(name), "chain pad%d first radix %d (%d stages)", kPad, radices[0], d.nst);
+    report(name, L, worst, 5e-6);
+}
+
 int main() {
+    check_chain<0>(384, {8, 8, 6});
+    check_chain<0>(375, {3, 5, 5, 5});
+    check_chain<0>(320, {5, 8, 8});
+    check_chain<0>(300, {3, 5, 5, 4});
+    check_chain<4>(2048, {4, 8, 8, 8});
+    check_chain<4>(512, {8, 8, 8});
+    check_chain<4>(4096, {8, 8, 8, 8});
+    check_chain<0>(36, {6, 6});
     const int sizes[] = {1, 2, 3, 4, 5, 6, 7, 8, 11, 13, 16, 30, 64, 77, 143, 360, 1001, 2048,
                          2304, 4096, 24000, 30000, 31200, 65536, 17, 397, 4099, 25011, 45001};
     for (int M : sizes) check_c2c(M);
