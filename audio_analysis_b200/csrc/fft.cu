@@ -13,7 +13,7 @@
 
 #include "fft.cuh"
 #include "fft_plan_host.hpp"
-#include "fft_spec.cuh"
+#include "fft_reg.cuh"
 
 namespace aa {
 
@@ -249,122 +249,106 @@ __global__ void __launch_bounds__(kPassThreads, 4) fft_pass2_kernel(PassArgs pa,
 }
 
 // ------------------------------------------------------------------------------------
-// compile-time specialised passes for the hot lengths (everything else uses the kernels above)
+// two-stage register-resident passes for the hot lengths (fft_reg.cuh); everything else uses the kernels above
 // ------------------------------------------------------------------------------------
 
-template <int L, int G>
-constexpr size_t spec_smem() { return sizeof(float2) * ((size_t)2 * G * (L | 1) + L); }
-
-template <int kSrc, int M1, int M2, int G, int... Rs>
-__global__ void __launch_bounds__(kPassThreads, 4) fft_pass1_spec(SrcDesc src, float2* __restrict__ scratch,
-                                                                   TwoLevelTwiddle twM, const float2* __restrict__ tw_g) {
-    constexpr int L = M1, Lp = L | 1, groups = (M2 + G - 1) / G, total = G * L;
-    extern __shared__ float2 smem[];
-    const int unit = blockIdx.x / groups;
-    const int col0 = (blockIdx.x - unit * groups) * G;
-    float2* a = smem;
-    float2* b = smem + G * Lp;
-    float2* tw_s = b + G * Lp;
-    spec_twiddles<L, 1, Rs...>(tw_s, tw_g);
-#pragma unroll 4
-    for (int e = threadIdx.x; e < total; e += kPassThreads) {
-        const int i = e / G, g = e % G;
-        const int col = col0 + g;
-        float2 v = make_float2(0.f, 0.f);
-        if (M2 % G == 0 || col < M2) v = fetch<kSrc>(src, unit, i * M2 + col);
-        a[g * Lp + i] = v;
+// transform pitch in shared memory: conflict-free for 64-bit accesses with g as the fastest thread index
+constexpr int reg_pitch(int G, int min_elems) {
+    int tp = min_elems;
+    if (G == 8) {
+        while (tp % 8 != 6) ++tp;
+    } else {
+        tp |= 1;
     }
-    __syncthreads();
-    spec_stages<kPassThreads, 0, L, G, Lp, 1, Rs...>(a, b, tw_s, tw_g);
-    float2* __restrict__ out = scratch + (size_t)unit * ((size_t)M1 * M2);
-#pragma unroll 4
-    for (int e = threadIdx.x; e < total; e += kPassThreads) {
-        const int i = e / G, g = e % G;
-        const int col = col0 + g;
-        if (M2 % G == 0 || col < M2) out[i * M2 + col] = cmul(a[g * Lp + i], twiddle2(twM, (long long)(col * i)));
-    }
+    return tp;
 }
 
-template <int M1, int M2, int G, int... Rs>
-__global__ void __launch_bounds__(kPassThreads, 4) fft_pass2_spec(const float2* __restrict__ scratch,
-                                                                   float2* __restrict__ out, long long out_stride,
-                                                                   int n_valid, int conj, float scale,
-                                                                   const float2* __restrict__ tw_g) {
-    constexpr int L = M2, Lp = L | 1, groups = (M1 + G - 1) / G, total = G * L;
+template <int RA, int RB, int G>
+using RegCfg = RegPass<RA, RB, G, reg_pitch(G, RB * (RA | 1))>;
+
+template <class P, int kSrc, int M2>
+__global__ void __launch_bounds__(P::kThreads) fft_cols_reg(SrcDesc src, float2* __restrict__ scratch, TwoLevelTwiddle twM,
+                                                            const float2* __restrict__ tw_full) {
+    static_assert(M2 % P::G == 0, "columns must split evenly over CTAs");
+    constexpr int groups = M2 / P::G;
     extern __shared__ float2 smem[];
+    float2* buf = smem;
+    float2* tws = smem + P::kBufElems;
     const int unit = blockIdx.x / groups;
-    const int row0 = (blockIdx.x - unit * groups) * G;
-    float2* a = smem;
-    float2* b = smem + G * Lp;
-    float2* tw_s = b + G * Lp;
-    spec_twiddles<L, 1, Rs...>(tw_s, tw_g);
-    const float2* __restrict__ in = scratch + (size_t)unit * ((size_t)M1 * M2);
-#pragma unroll 4
-    for (int e = threadIdx.x; e < total; e += kPassThreads) {
-        const int g = e / L, i = e % L;
-        const int row = row0 + g;
-        float2 v = make_float2(0.f, 0.f);
-        if (M1 % G == 0 || row < M1) v = __ldg(in + row * M2 + i);
-        a[g * Lp + i] = v;
+    const int col0 = (blockIdx.x - unit * groups) * P::G;
+    reg_fill_twiddles<P>((int)threadIdx.x, P::kThreads, tws, tw_full);
+    if (kSrc == SRC_BAND_PACKED) {
+        const int row = unit / src.n_bands;
+        RegSrcBand s;
+        s.X = (const float2*)src.base + (size_t)row * src.unit_stride;
+        s.b = src.bands[unit - row * src.n_bands];
+        s.freq_scale = src.freq_scale;
+        s.M = src.M;
+        s.twN = src.twN;
+        reg_cols_stage_a<P>((int)threadIdx.x, s, M2, col0, buf);
+    } else if (kSrc == SRC_COMPLEX) {
+        RegSrcComplex s{(const float2*)src.base + (size_t)unit * src.unit_stride};
+        reg_cols_stage_a<P>((int)threadIdx.x, s, M2, col0, buf);
+    } else {  // SRC_REAL_PACKED with even length: z[m] = (x[2m], x[2m+1]) is a plain float2 view of the row
+        RegSrcComplex s{(const float2*)((const float*)src.base + (size_t)unit * src.unit_stride)};
+        reg_cols_stage_a<P>((int)threadIdx.x, s, M2, col0, buf);
     }
     __syncthreads();
-    spec_stages<kPassThreads, 0, L, G, Lp, 1, Rs...>(a, b, tw_s, tw_g);
-    float2* __restrict__ o = out + (size_t)unit * out_stride;
-#pragma unroll 4
-    for (int e = threadIdx.x; e < total; e += kPassThreads) {
-        const int i = e / G, g = e % G;
-        const int row = row0 + g;
-        const int idx = i * M1 + row;
-        if ((M1 % G == 0 || row < M1) && idx < n_valid) {
-            float2 v = a[g * Lp + i];
-            if (conj) v.y = -v.y;
-            o[idx] = cscale(v, scale);
-        }
-    }
+    reg_cols_stage_b<P>((int)threadIdx.x, buf, tws, scratch + (size_t)unit * ((size_t)P::L * M2), M2, col0, twM);
 }
 
-// (M1, M2) pairs with specialised kernels.  Radix chains start with an odd radix where there is one:
-// a first stage of radix 8 writes shared memory with stride 8 (an 8-way bank conflict).
-#define AA_SPEC_LIST(X)                      \
-    X(375, 384, 8, (3, 5, 5, 5), (8, 8, 6)) /* N = 288000 */ \
-    X(300, 320, 8, (3, 5, 5, 4), (5, 8, 8))    /* N = 192000 */
-
-#define AA_UNPACK(...) __VA_ARGS__
+template <class P, int M1>
+__global__ void __launch_bounds__(P::kThreads) fft_rows_reg(const float2* __restrict__ scratch, float2* __restrict__ out,
+                                                            long long out_stride, int n_valid, int conj, float scale,
+                                                            const float2* __restrict__ tw_full) {
+    static_assert(M1 % P::G == 0, "rows must split evenly over CTAs");
+    constexpr int groups = M1 / P::G;
+    extern __shared__ float2 smem[];
+    float2* buf = smem;
+    float2* tws = smem + P::kBufElems;
+    const int unit = blockIdx.x / groups;
+    const int row0 = (blockIdx.x - unit * groups) * P::G;
+    reg_fill_twiddles<P>((int)threadIdx.x, P::kThreads, tws, tw_full);
+    reg_rows_stage_a<P>((int)threadIdx.x, scratch + (size_t)unit * ((size_t)M1 * P::L), row0, buf);
+    __syncthreads();
+    reg_rows_stage_b<P>((int)threadIdx.x, buf, tws, out + (size_t)unit * out_stride, M1, row0, n_valid, conj, scale);
+}
 
 template <int kSrc>
-bool launch_pass1_spec(const C2CPlan* p, const SrcDesc& src, float2* scratch, long long units, cudaStream_t stream) {
-#define X(m1, m2, g, r1, r2)                                                                                   \
-    if (p->M1 == m1 && p->M2 == m2) {                                                                          \
-        auto k = fft_pass1_spec<kSrc, m1, m2, g, AA_UNPACK r1>;                                               \
-        static bool once = false;                                                                              \
-        if (!once) {                                                                                           \
-            cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)spec_smem<m1, g>());   \
-            once = true;                                                                                       \
-        }                                                                                                      \
-        k<<<(unsigned)(units * ((m2 + g - 1) / g)), kPassThreads, spec_smem<m1, g>(), stream>>>(               \
-            src, scratch, p->twM.dev, p->s1.dev.tw);                                                           \
-        return true;                                                                                           \
+bool launch_cols_reg(const C2CPlan* p, const SrcDesc& src, float2* scratch, long long units, cudaStream_t stream) {
+#define X(ra1, rb1, g1, ra2, rb2, g2)                                                                         \
+    if (p->M1 == ra1 * rb1 && p->M2 == ra2 * rb2) {                                                           \
+        using P = RegCfg<ra1, rb1, g1>;                                                                       \
+        auto k = fft_cols_reg<P, kSrc, ra2 * rb2>;                                                            \
+        static bool once = false;                                                                             \
+        if (!once) {                                                                                          \
+            cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)P::kSmemBytes);         \
+            once = true;                                                                                      \
+        }                                                                                                     \
+        k<<<(unsigned)(units * ((ra2 * rb2) / g1)), P::kThreads, P::kSmemBytes, stream>>>(src, scratch, p->twM.dev, \
+                                                                                         p->s1.dev.tw);       \
+        return true;                                                                                          \
     }
-    AA_SPEC_LIST(X)
+    AA_REG_LIST(X)
 #undef X
     return false;
 }
 
-bool launch_pass2_spec(const C2CPlan* p, const float2* scratch, const DstDesc& dst, long long units,
-                       cudaStream_t stream) {
-#define X(m1, m2, g, r1, r2)                                                                                   \
-    if (p->M1 == m1 && p->M2 == m2) {                                                                          \
-        auto k = fft_pass2_spec<m1, m2, g, AA_UNPACK r2>;                                                     \
-        static bool once = false;                                                                              \
-        if (!once) {                                                                                           \
-            cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)spec_smem<m2, g>());   \
-            once = true;                                                                                       \
-        }                                                                                                      \
-        k<<<(unsigned)(units * ((m1 + g - 1) / g)), kPassThreads, spec_smem<m2, g>(), stream>>>(               \
-            scratch, (float2*)dst.base, dst.unit_stride, dst.n_valid, dst.conj1, dst.scale1, p->s2.dev.tw);    \
-        return true;                                                                                           \
+bool launch_rows_reg(const C2CPlan* p, const float2* scratch, const DstDesc& dst, long long units, cudaStream_t stream) {
+#define X(ra1, rb1, g1, ra2, rb2, g2)                                                                         \
+    if (p->M1 == ra1 * rb1 && p->M2 == ra2 * rb2) {                                                           \
+        using P = RegCfg<ra2, rb2, g2>;                                                                       \
+        auto k = fft_rows_reg<P, ra1 * rb1>;                                                                  \
+        static bool once = false;                                                                             \
+        if (!once) {                                                                                          \
+            cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)P::kSmemBytes);         \
+            once = true;                                                                                      \
+        }                                                                                                     \
+        k<<<(unsigned)(units * ((ra1 * rb1) / g2)), P::kThreads, P::kSmemBytes, stream>>>(                    \
+            scratch, (float2*)dst.base, dst.unit_stride, dst.n_valid, dst.conj1, dst.scale1, p->s2.dev.tw);   \
+        return true;                                                                                          \
     }
-    AA_SPEC_LIST(X)
+    AA_REG_LIST(X)
 #undef X
     return false;
 }
@@ -417,10 +401,12 @@ int exec_direct(const C2CPlan* p, const SrcDesc& src, const DstDesc& dst, long l
         AA_REQUIRE(grid < 2147483647LL, AA_ERR_INVALID_ARGUMENT, "fft grid too large");
         const unsigned g = (unsigned)grid;
         const bool use_spec = getenv("AA_FFT_GENERIC") == nullptr && units * (long long)p->M < 2147483647LL;
-        if (use_spec && fast_src && src.mode == SRC_BAND_PACKED &&
-            launch_pass1_spec<SRC_BAND_PACKED>(p, src, scratch, units, stream)) {
-        } else if (use_spec && fast_src && src.mode == SRC_REAL_PACKED &&
-                   launch_pass1_spec<SRC_REAL_PACKED>(p, src, scratch, units, stream)) {
+        if (use_spec && fast_src && src.mode == SRC_BAND_PACKED && src.conj &&
+            launch_cols_reg<SRC_BAND_PACKED>(p, src, scratch, units, stream)) {
+        } else if (use_spec && fast_src && src.mode == SRC_REAL_PACKED && !src.clip && src.n_valid == 2 * p->M &&
+                   (src.unit_stride % 2) == 0 && launch_cols_reg<SRC_REAL_PACKED>(p, src, scratch, units, stream)) {
+        } else if (use_spec && fast_src && src.mode == SRC_COMPLEX && !src.conj && src.n_valid >= p->M &&
+                   launch_cols_reg<SRC_COMPLEX>(p, src, scratch, units, stream)) {
         } else if (fast_src && src.mode == SRC_COMPLEX)
             fft_pass1_kernel<SRC_COMPLEX><<<g, kPassThreads, p->smem1, stream>>>(pa, src, scratch, (long long)p->M);
         else if (fast_src && src.mode == SRC_REAL_PACKED)
@@ -445,7 +431,7 @@ int exec_direct(const C2CPlan* p, const SrcDesc& src, const DstDesc& dst, long l
     const bool dst_plain = plain_complex_dst(dst);
     const bool spec2 = getenv("AA_FFT_GENERIC") == nullptr && p->M1 > 1 && src_plain && dst_plain &&
                        units * (long long)p->M < 2147483647LL &&
-                       launch_pass2_spec(p, scratch, dst, units, stream);
+                       launch_rows_reg(p, scratch, dst, units, stream);
     if (spec2) {
     } else if (src_plain && dst_plain)
         fft_pass2_kernel<SRC_COMPLEX, DST_COMPLEX><<<g, kPassThreads, p->smem2, stream>>>(pa, src2, dst);

@@ -16,6 +16,24 @@ constexpr int kMaxSubLen = 4096;      // longest in-CTA transform
 constexpr int kSinglePassMax = 2048;  // M <= this: one pass
 constexpr int kTwoLevelShift = 10;
 
+// (M1 = RA1 * RB1, M2 = RA2 * RB2) splits served by the two-stage register-resident kernels of fft.cu
+// (fft_reg.cuh): X(RA1, RB1, G1, RA2, RB2, G2).  host_direct_plan() prefers these splits.
+#define AA_REG_LIST(X)                                        \
+    X(18, 20, 8, 20, 20, 8) /* N = 288000: M = 360 x 400 */   \
+    X(12, 20, 8, 20, 20, 8) /* N = 192000: M = 240 x 400 */
+
+inline bool reg_split_for(int M, int* M1, int* M2) {
+#define X(ra1, rb1, g1, ra2, rb2, g2)                   \
+    if (M == (ra1) * (rb1) * (ra2) * (rb2)) {           \
+        *M1 = (ra1) * (rb1);                            \
+        *M2 = (ra2) * (rb2);                            \
+        return true;                                    \
+    }
+    AA_REG_LIST(X)
+#undef X
+    return false;
+}
+
 struct HostSubPlan {
     int L = 1;
     int nst = 0;
@@ -116,9 +134,10 @@ inline bool direct_plan_possible(int M) {
 inline bool host_direct_plan(int M, HostC2C* p) {
     p->M = M;
     p->bluestein = false;
-    int best1 = -1;
+    int best1 = -1, reg2 = 0;
     if (M <= kSinglePassMax) {
         best1 = 1;
+    } else if (reg_split_for(M, &best1, &reg2)) {
     } else {
         int best_cost = 1 << 30;
         for (int d = 1; (long long)d * d <= M; ++d) {

@@ -1,0 +1,167 @@
+// Two-stage register-resident FFT passes (the hot lengths of the rt60bands filterbank).
+//
+// A length L = RA * RB transform is done by RB butterflies of radix RA (stage A) followed by RA
+// butterflies of radix RB (stage B), each butterfly living in one thread's registers
+// (fft_radix.cuh).  Stage A reads its inputs straight from global memory, stage B writes its
+// outputs straight to global memory: the data crosses shared memory exactly once per pass.
+// A CTA works on G transforms side by side; the transform index g is the fastest thread index in
+// both stages, so that global accesses of adjacent transforms (adjacent columns in pass 1,
+// adjacent rows in pass 2) coalesce into whole sectors.
+//
+// Stockham index algebra (fft_core.cuh) for two stages:
+//   stage A (Ns = 1):  butterfly ja in [0, RB) reads x[ja + r RB], writes d[ja RA + r]
+//   stage B (Ns = RA): butterfly jb in [0, RA) reads d[jb + r RA] * w_L^{r jb}, writes X[jb + q RA]
+// so stage B's input r of butterfly jb is stage A's output jb of butterfly r.
+//
+// The stage bodies are host/device functions of the thread index so that
+// tests/csrc/fft_model_check.cu can run every thread of a CTA serially on the CPU.
+#pragma once
+
+#include "fft_access.cuh"
+#include "fft_radix.cuh"
+
+namespace aa {
+
+template <int RA_, int RB_, int G_, int TP_>
+struct RegPass {
+    static constexpr int RA = RA_, RB = RB_, L = RA_ * RB_, G = G_, TP = TP_;
+    static constexpr int PA = RA_ | 1;  // odd pitch between stage-A butterflies: no bank conflicts
+    static constexpr int kThreadsA = G_ * RB_, kThreadsB = G_ * RA_;
+    static constexpr int kThreadsMax = kThreadsA > kThreadsB ? kThreadsA : kThreadsB;
+    static constexpr int kThreads = (kThreadsMax + 31) / 32 * 32;
+    static constexpr int kBufElems = G_ * TP_;
+    static constexpr size_t kSmemBytes = sizeof(float2) * (size_t)(kBufElems + L);
+    static_assert(TP_ >= RB_ * PA, "transform pitch too small");
+    AA_HD static int slot(int g, int ja, int ra) { return g * TP + ja * PA + ra; }
+};
+
+// inter-stage twiddle table in shared memory: tws[r * RA + jb] = w_L^{r jb}; full = exp(-2 pi i m / L)
+template <class P>
+AA_HD void reg_fill_twiddles(int t, int nthreads, float2* tws, const float2* full) {
+    for (int m = t; m < P::L; m += nthreads) {
+        const int r = m / P::RA, jb = m - r * P::RA;
+        tws[m] = load_c(full + r * jb);
+    }
+}
+
+// ---- element sources ---------------------------------------------------------------------------
+// get(idx, &v) returns false when the element is structurally zero (v is then zero too).
+
+struct RegSrcComplex {
+    const float2* p;
+    AA_HD bool get(int idx, float2* v) const {
+        *v = load_c(p + idx);
+        return true;
+    }
+};
+
+// Packed, band-masked, conjugated half spectrum of one (row, band) unit (rt60bands.py:170-175):
+// the same arithmetic as fetch<SRC_BAND_PACKED> of the generic passes.
+struct RegSrcBand {
+    const float2* X;  // half spectrum of the row, k in [0, M]
+    BandDev b;
+    double freq_scale;
+    int M;
+    TwoLevelTwiddle twN;
+    AA_HD float2 masked(int k) const {
+        if (k < b.k_first || k > b.k_last) return make_float2(0.f, 0.f);
+        const float f = (float)((double)k * freq_scale);
+        const float m = band_mask_value(b, f);
+        if (m == 0.0f) return make_float2(0.f, 0.f);
+        return cscale(load_c(X + k), m);
+    }
+    AA_HD bool get(int idx, float2* v) const {
+        const int mk = M - idx;
+        const bool in_k = (idx >= b.k_first && idx <= b.k_last), in_m = (mk >= b.k_first && mk <= b.k_last);
+        if (!in_k && !in_m) {
+            *v = make_float2(0.f, 0.f);
+            return false;
+        }
+        *v = cconj(pack_half_spectrum(masked(idx), masked(mk), twiddle2(twN, idx)));
+        return true;
+    }
+};
+
+// ---- pass 1: columns.  CTA = G adjacent columns, transform over n1 (stride M2), output [k1 * M2 + col] -------
+
+template <class P, class Src>
+AA_HD void reg_cols_stage_a(int t, const Src& src, int M2, int col0, float2* buf) {
+    if (t >= P::kThreadsA) return;
+    const int ja = t / P::G, g = t - ja * P::G;
+    float2 v[P::RA];
+    bool any = false;
+    static_for<0, P::RA>([&](auto r_) {
+        constexpr int r = decltype(r_)::value;
+        any |= src.get((ja + r * P::RB) * M2 + col0 + g, &v[r]);
+    });
+    if (any) dft_r<P::RA>(v);
+    static_for<0, P::RA>([&](auto r_) {
+        constexpr int r = decltype(r_)::value;
+        buf[P::slot(g, ja, r)] = v[r];
+    });
+}
+
+template <class P>
+AA_HD void reg_cols_stage_b(int t, const float2* buf, const float2* tws, float2* scratch_unit, int M2, int col0,
+                            const TwoLevelTwiddle& twM) {
+    if (t >= P::kThreadsB) return;
+    const int jb = t / P::G, g = t - jb * P::G;
+    float2 v[P::RB];
+    static_for<0, P::RB>([&](auto r_) {
+        constexpr int r = decltype(r_)::value;
+        const float2 x = buf[P::slot(g, r, jb)];
+        v[r] = (r == 0) ? x : cmul(x, tws[r * P::RA + jb]);
+    });
+    dft_r<P::RB>(v);
+    const int col = col0 + g;
+    static_for<0, P::RB>([&](auto q_) {
+        constexpr int q = decltype(q_)::value;
+        const int k1 = jb + q * P::RA;
+        scratch_unit[k1 * M2 + col] = cmul(v[q], twiddle2(twM, (long long)(col * k1)));
+    });
+}
+
+// ---- pass 2: rows.  CTA = G adjacent rows k1, transform over n2 (contiguous), output [k2 * M1 + row] ----------
+
+template <class P>
+AA_HD void reg_rows_stage_a(int t, const float2* scratch_unit, int row0, float2* buf) {
+    if (t >= P::kThreadsA) return;
+    const int ja = t / P::G, g = t - ja * P::G;
+    const float2* in = scratch_unit + (row0 + g) * P::L + ja;
+    float2 v[P::RA];
+    static_for<0, P::RA>([&](auto r_) {
+        constexpr int r = decltype(r_)::value;
+        v[r] = load_c(in + r * P::RB);
+    });
+    dft_r<P::RA>(v);
+    static_for<0, P::RA>([&](auto r_) {
+        constexpr int r = decltype(r_)::value;
+        buf[P::slot(g, ja, r)] = v[r];
+    });
+}
+
+template <class P>
+AA_HD void reg_rows_stage_b(int t, const float2* buf, const float2* tws, float2* out_unit, int M1, int row0,
+                            int n_valid, int conj, float scale) {
+    if (t >= P::kThreadsB) return;
+    const int jb = t / P::G, g = t - jb * P::G;
+    float2 v[P::RB];
+    static_for<0, P::RB>([&](auto r_) {
+        constexpr int r = decltype(r_)::value;
+        const float2 x = buf[P::slot(g, r, jb)];
+        v[r] = (r == 0) ? x : cmul(x, tws[r * P::RA + jb]);
+    });
+    dft_r<P::RB>(v);
+    const int row = row0 + g;
+    static_for<0, P::RB>([&](auto q_) {
+        constexpr int q = decltype(q_)::value;
+        const int idx = (jb + q * P::RA) * M1 + row;
+        if (idx < n_valid) {
+            float2 o = v[q];
+            if (conj) o.y = -o.y;
+            out_unit[idx] = cscale(o, scale);
+        }
+    });
+}
+
+}  // namespace aa
