@@ -45,6 +45,17 @@ __global__ void untangle_kernel(const float2* __restrict__ Z, float2* __restrict
     }
 }
 
+// band_mask_value() for every bin of every band's support, once per call: the masks are the same for all rows
+// (rt60bands.py:365-387 rebuilds them per channel and band), so the FFT passes read a table instead of
+// evaluating two float32 cosines per bin.
+__global__ void band_mask_kernel(const BandDev* __restrict__ bands, double freq_scale) {
+    BandDev b = bands[blockIdx.y];
+    float* __restrict__ out = const_cast<float*>(b.mask);
+    b.mask = nullptr;
+    for (int k = b.k_first + blockIdx.x * blockDim.x + threadIdx.x; k <= b.k_last; k += gridDim.x * blockDim.x)
+        out[k - b.k_first] = band_mask_value(b, (float)((double)k * freq_scale));
+}
+
 // Host mirror of _make_lowpass_mask / _make_highpass_mask / _make_bandpass_mask edge handling
 // (analyse/rt60bands.py:127-167); python floats are doubles, numpy rounds them to float32 when they
 // meet the float32 frequency array.
@@ -93,7 +104,7 @@ int make_band_dev(const aa_band& b, double tw_oct, double nyq, double freq_scale
 }
 
 struct Layout {
-    size_t off_bands, off_X, off_y, off_scratch, off_db0, off_db1, off_unit_start, total;
+    size_t off_bands, off_mask, off_X, off_y, off_scratch, off_db0, off_db1, off_unit_start, total;
 };
 
 Layout make_layout(const aa_bands_plan* p, long long rows, int nb, bool smoothing = false) {
@@ -102,6 +113,8 @@ Layout make_layout(const aa_bands_plan* p, long long rows, int nb, bool smoothin
     size_t o = 0;
     l.off_bands = o;
     o += align_up(sizeof(BandDev) * AA_MAX_BANDS);
+    l.off_mask = o;  // mask tables: at most one value per rfft bin per band
+    o += align_up(sizeof(float) * (size_t)nb * (size_t)(p->n / 2 + 1));
     l.off_X = o;
     o += align_up(sizeof(float2) * (size_t)rows * (size_t)p->x_stride);
     l.off_y = o;  // also the forward transform's packed output Z (rows * M float2 <= units * y_stride floats)
@@ -203,11 +216,25 @@ int rt60bands_batch(const aa_bands_plan* plan, const float* d_x, long long row_s
     float2* d_scr = reinterpret_cast<float2*>(ws + lay.off_scratch);
 
     std::vector<BandDev> hb((size_t)nb);
+    float* d_mask = reinterpret_cast<float*>(ws + lay.off_mask);
+    size_t mask_off = 0;
+    int widest = 0;
     for (int i = 0; i < nb; ++i) {
         int rc = make_band_dev(bands[i], tw_oct, nyq, freq_scale, N / 2 + 1, &hb[(size_t)i]);
         if (rc != AA_OK) return rc;
+        const int support = hb[(size_t)i].k_last - hb[(size_t)i].k_first + 1;
+        hb[(size_t)i].mask = d_mask + mask_off;
+        if (support > 0) mask_off += (size_t)support;
+        if (support > widest) widest = support;
     }
     AA_CUDA_TRY(cudaMemcpyAsync(d_bands, hb.data(), sizeof(BandDev) * (size_t)nb, cudaMemcpyHostToDevice, stream));
+    if (widest > 0) {
+        int bx = (widest + 255) / 256;
+        if (bx > 64) bx = 64;
+        band_mask_kernel<<<dim3((unsigned)bx, (unsigned)nb), 256, 0, stream>>>(d_bands, freq_scale);
+        int rc = launch_check("band_mask_kernel");
+        if (rc != AA_OK) return rc;
+    }
     // the host vector must outlive the copy: pageable-memory async copies are staged before returning
 
     for (long long r0 = 0; r0 < n_rows; r0 += rc_rows) {

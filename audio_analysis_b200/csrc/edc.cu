@@ -175,6 +175,40 @@ __global__ void __launch_bounds__(kThreads, 2) edc_kernel(EdcArgs a) {
                 const int k = kb + u;
                 v[u] = (k < my_tile1 && k >= k_skip) ? load_tile(x, k, lane, len) : make_float4(0.f, 0.f, 0.f, 0.f);
             }
+            if constexpr (!kWriteDb) {
+                // metrics only: tile totals by one 4-way transpose-reduce (6 shuffles for 4 tiles).  The totals
+                // may differ from phase 2's scan totals in the last bit; nothing is stored, so curve
+                // monotonicity across tile boundaries is not at stake (the crossing search tolerates it).
+                float ts[kUnroll];
+#pragma unroll
+                for (int u = 0; u < kUnroll; ++u) {
+                    const int k = kb + u;
+                    ts[u] = 0.f;
+                    if (k < my_tile1 && k >= k_skip) {
+                        if (find_peak) {
+                            const int i0 = k * kTile + lane * 4;
+                            float m;
+                            m = fabsf(v[u].x); if (m > amax) { amax = m; aidx = i0; }
+                            m = fabsf(v[u].y); if (m > amax) { amax = m; aidx = i0 + 1; }
+                            m = fabsf(v[u].z); if (m > amax) { amax = m; aidx = i0 + 2; }
+                            m = fabsf(v[u].w); if (m > amax) { amax = m; aidx = i0 + 3; }
+                        }
+                        ts[u] = fmaf(v[u].x, v[u].x, fmaf(v[u].y, v[u].y, fmaf(v[u].z, v[u].z, v[u].w * v[u].w)));
+                    }
+                }
+                static_assert(kUnroll == 4, "transpose-reduce is written for 4 tiles");
+                const bool hi16 = (lane & 16) != 0, hi8 = (lane & 8) != 0;
+                float a0 = hi16 ? ts[2] : ts[0], a1 = hi16 ? ts[3] : ts[1];
+                a0 += __shfl_xor_sync(kFullMask, hi16 ? ts[0] : ts[2], 16);
+                a1 += __shfl_xor_sync(kFullMask, hi16 ? ts[1] : ts[3], 16);
+                float c = hi8 ? a1 : a0;
+                c += __shfl_xor_sync(kFullMask, hi8 ? a0 : a1, 8);
+                c += __shfl_xor_sync(kFullMask, c, 4);
+                c += __shfl_xor_sync(kFullMask, c, 2);
+                c += __shfl_xor_sync(kFullMask, c, 1);
+                const int u_own = lane >> 3;  // lanes 0, 8, 16, 24 own tiles kb + 0..3
+                if ((lane & 7) == 0 && kb + u_own < my_tile0 + tpw) tile_sum[kb + u_own - cta_tile0] = c;
+            } else {
 #pragma unroll
             for (int u = 0; u < kUnroll; ++u) {
                 const int k = kb + u;
@@ -193,6 +227,7 @@ __global__ void __launch_bounds__(kThreads, 2) edc_kernel(EdcArgs a) {
                     tsum = __fadd_rn(t.excl, t.s[0]);  // lane 0: whole-tile sum, same ops as phase 2
                 }
                 if (lane == 0) tile_sum[k - cta_tile0] = tsum;
+            }
             }
         }
     }

@@ -274,9 +274,11 @@ __global__ void __launch_bounds__(P::kThreads) fft_cols_reg(SrcDesc src, float2*
     extern __shared__ float2 smem[];
     float2* buf = smem;
     float2* tws = smem + P::kBufElems;
+    float2* colq = tws + P::L;
     const int unit = blockIdx.x / groups;
     const int col0 = (blockIdx.x - unit * groups) * P::G;
     reg_fill_twiddles<P>((int)threadIdx.x, P::kThreads, tws, tw_full);
+    reg_cols_fill_colq<P>((int)threadIdx.x, colq, col0, twM);
     if (kSrc == SRC_BAND_PACKED) {
         const int row = unit / src.n_bands;
         RegSrcBand s;
@@ -294,7 +296,7 @@ __global__ void __launch_bounds__(P::kThreads) fft_cols_reg(SrcDesc src, float2*
         reg_cols_stage_a<P>((int)threadIdx.x, s, M2, col0, buf);
     }
     __syncthreads();
-    reg_cols_stage_b<P>((int)threadIdx.x, buf, tws, scratch + (size_t)unit * ((size_t)P::L * M2), M2, col0, twM);
+    reg_cols_stage_b<P>((int)threadIdx.x, buf, tws, colq, scratch + (size_t)unit * ((size_t)P::L * M2), M2, col0, twM);
 }
 
 template <class P, int M1>

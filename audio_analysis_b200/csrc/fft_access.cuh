@@ -28,6 +28,7 @@ struct BandDev {
     float lp_pass, lp_stop, lp_span;
     int lp_step;
     int k_first, k_last;  // inclusive rfft-bin range outside of which the mask is exactly 0
+    const float* mask;    // optional table of band_mask_value() for k in [k_first, k_last] (same float32 arithmetic)
 };
 
 AA_HD float ramp01(float f, float x0, float span, int step, float x1) {
@@ -109,8 +110,7 @@ AA_HD float load_r(const float* p) {
 // masked half-spectrum value Y[k], k in [0, N/2]
 AA_HD float2 band_Y(const SrcDesc& s, const float2* X, const BandDev& b, int k) {
     if (k < b.k_first || k > b.k_last) return make_float2(0.f, 0.f);
-    float f = (float)((double)k * s.freq_scale);
-    float m = band_mask_value(b, f);
+    const float m = b.mask ? load_r(b.mask + (k - b.k_first)) : band_mask_value(b, (float)((double)k * s.freq_scale));
     if (m == 0.0f) return make_float2(0.f, 0.f);
     return cscale(load_c(X + k), m);
 }

@@ -30,7 +30,8 @@ struct RegPass {
     static constexpr int kThreadsMax = kThreadsA > kThreadsB ? kThreadsA : kThreadsB;
     static constexpr int kThreads = (kThreadsMax + 31) / 32 * 32;
     static constexpr int kBufElems = G_ * TP_;
-    static constexpr size_t kSmemBytes = sizeof(float2) * (size_t)(kBufElems + L);
+    static constexpr int kColQElems = G_ * RB_;  // pass 1 only: w_M^{RA col q} per (column, output block q)
+    static constexpr size_t kSmemBytes = sizeof(float2) * (size_t)(kBufElems + L + kColQElems);
     static_assert(TP_ >= RB_ * PA, "transform pitch too small");
     AA_HD static int slot(int g, int ja, int ra) { return g * TP + ja * PA + ra; }
 };
@@ -63,21 +64,22 @@ struct RegSrcBand {
     double freq_scale;
     int M;
     TwoLevelTwiddle twN;
-    AA_HD float2 masked(int k) const {
-        if (k < b.k_first || k > b.k_last) return make_float2(0.f, 0.f);
-        const float f = (float)((double)k * freq_scale);
-        const float m = band_mask_value(b, f);
+    AA_HD float2 masked(int k) const {  // k inside [k_first, k_last]
+        const float m = b.mask ? load_r(b.mask + (k - b.k_first)) : band_mask_value(b, (float)((double)k * freq_scale));
         if (m == 0.0f) return make_float2(0.f, 0.f);
         return cscale(load_c(X + k), m);
     }
     AA_HD bool get(int idx, float2* v) const {
+        const unsigned span = (unsigned)(b.k_last - b.k_first);  // k_last < k_first (empty band) wraps to "never"
         const int mk = M - idx;
-        const bool in_k = (idx >= b.k_first && idx <= b.k_last), in_m = (mk >= b.k_first && mk <= b.k_last);
+        const bool in_k = (unsigned)(idx - b.k_first) <= span && b.k_last >= b.k_first;
+        const bool in_m = (unsigned)(mk - b.k_first) <= span && b.k_last >= b.k_first;
         if (!in_k && !in_m) {
             *v = make_float2(0.f, 0.f);
             return false;
         }
-        *v = cconj(pack_half_spectrum(masked(idx), masked(mk), twiddle2(twN, idx)));
+        const float2 zero = make_float2(0.f, 0.f);
+        *v = cconj(pack_half_spectrum(in_k ? masked(idx) : zero, in_m ? masked(mk) : zero, twiddle2(twN, idx)));
         return true;
     }
 };
@@ -101,9 +103,18 @@ AA_HD void reg_cols_stage_a(int t, const Src& src, int M2, int col0, float2* buf
     });
 }
 
+// four-step twiddle w_M^{col k1}, k1 = jb + q RA, factored as w_M^{col jb} * w_M^{RA col q}: the second factor is
+// shared by every butterfly jb of the column and lives in shared memory, colq[q * G + g]
 template <class P>
-AA_HD void reg_cols_stage_b(int t, const float2* buf, const float2* tws, float2* scratch_unit, int M2, int col0,
-                            const TwoLevelTwiddle& twM) {
+AA_HD void reg_cols_fill_colq(int t, float2* colq, int col0, const TwoLevelTwiddle& twM) {
+    if (t >= P::kColQElems) return;
+    const int q = t / P::G, g = t - q * P::G;
+    colq[t] = twiddle2(twM, (long long)(P::RA * (col0 + g)) * q);
+}
+
+template <class P>
+AA_HD void reg_cols_stage_b(int t, const float2* buf, const float2* tws, const float2* colq, float2* scratch_unit,
+                            int M2, int col0, const TwoLevelTwiddle& twM) {
     if (t >= P::kThreadsB) return;
     const int jb = t / P::G, g = t - jb * P::G;
     float2 v[P::RB];
@@ -114,10 +125,11 @@ AA_HD void reg_cols_stage_b(int t, const float2* buf, const float2* tws, float2*
     });
     dft_r<P::RB>(v);
     const int col = col0 + g;
+    const float2 c = twiddle2(twM, (long long)(col * jb));
     static_for<0, P::RB>([&](auto q_) {
         constexpr int q = decltype(q_)::value;
         const int k1 = jb + q * P::RA;
-        scratch_unit[k1 * M2 + col] = cmul(v[q], twiddle2(twM, (long long)(col * k1)));
+        scratch_unit[k1 * M2 + col] = cmul(v[q], cmul(c, colq[q * P::G + g]));
     });
 }
 

@@ -12,6 +12,7 @@ every row starts 16-byte aligned.
 from __future__ import annotations
 
 import ctypes as C
+import os
 from dataclasses import dataclass
 from typing import Dict, List, Optional, Sequence, Tuple, Union
 
@@ -330,7 +331,7 @@ def rt60bands(rows: Rows, start_idx: torch.Tensor, bands: Sequence[Tuple[int, Op
     b, nb = rows.n_rows, len(bands)
     plan = bands_plan(rows.n, dev)
     one = int(lib.aa_bands_workspace_bytes(plan.handle, 1, nb))
-    budget = int(workspace_bytes or DEFAULT_WORKSPACE_BYTES)
+    budget = int(workspace_bytes or os.environ.get("AA_BANDS_WORKSPACE_BYTES") or DEFAULT_WORKSPACE_BYTES)
     if budget < one:
         budget = one
     allrows = int(lib.aa_bands_workspace_bytes(plan.handle, b, nb))

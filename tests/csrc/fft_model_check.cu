@@ -118,7 +118,7 @@ static void emu_reg_unit(const HostC2C& p, const SrcDesc& src, const DstDesc& ds
     using P1 = RegPass<RA1, RB1, G1, emu_reg_pitch(G1, RB1 * (RA1 | 1))>;
     using P2 = RegPass<RA2, RB2, G2, emu_reg_pitch(G2, RB2 * (RA2 | 1))>;
     const int M1 = P1::L, M2 = P2::L;
-    std::vector<float2> scratch((size_t)M1 * M2), buf, tws;
+    std::vector<float2> scratch((size_t)M1 * M2), buf, tws, colq((size_t)P1::kColQElems);
     TwoLevelTwiddle twM = dev_view(p.twM);
     buf.assign((size_t)P1::kBufElems, make_float2(0, 0));
     tws.assign((size_t)P1::L, make_float2(0, 0));
@@ -143,7 +143,9 @@ static void emu_reg_unit(const HostC2C& p, const SrcDesc& src, const DstDesc& ds
                 reg_cols_stage_a<P1>(t, s, M2, col0, buf.data());
             }
         }
-        for (int t = 0; t < P1::kThreads; ++t) reg_cols_stage_b<P1>(t, buf.data(), tws.data(), scratch.data(), M2, col0, twM);
+        for (int t = 0; t < P1::kThreads; ++t) reg_cols_fill_colq<P1>(t, colq.data(), col0, twM);
+        for (int t = 0; t < P1::kThreads; ++t)
+            reg_cols_stage_b<P1>(t, buf.data(), tws.data(), colq.data(), scratch.data(), M2, col0, twM);
     }
     buf.assign((size_t)P2::kBufElems, make_float2(0, 0));
     tws.assign((size_t)P2::L, make_float2(0, 0));
