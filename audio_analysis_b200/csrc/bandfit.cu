@@ -1,0 +1,365 @@
+// Band EDC + crossings + decay fits from per-tile energy partials (metrics only).
+//
+// The register-pass rows kernel (fft.cu: fft_rows_reg<.., true>) stores, next to a band signal y, the energy of
+// every group of 8 rows of its output matrix.  A band signal therefore arrives with its energy already summed over
+// "tiles" of TL = 2 M1 consecutive samples (M2 tiles, M1 / 8 partials each), and the Schroeder integral
+// (analyse/decay.py:150-158) is a suffix scan over those M2 numbers.  Only the few tiles that hold the start
+// sample, a level crossing (decay.py:173-199) or fit points (decay.py:224-249) are read again at sample
+// resolution - about a tenth of the signal - instead of streaming it twice as the general kernel (edc.cu) does.
+//
+// One CTA of 8 warps per (row, band) unit.  Semantics are those of edc.cu / edc_body.cuh: float32 squares and
+// in-tile sums, float64 carries, float32 dB curve and times, first sample <= target, fit mask on float32 times,
+// closed-form least squares in float64 (fit_math.cuh).
+#include "edc_body.cuh"
+#include "kernels.cuh"
+
+namespace aa {
+
+namespace {
+
+using edc::EdcArgs;
+using edc::kMaxTargets;
+using edc::TileScan;
+using edc::tile_scan;
+using edc::to_db;
+
+constexpr int kFitThreads = 256;
+constexpr int kFitWarps = kFitThreads / 32;
+constexpr int kSub = 128;     // samples per warp step: one float4 per lane
+constexpr int kMaxSub = 8;    // tile length <= 1024 samples
+
+struct BandFitArgs {
+    const float* y;
+    long long y_stride;
+    const float* part;        // [unit][n_groups][n_tiles]
+    long long part_stride;
+    int n_groups, n_tiles, tile_len, n;
+    EdcArgs e;                // start_in / start_div / rt60_out / targets / fit ranges / eps / floor / sr / min_samples
+};
+
+struct FitShared {
+    double warp_tot[kFitWarps];
+    double e0, inv_e0;
+    int cross_ok[kMaxTargets], cross_idx[kMaxTargets];
+    double cross_t[kMaxTargets];
+    int fit_valid[AA_MAX_FITS], fit_first[AA_MAX_FITS], fit_last[AA_MAX_FITS];
+    double fit_ts[AA_MAX_FITS], fit_te[AA_MAX_FITS];
+    double warp_acc[kFitWarps][AA_MAX_FITS * 3];
+};
+
+// One tile at sample resolution, visited by a warp from its last 128-sample step to its first:
+// f(j, scan, after) gets the step's suffix scan and the float64 energy that follows the step
+// (later steps of the tile + later tiles).
+template <int NS, class F>
+__device__ __forceinline__ void visit_tile_reverse(const float* __restrict__ y, int k, int tile_len, int n, double carry_k,
+                                                   int lane, F&& f) {
+    float4 v[NS];
+#pragma unroll
+    for (int j = 0; j < NS; ++j) {
+        const int off = j * kSub + 4 * lane;
+        const int i0 = k * tile_len + off;
+        v[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (off < tile_len) {
+            if (i0 + 3 < n) v[j] = ldg_f4(y + i0);
+            else {
+                if (i0 < n) v[j].x = __ldg(y + i0);
+                if (i0 + 1 < n) v[j].y = __ldg(y + i0 + 1);
+                if (i0 + 2 < n) v[j].z = __ldg(y + i0 + 2);
+            }
+        }
+    }
+    double after = carry_k;
+#pragma unroll
+    for (int j = NS - 1; j >= 0; --j) {
+        const TileScan sc = tile_scan(v[j]);
+        f(j, sc, after);
+        after += (double)__shfl_sync(kFullMask, __fadd_rn(sc.excl, sc.s[0]), 0);
+    }
+}
+
+template <int NS>
+__global__ void __launch_bounds__(kFitThreads) band_fit_kernel(BandFitArgs a) {
+    extern __shared__ __align__(16) unsigned char dyn_smem[];
+    __shared__ FitShared sh;
+    const int unit = blockIdx.x;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int NT = a.n_tiles, TL = a.tile_len, n = a.n;
+    double* carry = reinterpret_cast<double*>(dyn_smem);   // [NT] energy after tile k
+    float* tsum = reinterpret_cast<float*>(carry + NT);    // [NT] tile energy
+    const float* __restrict__ y = a.y + (long long)unit * a.y_stride;
+    const float* __restrict__ part = a.part + (long long)unit * a.part_stride;
+    const EdcArgs& p = a.e;
+    const int start = min(max(p.start_in[unit / p.start_div], 0), n);
+    const int n_an = n - start;
+    const float srf = (float)p.sr;
+
+    if (n_an < p.min_samples) {  // rt60bands.py:395-397: every metric None
+        if (threadIdx.x < AA_MAX_FITS) p.rt60_out[(long long)unit * AA_MAX_FITS + threadIdx.x] = nan("");
+        return;
+    }
+
+    // ---- tile energies and their float64 exclusive suffix scan
+    const int per = (NT + kFitThreads - 1) / kFitThreads;
+    const int t0 = threadIdx.x * per;
+    double mine = 0.0;
+    for (int q = 0; q < per; ++q) {
+        const int k = t0 + q;
+        if (k < NT) {
+            float s = 0.f;
+            for (int g = 0; g < a.n_groups; ++g) s += __ldg(part + (long long)g * NT + k);
+            tsum[k] = s;
+            mine += (double)s;
+        }
+    }
+    double inc = mine;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        double o = __shfl_down_sync(kFullMask, inc, d);
+        if (lane + d < 32) inc += o;
+    }
+    if (lane == 0) sh.warp_tot[warp] = inc;
+    __syncthreads();
+    {
+        double higher = 0.0;
+        for (int w = warp + 1; w < kFitWarps; ++w) higher += sh.warp_tot[w];
+        double after = __shfl_down_sync(kFullMask, inc, 1);
+        if (lane == 31) after = 0.0;
+        double running = higher + after;
+        for (int q = per - 1; q >= 0; --q) {
+            const int k = t0 + q;
+            if (k < NT) {
+                carry[k] = running;
+                running += (double)tsum[k];
+            }
+        }
+    }
+    __syncthreads();
+
+    // ---- E0 = E[start]
+    const int ks = min(start / TL, NT - 1);
+    if (warp == 0) {
+        const int pofs = start - ks * TL;
+        const int pj = pofs / kSub, pl = (pofs % kSub) >> 2, pc = pofs & 3;
+        visit_tile_reverse<NS>(y, ks, TL, n, carry[ks], lane, [&](int j, const TileScan& sc, double after) {
+            if (j == pj && lane == pl) {
+                const float sj = (pc == 0) ? sc.s[0] : (pc == 1) ? sc.s[1] : (pc == 2) ? sc.s[2] : sc.s[3];
+                const double e = after + (double)__fadd_rn(sc.excl, sj);
+                sh.e0 = e;
+                sh.inv_e0 = 1.0 / fmax(e, p.eps);
+            }
+        });
+    }
+    __syncthreads();
+    const double inv_e0 = sh.inv_e0;
+    const int n_targets = 2 + 2 * p.n_fits;
+
+    // ---- crossings (decay.py:173-199): warp w resolves target w
+    for (int tg = warp; tg < n_targets; tg += kFitWarps) {
+        const double tau = p.target[tg];
+        const float tauf = (float)tau;
+        int found = 0, idx = 0;
+        float y0 = 0.f, y1 = 0.f;
+        if (tauf >= 0.0f) {
+            found = 1;  // the curve starts at exactly 0 dB (decay.py:186-187)
+            idx = start;
+        } else {
+            int hit = -1;
+            for (int kb = ks; kb < NT && hit < 0; kb += 32) {
+                const int k = kb + lane;
+                bool ok = false;
+                if (k < NT) {
+                    const float b_next = to_db(carry[k], p.eps, inv_e0, p.floor_db);
+                    float b_first = 0.0f;
+                    if (k > ks) b_first = to_db(carry[k] + (double)tsum[k], p.eps, inv_e0, p.floor_db);
+                    ok = (b_first > tauf) && (b_next <= tauf);
+                }
+                const unsigned m = __ballot_sync(kFullMask, ok);
+                if (m) hit = kb + (__ffs(m) - 1);
+            }
+            if (hit >= 0) {
+                const int k = hit;
+                // steps are visited last to first; the curve is monotone, so the last step that reports a
+                // sample <= target holds the first such sample
+                visit_tile_reverse<NS>(y, k, TL, n, carry[k], lane, [&](int j, const TileScan& sc, double after) {
+                    int first_c = 4;
+                    float dbv = 0.f;
+                    double ev = 0.0;
+#pragma unroll
+                    for (int c = 3; c >= 0; --c) {
+                        const int off = j * kSub + 4 * lane + c;
+                        const int i = k * TL + off;
+                        const double e = after + (double)__fadd_rn(sc.excl, sc.s[c]);
+                        const float d = to_db(e, p.eps, inv_e0, p.floor_db);
+                        if (off < TL && i >= start && i < n && d <= tauf) {
+                            first_c = c;
+                            dbv = d;
+                            ev = e;
+                        }
+                    }
+                    const unsigned m = __ballot_sync(kFullMask, first_c < 4);
+                    if (m) {
+                        const int fl = __ffs(m) - 1;
+                        float py0 = 0.f;
+                        int pidx = 0;
+                        if (lane == fl) {
+                            pidx = k * TL + j * kSub + 4 * lane + first_c;
+                            // value one sample earlier: E[i-1] = E[i] + y[i-1]^2 (i > start because b_first > tau)
+                            const float yp = __ldg(y + pidx - 1);
+                            py0 = to_db(ev + (double)__fmul_rn(yp, yp), p.eps, inv_e0, p.floor_db);
+                        }
+                        found = 1;
+                        idx = __shfl_sync(kFullMask, pidx, fl);
+                        y1 = __shfl_sync(kFullMask, dbv, fl);
+                        y0 = __shfl_sync(kFullMask, py0, fl);
+                    }
+                });
+                if (!found && k + 1 < NT && (k + 1) * TL < n) {
+                    // every sample of the tile is above the target: the crossing is the first sample of tile k+1
+                    found = 1;
+                    idx = (k + 1) * TL;
+                    y1 = to_db(carry[k], p.eps, inv_e0, p.floor_db);
+                    const float yp = __ldg(y + idx - 1);
+                    y0 = to_db(carry[k] + (double)__fmul_rn(yp, yp), p.eps, inv_e0, p.floor_db);
+                }
+            }
+        }
+        if (lane == 0) {
+            sh.cross_ok[tg] = found;
+            sh.cross_idx[tg] = idx;
+            sh.cross_t[tg] = found ? crossing_time_rel(idx - start, y0, y1, tau, srf) : 0.0;
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x < p.n_fits) {
+        const int f = threadIdx.x;
+        const int ts_i = 2 + 2 * f, te_i = 3 + 2 * f;
+        int first = 0, last = -1;
+        const int valid = fit_index_range(sh.cross_ok[ts_i], sh.cross_ok[te_i], sh.cross_t[ts_i], sh.cross_t[te_i],
+                                          sh.cross_idx[ts_i] - start, sh.cross_idx[te_i] - start, srf, &first, &last);
+        sh.fit_valid[f] = valid;
+        sh.fit_first[f] = start + first;
+        sh.fit_last[f] = start + last;
+        sh.fit_ts[f] = sh.cross_t[ts_i];
+        sh.fit_te[f] = sh.cross_t[te_i];
+    }
+    __syncthreads();
+
+    // ---- regression sums over the fit ranges (decay.py:224-249)
+    double acc[AA_MAX_FITS * 3];
+#pragma unroll
+    for (int q = 0; q < AA_MAX_FITS * 3; ++q) acc[q] = 0.0;
+    int ffirst[AA_MAX_FITS], flast[AA_MAX_FITS];
+    double ymid[AA_MAX_FITS];
+    int lo = 0x7fffffff, hi = -1;
+#pragma unroll
+    for (int f = 0; f < AA_MAX_FITS; ++f) {
+        const bool on = f < p.n_fits && sh.fit_valid[f];
+        ffirst[f] = on ? sh.fit_first[f] : 0x7fffffff;
+        flast[f] = on ? sh.fit_last[f] : -1;
+        ymid[f] = 0.5 * (p.fit_hi[f] + p.fit_lo[f]);
+        if (on) {
+            lo = min(lo, ffirst[f]);
+            hi = max(hi, flast[f]);
+        }
+    }
+    if (hi >= lo) {
+        const int k_lo = lo / TL, k_hi = min(hi / TL, NT - 1);
+        for (int k = k_lo + warp; k <= k_hi; k += kFitWarps) {
+            visit_tile_reverse<NS>(y, k, TL, n, carry[k], lane, [&](int j, const TileScan& sc, double after) {
+                const int i0 = k * TL + j * kSub + 4 * lane;
+                const int s_lo = k * TL + j * kSub, s_hi = s_lo + kSub - 1;
+                bool any = false;
+#pragma unroll
+                for (int f = 0; f < AA_MAX_FITS; ++f) any |= (ffirst[f] <= s_hi && flast[f] >= s_lo);
+                if (!any) return;  // warp-uniform
+                float db[4];
+#pragma unroll
+                for (int c = 0; c < 4; ++c)
+                    db[c] = to_db(after + (double)__fadd_rn(sc.excl, sc.s[c]), p.eps, inv_e0, p.floor_db);
+#pragma unroll
+                for (int f = 0; f < AA_MAX_FITS; ++f) {
+                    if (ffirst[f] <= s_hi && flast[f] >= s_lo) {
+#pragma unroll
+                        for (int c = 0; c < 4; ++c) {
+                            const int i = i0 + c;
+                            if (j * kSub + 4 * lane + c < TL && i >= ffirst[f] && i <= flast[f]) {
+                                const double u2 = (double)(i - ffirst[f]);
+                                const double yc = (double)db[c] - ymid[f];
+                                acc[f * 3 + 0] += yc;
+                                acc[f * 3 + 1] = fma(u2, yc, acc[f * 3 + 1]);
+                                acc[f * 3 + 2] = fma(yc, yc, acc[f * 3 + 2]);
+                            }
+                        }
+                    }
+                }
+            });
+        }
+    }
+#pragma unroll
+    for (int q = 0; q < AA_MAX_FITS * 3; ++q) {
+        const double s = warp_sum(acc[q]);
+        if (lane == 0) sh.warp_acc[warp][q] = s;
+    }
+    __syncthreads();
+    if (threadIdx.x < AA_MAX_FITS) {
+        const int f = threadIdx.x;
+        double rt60 = nan("");
+        if (f < p.n_fits && sh.fit_valid[f]) {
+            double s0 = 0.0, s1 = 0.0, s2 = 0.0;
+            for (int w = 0; w < kFitWarps; ++w) {
+                s0 += sh.warp_acc[w][f * 3 + 0];
+                s1 += sh.warp_acc[w][f * 3 + 1];
+                s2 += sh.warp_acc[w][f * 3 + 2];
+            }
+            double res[AA_FIT_COLS];
+            rt60 = fit_finalize(s0, s1, s2, sh.fit_first[f] - start, sh.fit_last[f] - start, ymid[f], p.sr, sh.fit_ts[f],
+                                sh.fit_te[f], res);
+        }
+        p.rt60_out[(long long)unit * AA_MAX_FITS + f] = rt60;
+    }
+}
+
+}  // namespace
+
+int launch_band_fit(const float* d_y, long long y_stride, const float* d_part, long long part_stride, int n_groups,
+                    int n_tiles, int tile_len, int n, long long n_units, const aa_decay_params* p,
+                    const int* d_start_idx, int start_div, int min_samples, double* d_rt60_out, cudaStream_t stream) {
+    AA_REQUIRE(d_y && d_part && p && d_start_idx && d_rt60_out, AA_ERR_INVALID_ARGUMENT, "null argument");
+    AA_REQUIRE(tile_len % 4 == 0 && tile_len >= 4 && tile_len <= kSub * kMaxSub, AA_ERR_UNSUPPORTED,
+               "tile length must be a multiple of 4 and at most 1024");
+    AA_REQUIRE((long long)n_tiles * tile_len >= n && y_stride % 4 == 0, AA_ERR_INVALID_ARGUMENT, "tiles do not cover the row");
+    AA_REQUIRE(p->n_fits >= 0 && p->n_fits <= AA_MAX_FITS, AA_ERR_INVALID_ARGUMENT, "n_fits out of range");
+    AA_REQUIRE(n_units < 2147483647LL, AA_ERR_INVALID_ARGUMENT, "too many band units");
+    if (n_units <= 0) return AA_OK;
+    BandFitArgs a{};
+    int rc = edc::fill_edc_args(p, &a.e);
+    if (rc != AA_OK) return rc;
+    a.y = d_y;
+    a.y_stride = y_stride;
+    a.part = d_part;
+    a.part_stride = part_stride;
+    a.n_groups = n_groups;
+    a.n_tiles = n_tiles;
+    a.tile_len = tile_len;
+    a.n = n;
+    a.e.start_in = d_start_idx;
+    a.e.start_div = start_div > 0 ? start_div : 1;
+    a.e.rt60_out = d_rt60_out;
+    a.e.min_samples = min_samples;
+    const size_t smem = (size_t)n_tiles * (sizeof(double) + sizeof(float));
+    AA_REQUIRE(smem <= 48 * 1024, AA_ERR_UNSUPPORTED, "too many tiles");
+    const unsigned grid = (unsigned)n_units;
+    switch ((tile_len + kSub - 1) / kSub) {
+        case 1: band_fit_kernel<1><<<grid, kFitThreads, smem, stream>>>(a); break;
+        case 2: band_fit_kernel<2><<<grid, kFitThreads, smem, stream>>>(a); break;
+        case 3: band_fit_kernel<3><<<grid, kFitThreads, smem, stream>>>(a); break;
+        case 4: band_fit_kernel<4><<<grid, kFitThreads, smem, stream>>>(a); break;
+        case 5: band_fit_kernel<5><<<grid, kFitThreads, smem, stream>>>(a); break;
+        case 6: band_fit_kernel<6><<<grid, kFitThreads, smem, stream>>>(a); break;
+        case 7: band_fit_kernel<7><<<grid, kFitThreads, smem, stream>>>(a); break;
+        default: band_fit_kernel<8><<<grid, kFitThreads, smem, stream>>>(a); break;
+    }
+    return launch_check("band_fit_kernel");
+}
+
+}  // namespace aa

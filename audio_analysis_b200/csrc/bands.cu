@@ -103,8 +103,34 @@ int make_band_dev(const aa_band& b, double tw_oct, double nyq, double freq_scale
     return AA_OK;
 }
 
+// band table + mask tables -> device (same stream as the transforms that read them)
+int upload_bands(const aa_band* bands, int nb, double tw_oct, double nyq, double freq_scale, int N, BandDev* d_bands,
+                 float* d_mask, cudaStream_t stream) {
+    std::vector<BandDev> hb((size_t)nb);
+    size_t mask_off = 0;
+    int widest = 0;
+    for (int i = 0; i < nb; ++i) {
+        int rc = make_band_dev(bands[i], tw_oct, nyq, freq_scale, N / 2 + 1, &hb[(size_t)i]);
+        if (rc != AA_OK) return rc;
+        const int support = hb[(size_t)i].k_last - hb[(size_t)i].k_first + 1;
+        hb[(size_t)i].mask = d_mask + mask_off;
+        if (support > 0) mask_off += (size_t)support;
+        if (support > widest) widest = support;
+    }
+    // pageable-memory async copies are staged before returning, so the host vector may go out of scope
+    AA_CUDA_TRY(cudaMemcpyAsync(d_bands, hb.data(), sizeof(BandDev) * (size_t)nb, cudaMemcpyHostToDevice, stream));
+    if (widest > 0) {
+        int bx = (widest + 255) / 256;
+        if (bx > 64) bx = 64;
+        band_mask_kernel<<<dim3((unsigned)bx, (unsigned)nb), 256, 0, stream>>>(d_bands, freq_scale);
+        int rc = launch_check("band_mask_kernel");
+        if (rc != AA_OK) return rc;
+    }
+    return AA_OK;
+}
+
 struct Layout {
-    size_t off_bands, off_mask, off_X, off_y, off_scratch, off_db0, off_db1, off_unit_start, total;
+    size_t off_bands, off_mask, off_X, off_y, off_scratch, off_part, off_db0, off_db1, off_unit_start, total;
 };
 
 Layout make_layout(const aa_bands_plan* p, long long rows, int nb, bool smoothing = false) {
@@ -123,6 +149,12 @@ Layout make_layout(const aa_bands_plan* p, long long rows, int nb, bool smoothin
     o += align_up(ybytes > zbytes ? ybytes : zbytes);
     l.off_scratch = o;
     o += align_up(sizeof(float2) * c2c_scratch_elems(p->c2c, units));
+    {  // per-tile energy partials of the band signals (register-pass lengths; bandfit.cu)
+        int tile_c = 0, n_tiles = 0, n_groups = 0;
+        l.off_part = o;
+        if (c2c_energy_layout(p->c2c, &tile_c, &n_tiles, &n_groups))
+            o += align_up(sizeof(float) * (size_t)units * (size_t)n_tiles * (size_t)n_groups);
+    }
     if (smoothing) {  // dB curves of the band signals, before and after the box filter (decay.py:161-164)
         l.off_db0 = o;
         o += align_up(sizeof(float) * (size_t)units * (size_t)p->y_stride);
@@ -215,27 +247,11 @@ int rt60bands_batch(const aa_bands_plan* plan, const float* d_x, long long row_s
     float2* d_Z = reinterpret_cast<float2*>(ws + lay.off_y);
     float2* d_scr = reinterpret_cast<float2*>(ws + lay.off_scratch);
 
-    std::vector<BandDev> hb((size_t)nb);
-    float* d_mask = reinterpret_cast<float*>(ws + lay.off_mask);
-    size_t mask_off = 0;
-    int widest = 0;
-    for (int i = 0; i < nb; ++i) {
-        int rc = make_band_dev(bands[i], tw_oct, nyq, freq_scale, N / 2 + 1, &hb[(size_t)i]);
-        if (rc != AA_OK) return rc;
-        const int support = hb[(size_t)i].k_last - hb[(size_t)i].k_first + 1;
-        hb[(size_t)i].mask = d_mask + mask_off;
-        if (support > 0) mask_off += (size_t)support;
-        if (support > widest) widest = support;
-    }
-    AA_CUDA_TRY(cudaMemcpyAsync(d_bands, hb.data(), sizeof(BandDev) * (size_t)nb, cudaMemcpyHostToDevice, stream));
-    if (widest > 0) {
-        int bx = (widest + 255) / 256;
-        if (bx > 64) bx = 64;
-        band_mask_kernel<<<dim3((unsigned)bx, (unsigned)nb), 256, 0, stream>>>(d_bands, freq_scale);
-        int rc = launch_check("band_mask_kernel");
+    {
+        int rc = upload_bands(bands, nb, tw_oct, nyq, freq_scale, N, d_bands, reinterpret_cast<float*>(ws + lay.off_mask),
+                              stream);
         if (rc != AA_OK) return rc;
     }
-    // the host vector must outlive the copy: pageable-memory async copies are staged before returning
 
     for (long long r0 = 0; r0 < n_rows; r0 += rc_rows) {
         const long long rows = (n_rows - r0 < rc_rows) ? (n_rows - r0) : rc_rows;
@@ -289,6 +305,13 @@ int rt60bands_batch(const aa_bands_plan* plan, const float* d_x, long long row_s
             d.scale1 = 1.0f / (float)N;
             d.scale2 = 1.0f;
         }
+        int tile_c = 0, n_tiles = 0, n_groups = 0;
+        const bool tiled = even && !smoothing && c2c_energy_layout(plan->c2c, &tile_c, &n_tiles, &n_groups);
+        float* d_part = reinterpret_cast<float*>(ws + lay.off_part);
+        if (tiled) {
+            d.energy = d_part;
+            d.energy_stride = (long long)n_tiles * n_groups;
+        }
         rc = c2c_exec(plan->c2c, s, d, units, d_scr, stream);
         if (rc != AA_OK) return rc;
         if (d_band_signal_out) {
@@ -297,7 +320,14 @@ int rt60bands_batch(const aa_bands_plan* plan, const float* d_x, long long row_s
                                           (size_t)units, cudaMemcpyDeviceToDevice, stream));
         }
         // ---- 3. band EDC + fits, metrics only
-        if (!smoothing) {
+        if (tiled) {
+            // the rows pass left the energy of every tile of 2 M1 samples next to the signal: suffix-scan those and
+            // revisit only the tiles with the start sample, a crossing or fit points
+            rc = launch_band_fit(d_y, plan->y_stride, d_part, (long long)n_tiles * n_groups, n_groups, n_tiles,
+                                 2 * tile_c, N, units, &pk, d_start_idx + r0, nb, 8,
+                                 d_metrics_out + r0 * nb * AA_MAX_FITS, stream);
+            if (rc != AA_OK) return rc;
+        } else if (!smoothing) {
             rc = launch_edc(d_y, plan->y_stride, nullptr, N, N, (int)units, &pk, d_start_idx + r0, nb, 8, nullptr, 0,
                             nullptr, nullptr, d_metrics_out + r0 * nb * AA_MAX_FITS, nullptr, nullptr, stream);
             if (rc != AA_OK) return rc;

@@ -277,8 +277,6 @@ __global__ void __launch_bounds__(P::kThreads) fft_cols_reg(SrcDesc src, float2*
     float2* colq = tws + P::L;
     const int unit = blockIdx.x / groups;
     const int col0 = (blockIdx.x - unit * groups) * P::G;
-    reg_fill_twiddles<P>((int)threadIdx.x, P::kThreads, tws, tw_full);
-    reg_cols_fill_colq<P>((int)threadIdx.x, colq, col0, twM);
     if (kSrc == SRC_BAND_PACKED) {
         const int row = unit / src.n_bands;
         RegSrcBand s;
@@ -295,25 +293,47 @@ __global__ void __launch_bounds__(P::kThreads) fft_cols_reg(SrcDesc src, float2*
         RegSrcComplex s{(const float2*)((const float*)src.base + (size_t)unit * src.unit_stride)};
         reg_cols_stage_a<P>((int)threadIdx.x, s, M2, col0, buf);
     }
+    // stage B's tables are filled after stage A's loads have been issued: their latency hides behind the butterflies
+    reg_fill_twiddles<P>((int)threadIdx.x, P::kThreads, tws, tw_full);
+    reg_cols_fill_colq<P>((int)threadIdx.x, colq, col0, twM);
     __syncthreads();
     reg_cols_stage_b<P>((int)threadIdx.x, buf, tws, colq, scratch + (size_t)unit * ((size_t)P::L * M2), M2, col0, twM);
 }
 
-template <class P, int M1>
+template <class P, int M1, bool kEnergy>
 __global__ void __launch_bounds__(P::kThreads) fft_rows_reg(const float2* __restrict__ scratch, float2* __restrict__ out,
                                                             long long out_stride, int n_valid, int conj, float scale,
-                                                            const float2* __restrict__ tw_full) {
+                                                            const float2* __restrict__ tw_full, float* __restrict__ energy,
+                                                            long long energy_stride) {
     static_assert(M1 % P::G == 0, "rows must split evenly over CTAs");
+    static_assert(!kEnergy || (P::G == 8 && P::kThreadsB % 32 == 0), "energy partials reduce over 8-lane groups");
     constexpr int groups = M1 / P::G;
     extern __shared__ float2 smem[];
     float2* buf = smem;
     float2* tws = smem + P::kBufElems;
     const int unit = blockIdx.x / groups;
-    const int row0 = (blockIdx.x - unit * groups) * P::G;
-    reg_fill_twiddles<P>((int)threadIdx.x, P::kThreads, tws, tw_full);
+    const int rg = blockIdx.x - unit * groups;
+    const int row0 = rg * P::G;
     reg_rows_stage_a<P>((int)threadIdx.x, scratch + (size_t)unit * ((size_t)M1 * P::L), row0, buf);
+    reg_fill_twiddles<P>((int)threadIdx.x, P::kThreads, tws, tw_full);  // after stage A's loads are in flight
     __syncthreads();
-    reg_rows_stage_b<P>((int)threadIdx.x, buf, tws, out + (size_t)unit * out_stride, M1, row0, n_valid, conj, scale);
+    if (kEnergy) {
+        float e[P::RB];
+        reg_rows_stage_b<P>((int)threadIdx.x, buf, tws, out + (size_t)unit * out_stride, M1, row0, n_valid, conj, scale, e);
+        // sum over the 8 rows of the group: g is the low 3 bits of the lane index
+        float* __restrict__ dst = energy + (size_t)unit * energy_stride + (size_t)rg * P::L;
+        const int jb = (int)threadIdx.x / P::G, g = (int)threadIdx.x - jb * P::G;
+#pragma unroll
+        for (int q = 0; q < P::RB; ++q) {
+            float v = e[q];
+            v += __shfl_xor_sync(0xffffffffu, v, 1);
+            v += __shfl_xor_sync(0xffffffffu, v, 2);
+            v += __shfl_xor_sync(0xffffffffu, v, 4);
+            if (g == 0 && threadIdx.x < P::kThreadsB) dst[jb + q * P::RA] = v;
+        }
+    } else {
+        reg_rows_stage_b<P>((int)threadIdx.x, buf, tws, out + (size_t)unit * out_stride, M1, row0, n_valid, conj, scale);
+    }
 }
 
 template <int kSrc>
@@ -340,14 +360,23 @@ bool launch_rows_reg(const C2CPlan* p, const float2* scratch, const DstDesc& dst
 #define X(ra1, rb1, g1, ra2, rb2, g2)                                                                         \
     if (p->M1 == ra1 * rb1 && p->M2 == ra2 * rb2) {                                                           \
         using P = RegCfg<ra2, rb2, g2>;                                                                       \
-        auto k = fft_rows_reg<P, ra1 * rb1>;                                                                  \
         static bool once = false;                                                                             \
         if (!once) {                                                                                          \
-            cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)P::kSmemBytes);         \
+            cudaFuncSetAttribute(fft_rows_reg<P, ra1 * rb1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                                 (int)P::kSmemBytes);                                                         \
+            cudaFuncSetAttribute(fft_rows_reg<P, ra1 * rb1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                                 (int)P::kSmemBytes);                                                         \
             once = true;                                                                                      \
         }                                                                                                     \
-        k<<<(unsigned)(units * ((ra1 * rb1) / g2)), P::kThreads, P::kSmemBytes, stream>>>(                    \
-            scratch, (float2*)dst.base, dst.unit_stride, dst.n_valid, dst.conj1, dst.scale1, p->s2.dev.tw);   \
+        const unsigned grid = (unsigned)(units * ((ra1 * rb1) / g2));                                         \
+        if (dst.energy)                                                                                       \
+            fft_rows_reg<P, ra1 * rb1, true><<<grid, P::kThreads, P::kSmemBytes, stream>>>(                   \
+                scratch, (float2*)dst.base, dst.unit_stride, dst.n_valid, dst.conj1, dst.scale1, p->s2.dev.tw, \
+                dst.energy, dst.energy_stride);                                                               \
+        else                                                                                                  \
+            fft_rows_reg<P, ra1 * rb1, false><<<grid, P::kThreads, P::kSmemBytes, stream>>>(                  \
+                scratch, (float2*)dst.base, dst.unit_stride, dst.n_valid, dst.conj1, dst.scale1, p->s2.dev.tw, \
+                nullptr, 0);                                                                                  \
         return true;                                                                                          \
     }
     AA_REG_LIST(X)
@@ -434,6 +463,10 @@ int exec_direct(const C2CPlan* p, const SrcDesc& src, const DstDesc& dst, long l
     const bool spec2 = getenv("AA_FFT_GENERIC") == nullptr && p->M1 > 1 && src_plain && dst_plain &&
                        units * (long long)p->M < 2147483647LL &&
                        launch_rows_reg(p, scratch, dst, units, stream);
+    if (!spec2 && dst.energy != nullptr) {
+        set_error("energy partials need the register-pass rows kernel");
+        return AA_ERR_UNSUPPORTED;
+    }
     if (spec2) {
     } else if (src_plain && dst_plain)
         fft_pass2_kernel<SRC_COMPLEX, DST_COMPLEX><<<g, kPassThreads, p->smem2, stream>>>(pa, src2, dst);
@@ -470,6 +503,22 @@ int build_direct(int M, C2CPlan* p) {
 }  // namespace
 
 bool is_smooth(long long n) { return is_smooth_host(n); }
+
+// Tiles of the energy partials a DstDesc may request from c2c_exec: rows are transformed in groups of 8, so a
+// transform's outputs fall into M2 tiles of M1 consecutive complex values and M1 / 8 partial sums per tile.
+bool c2c_energy_layout(const C2CPlan* p, int* tile_complex, int* n_tiles, int* n_groups) {
+    if (p->bluestein || p->M1 <= 1 || getenv("AA_FFT_GENERIC") != nullptr) return false;
+#define X(ra1, rb1, g1, ra2, rb2, g2)                                              \
+    if (p->M1 == (ra1) * (rb1) && p->M2 == (ra2) * (rb2) && (g2) == 8) {           \
+        *tile_complex = p->M1;                                                     \
+        *n_tiles = p->M2;                                                          \
+        *n_groups = p->M1 / (g2);                                                  \
+        return true;                                                               \
+    }
+    AA_REG_LIST(X)
+#undef X
+    return false;
+}
 
 int build_two_level(long long len, TwoLevelTable* out) {
     HostTwoLevel h;

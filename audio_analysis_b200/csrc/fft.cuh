@@ -33,6 +33,8 @@ struct C2CPlan {
     float2* d_H = nullptr;      // FFT_P of the wrapped conjugate chirp
 };
 
+// layout of the optional energy partials (DstDesc::energy); false when this plan cannot produce them
+bool c2c_energy_layout(const C2CPlan* p, int* tile_complex, int* n_tiles, int* n_groups);
 // true if n factors completely into the supported radices
 bool is_smooth(long long n);
 int build_two_level(long long len, TwoLevelTable* out);

@@ -99,6 +99,14 @@ AA_HD float2 load_c(const float2* p) {
     return *p;
 #endif
 }
+// L2-only load (ld.global.cg): for buffers rewritten by other SMs during the same kernel
+AA_HD float2 load_c_cg(const float2* p) {
+#ifdef __CUDA_ARCH__
+    return __ldcg(p);
+#else
+    return *p;
+#endif
+}
 AA_HD float load_r(const float* p) {
 #ifdef __CUDA_ARCH__
     return __ldg(p);
@@ -206,6 +214,10 @@ struct DstDesc {
     int conj2;            // 4. conjugate        (caller-level inverse on top of Bluestein)
     float scale2;         // 5. scale
     const float2* table;  // DST_MUL_TABLE
+    // optional (register-pass lengths only, see c2c_energy_layout): per-tile energy partials of the stored values,
+    // energy[unit * energy_stride + row_group * M2 + k2] = sum over the group's rows k1 of |out[k2 * M1 + k1]|^2
+    float* energy;
+    long long energy_stride;
 };
 
 AA_HD void dst_put(const DstDesc& d, long long unit, int idx, float2 v) {

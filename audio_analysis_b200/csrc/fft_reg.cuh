@@ -135,7 +135,7 @@ AA_HD void reg_cols_stage_b(int t, const float2* buf, const float2* tws, const f
 
 // ---- pass 2: rows.  CTA = G adjacent rows k1, transform over n2 (contiguous), output [k2 * M1 + row] ----------
 
-template <class P>
+template <class P, bool kCg = false>
 AA_HD void reg_rows_stage_a(int t, const float2* scratch_unit, int row0, float2* buf) {
     if (t >= P::kThreadsA) return;
     const int ja = t / P::G, g = t - ja * P::G;
@@ -143,7 +143,7 @@ AA_HD void reg_rows_stage_a(int t, const float2* scratch_unit, int row0, float2*
     float2 v[P::RA];
     static_for<0, P::RA>([&](auto r_) {
         constexpr int r = decltype(r_)::value;
-        v[r] = load_c(in + r * P::RB);
+        v[r] = kCg ? load_c_cg(in + r * P::RB) : load_c(in + r * P::RB);
     });
     dft_r<P::RA>(v);
     static_for<0, P::RA>([&](auto r_) {
@@ -152,9 +152,11 @@ AA_HD void reg_rows_stage_a(int t, const float2* scratch_unit, int row0, float2*
     });
 }
 
+// energy != nullptr: also returns |output|^2 of the thread's RB outputs (the band signal's two real samples per
+// complex output), for the per-tile energy partials that feed the band EDC (bands.cu: band_fit_kernel)
 template <class P>
 AA_HD void reg_rows_stage_b(int t, const float2* buf, const float2* tws, float2* out_unit, int M1, int row0,
-                            int n_valid, int conj, float scale) {
+                            int n_valid, int conj, float scale, float* energy = nullptr) {
     if (t >= P::kThreadsB) return;
     const int jb = t / P::G, g = t - jb * P::G;
     float2 v[P::RB];
@@ -168,11 +170,11 @@ AA_HD void reg_rows_stage_b(int t, const float2* buf, const float2* tws, float2*
     static_for<0, P::RB>([&](auto q_) {
         constexpr int q = decltype(q_)::value;
         const int idx = (jb + q * P::RA) * M1 + row;
-        if (idx < n_valid) {
-            float2 o = v[q];
-            if (conj) o.y = -o.y;
-            out_unit[idx] = cscale(o, scale);
-        }
+        float2 o = v[q];
+        if (conj) o.y = -o.y;
+        o = cscale(o, scale);
+        if (energy) energy[q] = (idx < n_valid) ? o.x * o.x + o.y * o.y : 0.0f;
+        if (idx < n_valid) out_unit[idx] = o;
     });
 }
 

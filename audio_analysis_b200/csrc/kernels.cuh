@@ -32,3 +32,12 @@ int launch_box_smooth(const float* d_in, float* d_out, long long stride, const i
                       const int* d_offsets, int n_rows, int window, double floor_db, cudaStream_t stream);
 
 }  // namespace aa
+
+namespace aa {
+
+// band EDC / fits from the energy partials written by the register-pass rows kernel (bandfit.cu)
+int launch_band_fit(const float* d_y, long long y_stride, const float* d_part, long long part_stride, int n_groups,
+                    int n_tiles, int tile_len, int n, long long n_units, const aa_decay_params* p,
+                    const int* d_start_idx, int start_div, int min_samples, double* d_rt60_out, cudaStream_t stream);
+
+}  // namespace aa
