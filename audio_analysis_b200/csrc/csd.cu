@@ -12,6 +12,7 @@
 // bins.  The running maximum stays on chip; a final in-place pass over the
 // CTA's own (L2-resident) output applies the reference level and the clip.
 #include <math.h>
+#include <stdlib.h>
 
 #include <map>
 #include <mutex>
@@ -20,6 +21,9 @@
 #include "aa_common.cuh"
 #include "fft_access.cuh"
 #include "fft_plan_host.hpp"
+#include "fft_spec.cuh"
+
+#include <cooperative_groups.h>
 
 namespace aa {
 
@@ -32,7 +36,19 @@ struct CsdTables {
     float2* d_tw = nullptr;
     float2* d_twN = nullptr;  // exp(-2 pi i k / n_fft), k in [0, n_fft/2]
     float* d_hann = nullptr;  // np.hanning(n_fft) (waterfall.py:212)
+    float2* d_twc = nullptr;  // compact per-stage twiddles of the compile-time radix chain (TMA kernel), or nullptr
 };
+
+// radix chains of the TMA kernel's n_fft/2-point transforms (must match csd_tma_dispatch below)
+inline bool tma_chain(int M, std::vector<int>* r) {
+    switch (M) {
+        case 512: *r = {8, 8, 8}; return true;
+        case 1024: *r = {4, 4, 8, 8}; return true;
+        case 2048: *r = {4, 8, 8, 8}; return true;
+        case 4096: *r = {8, 8, 8, 8}; return true;
+        default: return false;
+    }
+}
 
 std::mutex g_mu;
 std::map<std::pair<int, int>, CsdTables> g_tables;  // (device, n_fft) -> immutable tables
@@ -71,6 +87,21 @@ int get_tables(int n_fft, CsdTables* out) {
     AA_CUDA_TRY(cudaMemcpy(t.d_tw, hp.tw.data(), sizeof(float2) * (size_t)M, cudaMemcpyHostToDevice));
     AA_CUDA_TRY(cudaMemcpy(t.d_twN, twn.data(), sizeof(float2) * ((size_t)M + 1), cudaMemcpyHostToDevice));
     AA_CUDA_TRY(cudaMemcpy(t.d_hann, hann.data(), sizeof(float) * (size_t)n_fft, cudaMemcpyHostToDevice));
+    std::vector<int> chain;
+    if (tma_chain(M, &chain)) {  // same layout as spec_twiddles() builds in shared memory (fft_spec.cuh)
+        std::vector<float2> twc((size_t)M, make_float2(1.f, 0.f));
+        int Ns = 1;
+        for (int R : chain) {
+            const int tmul = M / (Ns * R);
+            for (int m = 0; m < Ns * (R - 1); ++m) {
+                const int r1 = m / Ns, k = m % Ns;
+                twc[(size_t)compact_twiddle_offset(Ns) + m] = hp.tw[(size_t)((r1 + 1) * k * tmul)];
+            }
+            Ns *= R;
+        }
+        AA_CUDA_TRY(cudaMalloc(&t.d_twc, sizeof(float2) * (size_t)M));
+        AA_CUDA_TRY(cudaMemcpy(t.d_twc, twc.data(), sizeof(float2) * (size_t)M, cudaMemcpyHostToDevice));
+    }
     t.sp.tw = t.d_tw;
     g_tables[key] = t;
     *out = t;
@@ -95,6 +126,7 @@ struct CsdArgs {
     SubPlanDev sp;
     const float2* twN;
     const float* hann;
+    const float2* twc;
 };
 
 __device__ __forceinline__ float block_max(float v, float* red) {
@@ -199,6 +231,226 @@ __global__ void __launch_bounds__(kCsdThreads) csd_kernel(CsdArgs a) {
     }
 }
 
+// ---------------------------------------------------------------------------------------------
+// TMA kernel: a cluster of CTAs per row, each CTA owning every C-th selected frame.
+//   * frames are staged by 1-D bulk copies (cp.async.bulk -> UBLKCP) of the 16-byte aligned superset of the
+//     frame into a two-deep shared-memory ring, completion on an mbarrier: the next frame lands while the
+//     current one is transformed;
+//   * compile-time radix chain with a padded shared-memory layout (fft_spec.cuh);
+//   * the CTA keeps its slices' dB values in shared memory, the cluster agrees on the reference level through
+//     distributed shared memory, and every output value is written to HBM exactly once, already normalised and
+//     clipped (waterfall.py:328-339): traffic = frames in + slices out, the algorithmic minimum.
+// ---------------------------------------------------------------------------------------------
+namespace cg = cooperative_groups;
+
+constexpr int kTmaFramesPerCta = 3;
+constexpr int kTmaPad = 4;
+
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra DONE_%=;\n"
+        "bra WAIT_%=;\n"
+        "DONE_%=:\n"
+        "}\n" ::"r"(smem_u32(bar)),
+        "r"(parity)
+        : "memory");
+}
+// global -> shared bulk copy; dst, src and bytes are multiples of 16
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, unsigned bytes, unsigned long long* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     smem_u32(dst)),
+                 "l"(src), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+
+template <int M>
+struct TmaCfg {
+    static constexpr int kNfft = 2 * M;
+    static constexpr int kRawFloats = kNfft + 8;                 // aligned superset of a frame
+    static constexpr int kFftElems = M + (M >> kTmaPad);         // padded complex buffer
+    static constexpr size_t kRawBytes = sizeof(float) * 2 * (size_t)kRawFloats;
+    static constexpr size_t kFftBytes = sizeof(float2) * 2 * (size_t)kFftElems;
+    static size_t smem_bytes(int n_bins) {
+        return kRawBytes + kFftBytes + sizeof(float) * (size_t)kTmaFramesPerCta * (size_t)((n_bins + 3) & ~3);
+    }
+};
+
+template <int M, int... Rs>
+__global__ void __launch_bounds__(kCsdThreads) csd_tma_kernel(CsdArgs a) {
+    using Cfg = TmaCfg<M>;
+    cg::cluster_group cluster = cg::this_cluster();
+    const int C = (int)cluster.num_blocks();
+    const int rank = (int)cluster.block_rank();
+    const int row = blockIdx.x / C;
+    extern __shared__ __align__(16) unsigned char dyn_smem[];
+    float* raw = reinterpret_cast<float*>(dyn_smem);                       // [2][kRawFloats]
+    float2* fa = reinterpret_cast<float2*>(dyn_smem + Cfg::kRawBytes);   // [kFftElems]
+    float2* fb = fa + Cfg::kFftElems;
+    float* outs = reinterpret_cast<float*>(dyn_smem + Cfg::kRawBytes + Cfg::kFftBytes);
+    const int out_pitch = (a.n_bins + 3) & ~3;
+    __shared__ unsigned long long bars[2];
+    __shared__ float red[kCsdThreads / 32];
+    __shared__ float cta_max;
+    __shared__ float slice_ref[kTmaFramesPerCta];
+
+    const int len = a.lengths ? a.lengths[row] : a.uniform_len;
+    const float* __restrict__ x = a.x + (long long)row * a.row_stride;
+    const int start = a.start_idx[row];
+    const int ns = min(a.n_slices[row], a.max_slices);
+    const int len4 = (len + 3) & ~3;
+    const int n_mine = (ns > rank) ? (ns - rank + C - 1) / C : 0;   // slices rank, rank + C, ...
+
+    auto frame_start = [&](int i) { return start + a.frame_idx[(long long)row * a.max_slices + rank + i * C] * a.hop; };
+    // thread 0 stages frame i into ring slot i & 1 (bulk copy when the aligned superset lies inside the row)
+    auto stage_frame = [&](int i) {
+        const int f0 = frame_start(i);
+        const int a0 = f0 & ~3;
+        const int nvec = (Cfg::kNfft + (f0 - a0) + 3) >> 2;
+        if (f0 >= 0 && a0 + 4 * nvec <= len4) {
+            mbar_expect_tx(&bars[i & 1], 16u * (unsigned)nvec);
+            bulk_g2s(raw + (i & 1) * Cfg::kRawFloats, x + a0, 16u * (unsigned)nvec, &bars[i & 1]);
+        }
+    };
+    if (threadIdx.x == 0) {
+        mbar_init(&bars[0], 1);
+        mbar_init(&bars[1], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        if (n_mine > 0) stage_frame(0);
+        if (n_mine > 1) stage_frame(1);
+    }
+    __syncthreads();
+
+    float run_max = -INFINITY;
+    for (int i = 0; i < n_mine; ++i) {
+        const int f0 = frame_start(i);
+        const int a0 = f0 & ~3;
+        const int shift = f0 - a0;
+        const int nvec = (Cfg::kNfft + shift + 3) >> 2;
+        float* rb = raw + (i & 1) * Cfg::kRawFloats;
+        if (f0 >= 0 && a0 + 4 * nvec <= len4) {
+            mbar_wait(&bars[i & 1], (unsigned)((i >> 1) & 1));
+        } else {  // frame sticks out of the row (not produced by the host-side frame selection): guarded loads
+            for (int q = threadIdx.x; q < nvec; q += kCsdThreads) {
+                const int g = a0 + 4 * q;
+                float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (g >= 0 && g + 4 <= len4) v = ldg_f4(x + g);
+                reinterpret_cast<float4*>(rb)[q] = v;
+            }
+            __syncthreads();
+        }
+        // window (waterfall.py:223) and pack z[m] = (w x)[2m] + i (w x)[2m+1]
+        for (int m = threadIdx.x; m < M; m += kCsdThreads) {
+            float x0 = rb[shift + 2 * m], x1 = rb[shift + 2 * m + 1];
+            if (f0 + 2 * m >= len) x0 = 0.f;
+            if (f0 + 2 * m + 1 >= len) x1 = 0.f;
+            if (a.use_hann) {
+                const float2 w = __ldg(reinterpret_cast<const float2*>(a.hann) + m);
+                x0 *= w.x;
+                x1 *= w.y;
+            }
+            fa[pad_index<kTmaPad>(m)] = make_float2(x0, x1);
+        }
+        __syncthreads();  // ring slot consumed
+        if (threadIdx.x == 0 && i + 2 < n_mine) {
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic reads before the async overwrite
+            stage_frame(i + 2);
+        }
+        float2* pa = fa;
+        float2* pb = fb;
+        spec_stages<kCsdThreads, kTmaPad, M, 1, Cfg::kFftElems, 1, Rs...>(pa, pb, a.twc, a.sp.tw);
+        // untangle -> |X|^2 -> dB, cropped to [bin_lo, bin_lo + n_bins)   (waterfall.py:224-227, :304-309)
+        float smax = -INFINITY;
+        float* __restrict__ o = outs + i * out_pitch;
+        for (int b = threadIdx.x; b < a.n_bins; b += kCsdThreads) {
+            const int k = a.bin_lo + b;
+            const float2 zk = pa[pad_index<kTmaPad>(k == M ? 0 : k)];
+            const float2 zm = pa[pad_index<kTmaPad>((M - k) == M ? 0 : (M - k))];
+            const float2 X = untangle_half_spectrum(zk, zm, __ldg(a.twN + k));
+            const float p = fmaxf(X.x * X.x + X.y * X.y, a.floor_lin_sq);
+            const float db = 10.0f * log10f(p);
+            o[b] = db;
+            smax = fmaxf(smax, db);
+        }
+        if (a.db_reference == AA_DBREF_SLICE_MAX) {
+            const float m = block_max(smax, red);
+            if (threadIdx.x == 0) slice_ref[i] = m;
+        } else {
+            run_max = fmaxf(run_max, smax);
+        }
+        __syncthreads();  // fa / fb free for the next frame
+    }
+    float gref = 0.f;
+    if (a.db_reference == AA_DBREF_GLOBAL_MAX) {  // waterfall.py:335: one level for all slices of the row
+        const float m = block_max(run_max, red);
+        if (threadIdx.x == 0) cta_max = m;
+        cluster.sync();
+        gref = -INFINITY;
+        for (int r = 0; r < C; ++r) gref = fmaxf(gref, *cluster.map_shared_rank(&cta_max, r));
+    }
+    __syncthreads();
+    float* __restrict__ out_row = a.out + (long long)row * a.max_slices * a.n_bins;
+    for (int i = 0; i < n_mine; ++i) {
+        const float ref = (a.db_reference == AA_DBREF_SLICE_MAX) ? slice_ref[i] : gref;
+        const float* __restrict__ src = outs + i * out_pitch;
+        float* __restrict__ o = out_row + (long long)(rank + i * C) * a.n_bins;
+        for (int b = threadIdx.x; b < a.n_bins; b += kCsdThreads) {
+            float v = src[b];
+            if (a.db_reference != AA_DBREF_NONE) v = fminf(fmaxf(v - ref, -a.dyn), 0.0f);  // waterfall.py:338-339
+            __stcs(o + b, v);
+        }
+    }
+    if (a.db_reference == AA_DBREF_GLOBAL_MAX) cluster.sync();  // peers may still be reading cta_max
+}
+
+template <int M, int... Rs>
+int launch_csd_tma(const CsdArgs& a, int n_rows, int cluster, cudaStream_t stream) {
+    auto kern = csd_tma_kernel<M, Rs...>;
+    const size_t smem = TmaCfg<M>::smem_bytes(a.n_bins);
+    AA_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3((unsigned)((long long)n_rows * cluster));
+    cfg.blockDim = dim3(kCsdThreads);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = (unsigned)cluster;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    AA_CUDA_TRY(cudaLaunchKernelEx(&cfg, kern, a));
+    count_launch();
+    return AA_OK;
+}
+
+// returns AA_ERR_UNSUPPORTED when the TMA kernel does not cover the request (the caller falls back)
+int csd_tma_dispatch(const CsdArgs& a, int n_rows, cudaStream_t stream) {
+    if (a.twc == nullptr || getenv("AA_CSD_GENERIC") != nullptr) return AA_ERR_UNSUPPORTED;
+    const int cluster = (a.max_slices + kTmaFramesPerCta - 1) / kTmaFramesPerCta;
+    if (cluster > 8) return AA_ERR_UNSUPPORTED;
+    switch (a.n_fft) {
+        case 1024: return launch_csd_tma<512, 8, 8, 8>(a, n_rows, cluster, stream);
+        case 2048: return launch_csd_tma<1024, 4, 4, 8, 8>(a, n_rows, cluster, stream);
+        case 4096: return launch_csd_tma<2048, 4, 8, 8, 8>(a, n_rows, cluster, stream);
+        case 8192: return launch_csd_tma<4096, 8, 8, 8, 8>(a, n_rows, cluster, stream);
+        default: return AA_ERR_UNSUPPORTED;
+    }
+}
+
 __global__ void pcm16_kernel(const short* __restrict__ pcm, long long pcm_stride, int n_frames, int n_channels,
                              int mode, float* __restrict__ out, long long out_stride) {
     const int file = blockIdx.y;
@@ -257,6 +509,11 @@ int launch_csd(const float* d_x, long long row_stride, const int* d_lengths, int
     a.sp = t.sp;
     a.twN = t.d_twN;
     a.hann = t.d_hann;
+    a.twc = t.d_twc;
+    {
+        const int rc_tma = csd_tma_dispatch(a, n_rows, stream);
+        if (rc_tma != AA_ERR_UNSUPPORTED) return rc_tma;
+    }
     const size_t smem = sizeof(float2) * (size_t)p->n_fft + sizeof(float) * ((size_t)p->n_fft + 8);
     AA_CUDA_TRY(cudaFuncSetAttribute(csd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 1024));
     csd_kernel<<<n_rows, kCsdThreads, smem, stream>>>(a);
