@@ -47,6 +47,18 @@ constexpr unsigned kFullMask = 0xffffffffu;
 // 10*log10(2): dB per octave of energy ratio.
 __device__ __forceinline__ float db10_from_ratio(float r) { return 3.010299956639812f * log2f(r); }
 
+// 10*log10(r) for a positive normal float32 r: log2 r = exponent + log2(mantissa), with the hardware log2
+// (absolute error about 2^-22 on [1, 2)) applied to the mantissa only, so the error stays at 1e-6 dB where the
+// plain fast intrinsic would lose two ulps of a value near -40.  The two roundings (product, fused sum) are
+// monotone, which keeps a monotone input sequence monotone.
+__device__ __forceinline__ float db10_from_ratio_fast(float r) {
+    const int bits = __float_as_int(r);
+    const float e = (float)((bits >> 23) - 127);
+    const float m = __int_as_float((bits & 0x007fffff) | 0x3f800000);
+    const float k = 3.010299956639812f;
+    return __fmaf_rn(e, k, __fmul_rn(k, __log2f(m)));
+}
+
 // Inclusive -> exclusive suffix sum over the lanes of a warp (sum of strictly
 // HIGHER lanes).  One fixed instruction sequence so that every caller gets
 // bit-identical partial sums for the same inputs (the EDC tile carries rely on it).

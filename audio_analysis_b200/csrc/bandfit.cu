@@ -21,6 +21,8 @@ using edc::EdcArgs;
 using edc::kMaxTargets;
 using edc::TileScan;
 using edc::tile_scan;
+using edc::ScanMasks;
+using edc::make_scan_masks;
 using edc::to_db;
 
 constexpr int kFitThreads = 256;
@@ -52,7 +54,7 @@ struct FitShared {
 // (later steps of the tile + later tiles).
 template <int NS, class F>
 __device__ __forceinline__ void visit_tile_reverse(const float* __restrict__ y, int k, int tile_len, int n, double carry_k,
-                                                   int lane, F&& f) {
+                                                   int lane, const ScanMasks& masks, F&& f) {
     float4 v[NS];
 #pragma unroll
     for (int j = 0; j < NS; ++j) {
@@ -71,7 +73,7 @@ __device__ __forceinline__ void visit_tile_reverse(const float* __restrict__ y, 
     double after = carry_k;
 #pragma unroll
     for (int j = NS - 1; j >= 0; --j) {
-        const TileScan sc = tile_scan(v[j]);
+        const TileScan sc = tile_scan(v[j], masks);
         f(j, sc, after);
         after += (double)__shfl_sync(kFullMask, __fadd_rn(sc.excl, sc.s[0]), 0);
     }
@@ -83,6 +85,7 @@ __global__ void __launch_bounds__(kFitThreads) band_fit_kernel(BandFitArgs a) {
     __shared__ FitShared sh;
     const int unit = blockIdx.x;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const ScanMasks masks = make_scan_masks();
     const int NT = a.n_tiles, TL = a.tile_len, n = a.n;
     double* carry = reinterpret_cast<double*>(dyn_smem);   // [NT] energy after tile k
     float* tsum = reinterpret_cast<float*>(carry + NT);    // [NT] tile energy
@@ -140,7 +143,7 @@ __global__ void __launch_bounds__(kFitThreads) band_fit_kernel(BandFitArgs a) {
     if (warp == 0) {
         const int pofs = start - ks * TL;
         const int pj = pofs / kSub, pl = (pofs % kSub) >> 2, pc = pofs & 3;
-        visit_tile_reverse<NS>(y, ks, TL, n, carry[ks], lane, [&](int j, const TileScan& sc, double after) {
+        visit_tile_reverse<NS>(y, ks, TL, n, carry[ks], lane, masks, [&](int j, const TileScan& sc, double after) {
             if (j == pj && lane == pl) {
                 const float sj = (pc == 0) ? sc.s[0] : (pc == 1) ? sc.s[1] : (pc == 2) ? sc.s[2] : sc.s[3];
                 const double e = after + (double)__fadd_rn(sc.excl, sj);
@@ -180,7 +183,7 @@ __global__ void __launch_bounds__(kFitThreads) band_fit_kernel(BandFitArgs a) {
                 const int k = hit;
                 // steps are visited last to first; the curve is monotone, so the last step that reports a
                 // sample <= target holds the first such sample
-                visit_tile_reverse<NS>(y, k, TL, n, carry[k], lane, [&](int j, const TileScan& sc, double after) {
+                visit_tile_reverse<NS>(y, k, TL, n, carry[k], lane, masks, [&](int j, const TileScan& sc, double after) {
                     int first_c = 4;
                     float dbv = 0.f;
                     double ev = 0.0;
@@ -265,7 +268,7 @@ __global__ void __launch_bounds__(kFitThreads) band_fit_kernel(BandFitArgs a) {
     if (hi >= lo) {
         const int k_lo = lo / TL, k_hi = min(hi / TL, NT - 1);
         for (int k = k_lo + warp; k <= k_hi; k += kFitWarps) {
-            visit_tile_reverse<NS>(y, k, TL, n, carry[k], lane, [&](int j, const TileScan& sc, double after) {
+            visit_tile_reverse<NS>(y, k, TL, n, carry[k], lane, masks, [&](int j, const TileScan& sc, double after) {
                 const int i0 = k * TL + j * kSub + 4 * lane;
                 const int s_lo = k * TL + j * kSub, s_hi = s_lo + kSub - 1;
                 bool any = false;

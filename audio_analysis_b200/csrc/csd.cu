@@ -380,7 +380,7 @@ __global__ void __launch_bounds__(kCsdThreads) csd_tma_kernel(CsdArgs a) {
             const float2 zm = pa[pad_index<kTmaPad>((M - k) == M ? 0 : (M - k))];
             const float2 X = untangle_half_spectrum(zk, zm, __ldg(a.twN + k));
             const float p = fmaxf(X.x * X.x + X.y * X.y, a.floor_lin_sq);
-            const float db = 10.0f * log10f(p);
+            const float db = 3.010299956639812f * log2f(p);  // 10 log10 |X|^2
             o[b] = db;
             smax = fmaxf(smax, db);
         }

@@ -96,14 +96,34 @@ __device__ __forceinline__ float4 load_tile(const float* __restrict__ x, int til
     return v;
 }
 
+// Per-lane 0/1 factors of the warp suffix scan: step d adds the value of lane + d when that lane exists.
+// inc = fma(o, 1, inc) rounds exactly like inc + o, and fma(o, 0, inc) leaves inc alone, so the scan costs one
+// shuffle and one FMA per step with no predicates.
+struct ScanMasks {
+    float m[5];   // d = 1, 2, 4, 8, 16
+    float last;   // 0 for lane 31 (nothing above it), 1 otherwise
+};
+
+__device__ __forceinline__ ScanMasks make_scan_masks() {
+    ScanMasks k;
+    const int lane = threadIdx.x & 31;
+#pragma unroll
+    for (int i = 0; i < 5; ++i) k.m[i] = (lane + (1 << i) < 32) ? 1.0f : 0.0f;
+    k.last = (lane == 31) ? 0.0f : 1.0f;
+    return k;
+}
+
 // The single scan routine shared by both phases (bit-identical partial sums).
-__device__ __forceinline__ TileScan tile_scan(float4 v) {
+__device__ __forceinline__ TileScan tile_scan(float4 v, const ScanMasks& k) {
     TileScan t;
     t.s[3] = __fmul_rn(v.w, v.w);
     t.s[2] = __fmaf_rn(v.z, v.z, t.s[3]);
     t.s[1] = __fmaf_rn(v.y, v.y, t.s[2]);
     t.s[0] = __fmaf_rn(v.x, v.x, t.s[1]);
-    t.excl = warp_suffix_exclusive(t.s[0]);
+    float inc = t.s[0];
+#pragma unroll
+    for (int i = 0; i < 5; ++i) inc = __fmaf_rn(__shfl_down_sync(kFullMask, inc, 1 << i), k.m[i], inc);
+    t.excl = __fmul_rn(__shfl_down_sync(kFullMask, inc, 1), k.last);
     return t;
 }
 
@@ -127,6 +147,7 @@ __device__ __forceinline__ void edc_row(const EdcArgs& a, int row, const float* 
     const int rank = (int)cluster.block_rank();
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
+    const ScanMasks masks = make_scan_masks();
 
     const int len = min(max(a.lengths ? a.lengths[row] : a.uniform_len, 0), a.max_len);
     const int nt = (len + kTile - 1) / kTile;
@@ -144,7 +165,8 @@ __device__ __forceinline__ void edc_row(const EdcArgs& a, int row, const float* 
     else if (!a.trim_to_peak) start_known = min(a.ignore, len);
 
     // ------------------------------------------------------------------ phase 1
-    float amax = -1.0f;
+    float amax = -1.0f;   // per lane: largest |x| seen and the first tile that holds it (index resolved below)
+    int atile = -1;
     int aidx = 0x7fffffff;
     {
         const int k_skip = (start_known >= 0) ? start_known / kTile : 0;
@@ -166,12 +188,8 @@ __device__ __forceinline__ void edc_row(const EdcArgs& a, int row, const float* 
                     ts[u] = 0.f;
                     if (k < my_tile1 && k >= k_skip) {
                         if (find_peak) {
-                            const int i0 = k * kTile + lane * 4;
-                            float m;
-                            m = fabsf(v[u].x); if (m > amax) { amax = m; aidx = i0; }
-                            m = fabsf(v[u].y); if (m > amax) { amax = m; aidx = i0 + 1; }
-                            m = fabsf(v[u].z); if (m > amax) { amax = m; aidx = i0 + 2; }
-                            m = fabsf(v[u].w); if (m > amax) { amax = m; aidx = i0 + 3; }
+                            const float m = fmaxf(fmaxf(fabsf(v[u].x), fabsf(v[u].y)), fmaxf(fabsf(v[u].z), fabsf(v[u].w)));
+                            if (m > amax) { amax = m; atile = k; }
                         }
                         ts[u] = fmaf(v[u].x, v[u].x, fmaf(v[u].y, v[u].y, fmaf(v[u].z, v[u].z, v[u].w * v[u].w)));
                     }
@@ -196,14 +214,10 @@ __device__ __forceinline__ void edc_row(const EdcArgs& a, int row, const float* 
                 float tsum = 0.f;
                 if (k < my_tile1 && k >= k_skip) {
                     if (find_peak) {
-                        const int i0 = k * kTile + lane * 4;
-                        float m;
-                        m = fabsf(v[u].x); if (m > amax) { amax = m; aidx = i0; }
-                        m = fabsf(v[u].y); if (m > amax) { amax = m; aidx = i0 + 1; }
-                        m = fabsf(v[u].z); if (m > amax) { amax = m; aidx = i0 + 2; }
-                        m = fabsf(v[u].w); if (m > amax) { amax = m; aidx = i0 + 3; }
+                        const float m = fmaxf(fmaxf(fabsf(v[u].x), fabsf(v[u].y)), fmaxf(fabsf(v[u].z), fabsf(v[u].w)));
+                        if (m > amax) { amax = m; atile = k; }
                     }
-                    TileScan t = tile_scan(v[u]);
+                    TileScan t = tile_scan(v[u], masks);
                     tsum = __fadd_rn(t.excl, t.s[0]);  // lane 0: whole-tile sum, same ops as phase 2
                 }
                 if (lane == 0) tile_sum[k - cta_tile0] = tsum;
@@ -212,6 +226,11 @@ __device__ __forceinline__ void edc_row(const EdcArgs& a, int row, const float* 
         }
     }
     if (find_peak) {
+        if (atile >= 0) {  // first sample of the lane's four that attains its maximum (first index wins ties, decay.py:136)
+            const float4 w = load_tile<kCg>(x, atile, lane, len);
+            const int i0 = atile * kTile + lane * 4;
+            aidx = (fabsf(w.x) == amax) ? i0 : (fabsf(w.y) == amax) ? i0 + 1 : (fabsf(w.z) == amax) ? i0 + 2 : i0 + 3;
+        }
 #pragma unroll
         for (int d = 16; d > 0; d >>= 1) {
             float om = __shfl_xor_sync(kFullMask, amax, d);
@@ -321,7 +340,7 @@ __device__ __forceinline__ void edc_row(const EdcArgs& a, int row, const float* 
     // ------------------------------------------------------------------ E0 = E[start]
     if (rank == owner && warp == 0) {
         float4 v = load_tile<kCg>(x, start_tile, lane, len);
-        TileScan t = tile_scan(v);
+        TileScan t = tile_scan(v, masks);
         const int p = start - start_tile * kTile;
         const int pl = p >> 2, pj = p & 3;
         float sj = (pj == 0) ? t.s[0] : (pj == 1) ? t.s[1] : (pj == 2) ? t.s[2] : t.s[3];
@@ -370,7 +389,7 @@ __device__ __forceinline__ void edc_row(const EdcArgs& a, int row, const float* 
                 const int k = hit;
                 const double base = carry[k - cta_tile0] + cta_carry;
                 float4 v = load_tile<kCg>(x, k, lane, len);
-                TileScan t = tile_scan(v);
+                TileScan t = tile_scan(v, masks);
                 float db[4];
                 int first_j = 4;
 #pragma unroll
@@ -433,19 +452,23 @@ __device__ __forceinline__ void edc_row(const EdcArgs& a, int row, const float* 
     __syncthreads();
 
     // ------------------------------------------------------------------ phase 2
+    // Per sample: ratio = (base + in-tile suffix) / E0 in float64 rounded once to float32, then 10 log10 through
+    // the exponent / mantissa split and one MUFU log2 (db10_from_ratio_fast), floor.  Per tile and fit: float sums of (y - ymid), j (y - ymid), (y - ymid)^2 over the lane's four
+    // samples, promoted to the float64 accumulators once per tile.
     double acc[AA_MAX_FITS * 3];
 #pragma unroll
     for (int q = 0; q < AA_MAX_FITS * 3; ++q) acc[q] = 0.0;
     int ffirst[AA_MAX_FITS], flast[AA_MAX_FITS];
-    double ymid[AA_MAX_FITS];
+    float ymid_f[AA_MAX_FITS];
 #pragma unroll
     for (int f = 0; f < AA_MAX_FITS; ++f) {
         const bool on = f < a.n_fits && sh.fit_valid[f];
         ffirst[f] = on ? sh.fit_first[f] : 0x7fffffff;
         flast[f] = on ? sh.fit_last[f] : -1;
-        ymid[f] = 0.5 * (a.fit_hi[f] + a.fit_lo[f]);
+        ymid_f[f] = (float)(0.5 * (a.fit_hi[f] + a.fit_lo[f]));
     }
     float* __restrict__ out = kWriteDb ? a.edc_out + (long long)row * a.edc_stride : nullptr;
+    const float floor_db = a.floor_db;
 
     for (int kb = max(my_tile0, start_tile); kb < my_tile1; kb += kUnroll) {
         float4 v[kUnroll];
@@ -465,12 +488,16 @@ __device__ __forceinline__ void edc_row(const EdcArgs& a, int row, const float* 
             if (!need[u]) continue;  // warp-uniform
             const int k = kb + u;
             const int t_lo = k * kTile, t_hi = t_lo + kTile - 1;
-            TileScan t = tile_scan(v[u]);
+            const TileScan t = tile_scan(v[u], masks);
             const double base = carry[k - cta_tile0] + cta_carry;
             float db[4];
 #pragma unroll
-            for (int j = 0; j < 4; ++j)
-                db[j] = to_db(base + (double)__fadd_rn(t.excl, t.s[j]), a.eps, inv_e0, a.floor_db);
+            for (int j = 0; j < 4; ++j) {
+                // the ratio is formed in float64 and rounded once, so the float32 curve inherits the exact
+                // monotonicity of the suffix sums (decay.py:151-157)
+                const float r = (float)(fmax(base + (double)__fadd_rn(t.excl, t.s[j]), a.eps) * inv_e0);
+                db[j] = fmaxf(db10_from_ratio_fast(r), floor_db);   // decay.py:158,167
+            }
             const int i0 = t_lo + lane * 4;
             if (kWriteDb) {
                 if (i0 >= start && i0 + 3 < len) {
@@ -483,18 +510,20 @@ __device__ __forceinline__ void edc_row(const EdcArgs& a, int row, const float* 
             }
 #pragma unroll
             for (int f = 0; f < AA_MAX_FITS; ++f) {
-                if (ffirst[f] <= t_hi && flast[f] >= t_lo) {
+                if (ffirst[f] <= t_hi && flast[f] >= t_lo) {  // warp-uniform
+                    float s0 = 0.f, s1 = 0.f, s2 = 0.f;
 #pragma unroll
                     for (int j = 0; j < 4; ++j) {
                         const int idx = i0 + j;
-                        if (idx >= ffirst[f] && idx <= flast[f]) {
-                            const double u2 = (double)(idx - ffirst[f]);
-                            const double yc = (double)db[j] - ymid[f];
-                            acc[f * 3 + 0] += yc;
-                            acc[f * 3 + 1] = fma(u2, yc, acc[f * 3 + 1]);
-                            acc[f * 3 + 2] = fma(yc, yc, acc[f * 3 + 2]);
-                        }
+                        const float yc = (idx >= ffirst[f] && idx <= flast[f]) ? db[j] - ymid_f[f] : 0.0f;
+                        s0 += yc;
+                        s1 = fmaf((float)j, yc, s1);
+                        s2 = fmaf(yc, yc, s2);
                     }
+                    const double ub = (double)(i0 - ffirst[f]);  // u of the lane's first sample (may be negative)
+                    acc[f * 3 + 0] += (double)s0;
+                    acc[f * 3 + 1] += fma(ub, (double)s0, (double)s1);
+                    acc[f * 3 + 2] += (double)s2;
                 }
             }
         }
@@ -535,7 +564,7 @@ __device__ __forceinline__ void edc_row(const EdcArgs& a, int row, const float* 
                     s1 += o->fit_sums[f][1];
                     s2 += o->fit_sums[f][2];
                 }
-                rt60 = fit_finalize(s0, s1, s2, sh.fit_first[f] - start, sh.fit_last[f] - start, ymid[f], a.sr,
+                rt60 = fit_finalize(s0, s1, s2, sh.fit_first[f] - start, sh.fit_last[f] - start, (double)ymid_f[f], a.sr,
                                     sh.fit_ts[f], sh.fit_te[f], res);
             }
             if (a.fits_out) {

@@ -187,18 +187,43 @@ def _normalise_slices(raw_db: np.ndarray, settings: WaterfallAnalysisSettings) -
 # --------------------------------------------------------------------------------------
 
 
-@dataclass
 class WaterfallPlan:
-    """Per-row selection for a batch: analysis start / length and the slice frames."""
+    """Per-row selection for a batch: analysis start / length and the slice frames.
 
-    start: np.ndarray        # [B] int32
-    length: np.ndarray       # [B] int64 analysed samples
-    frames: np.ndarray       # [B, S_max] int32
-    n_slices: np.ndarray     # [B] int32
-    bin_lo: int
-    freq: np.ndarray         # [F] float32
-    hop_length: int
-    sample_rate_hz: int
+    The selection is computed on the device; the host copies (`start`, `length`, `frames`, `n_slices`
+    as numpy arrays) are made on first access, so enqueueing a batch never waits for the GPU.
+    """
+
+    def __init__(self, start, length, frames, n_slices, bin_lo: int, freq: np.ndarray, hop_length: int,
+                 sample_rate_hz: int):
+        self._dev = {"start": start, "length": length, "frames": frames, "n_slices": n_slices}
+        self._host: Dict[str, np.ndarray] = {}
+        self.bin_lo = int(bin_lo)
+        self.freq = freq                      # [F] float32
+        self.hop_length = int(hop_length)
+        self.sample_rate_hz = int(sample_rate_hz)
+
+    def _get(self, name: str, dtype) -> np.ndarray:
+        if name not in self._host:
+            v = self._dev[name]
+            self._host[name] = (v.cpu().numpy() if hasattr(v, "cpu") else np.asarray(v)).astype(dtype)
+        return self._host[name]
+
+    @property
+    def start(self) -> np.ndarray:        # [B] int32
+        return self._get("start", np.int32)
+
+    @property
+    def length(self) -> np.ndarray:       # [B] int64 analysed samples
+        return self._get("length", np.int64)
+
+    @property
+    def frames(self) -> np.ndarray:       # [B, S_max] int32
+        return self._get("frames", np.int32)
+
+    @property
+    def n_slices(self) -> np.ndarray:     # [B] int32
+        return self._get("n_slices", np.int32)
 
     def slice_times(self, row: int) -> np.ndarray:
         """Window-start times of the row's slices, float32 like the reference (waterfall.py:229, :400)."""
@@ -237,6 +262,21 @@ def slice_table(settings: WaterfallAnalysisSettings, sample_rate_hz: int, max_fr
     return frames, counts
 
 
+_device_tables: Dict[tuple, tuple] = {}
+
+
+def _device_slice_table(table: np.ndarray, counts: np.ndarray, dev):
+    """Device copies of a slice table, cached per (table identity, device)."""
+    import torch
+
+    key = (id(table), str(dev))
+    have = _device_tables.get(key)
+    if have is None or have[0] is not table:
+        have = (table, torch.from_numpy(table).to(dev), torch.from_numpy(counts).to(dev))
+        _device_tables[key] = have
+    return have[1], have[2]
+
+
 def run_waterfall(rows: engine.Rows, sample_rate_hz: int, settings: WaterfallAnalysisSettings, peaks=None,
                   validate: bool = True):
     """Device-level call: returns (slices tensor [B, S_max, F], WaterfallPlan).
@@ -272,8 +312,7 @@ def run_waterfall(rows: engine.Rows, sample_rate_hz: int, settings: WaterfallAna
     table, counts = slice_table(settings, sample_rate_hz, max_frames)
     n_frames = torch.where(remaining >= n_fft, 1 + torch.div(remaining - n_fft, hop, rounding_mode="floor"),
                            torch.zeros_like(remaining)).to(torch.int64)
-    table_d = torch.from_numpy(table).to(dev)
-    counts_d = torch.from_numpy(counts).to(dev)
+    table_d, counts_d = _device_slice_table(table, counts, dev)
     frames_d = table_d[n_frames].contiguous()
     nslices_d = counts_d[n_frames].contiguous()
     smoothing = int(settings.smoothing_log_bins or 0) > 1
@@ -282,8 +321,7 @@ def run_waterfall(rows: engine.Rows, sample_rate_hz: int, settings: WaterfallAna
                                settings.dynamic_range_db)
     start = start.contiguous()
     slices = engine.csd(rows, start, frames_d, nslices_d, params)
-    plan = WaterfallPlan(start=start.cpu().numpy().astype(np.int32), length=remaining.cpu().numpy().astype(np.int64),
-                         frames=frames_d.cpu().numpy(), n_slices=nslices_d.cpu().numpy(), bin_lo=bin_lo, freq=freq,
+    plan = WaterfallPlan(start=start, length=remaining, frames=frames_d, n_slices=nslices_d, bin_lo=bin_lo, freq=freq,
                          hop_length=hop, sample_rate_hz=int(sample_rate_hz))
     if validate:
         if np.any(plan.length < n_fft):
