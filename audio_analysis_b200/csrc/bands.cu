@@ -289,6 +289,7 @@ int rt60bands_batch(const aa_bands_plan* plan, const float* d_x, long long row_s
         s.conj = 1;
         s.n_bands = nb;
         s.bands = d_bands;
+        s.bands_have_tables = 1;
         s.freq_scale = freq_scale;
         s.N = N;
         s.M = even ? M : 0;

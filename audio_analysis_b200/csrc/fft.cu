@@ -432,7 +432,7 @@ int exec_direct(const C2CPlan* p, const SrcDesc& src, const DstDesc& dst, long l
         AA_REQUIRE(grid < 2147483647LL, AA_ERR_INVALID_ARGUMENT, "fft grid too large");
         const unsigned g = (unsigned)grid;
         const bool use_spec = getenv("AA_FFT_GENERIC") == nullptr && units * (long long)p->M < 2147483647LL;
-        if (use_spec && fast_src && src.mode == SRC_BAND_PACKED && src.conj &&
+        if (use_spec && fast_src && src.mode == SRC_BAND_PACKED && src.conj && src.bands_have_tables &&
             launch_cols_reg<SRC_BAND_PACKED>(p, src, scratch, units, stream)) {
         } else if (use_spec && fast_src && src.mode == SRC_REAL_PACKED && !src.clip && src.n_valid == 2 * p->M &&
                    (src.unit_stride % 2) == 0 && launch_cols_reg<SRC_REAL_PACKED>(p, src, scratch, units, stream)) {

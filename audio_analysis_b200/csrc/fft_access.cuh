@@ -81,6 +81,7 @@ struct SrcDesc {
     // band modes: unit = row * n_bands + band
     int n_bands;
     const BandDev* bands;
+    int bands_have_tables;  // every bands[i].mask points at a table (required by the register-pass kernels)
     double freq_scale;      // rfftfreq: f_k = float(k * freq_scale)
     int N, M;               // real length and N/2
     TwoLevelTwiddle twN;    // exp(-2 pi i k / N)

@@ -65,8 +65,13 @@ struct RegSrcBand {
     int M;
     TwoLevelTwiddle twN;
     AA_HD float2 masked(int k) const {  // k inside [k_first, k_last]
-        const float m = b.mask ? load_r(b.mask + (k - b.k_first)) : band_mask_value(b, (float)((double)k * freq_scale));
-        if (m == 0.0f) return make_float2(0.f, 0.f);
+#ifdef __CUDA_ARCH__
+        // device: the per-call mask table is mandatory here (bands.cu builds it); evaluating the raised cosines
+        // inline would put 2 x RA copies of cosf into the kernel and overflow the instruction cache
+        const float m = load_r(b.mask + (k - b.k_first));
+#else
+        const float m = b.mask ? b.mask[k - b.k_first] : band_mask_value(b, (float)((double)k * freq_scale));
+#endif
         return cscale(load_c(X + k), m);
     }
     AA_HD bool get(int idx, float2* v) const {

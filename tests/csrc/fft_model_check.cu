@@ -163,7 +163,7 @@ static void emu_reg_unit(const HostC2C& p, const SrcDesc& src, const DstDesc& ds
 // mirrors the dispatch in exec_direct(): register passes for the listed splits and plain sources / sinks
 static bool emu_reg_direct(const HostC2C& p, const SrcDesc& src, const DstDesc& dst, long long units) {
     const bool src_ok = src.chirp == nullptr &&
-                        ((src.mode == SRC_BAND_PACKED && src.conj) ||
+                        ((src.mode == SRC_BAND_PACKED && src.conj && src.bands_have_tables) ||
                          (src.mode == SRC_REAL_PACKED && !src.clip && src.n_valid == 2 * p.M && src.unit_stride % 2 == 0) ||
                          (src.mode == SRC_COMPLEX && !src.conj && src.n_valid >= p.M));
     const bool dst_ok = dst.mode == DST_COMPLEX && dst.chirp == nullptr && dst.conj2 == 0 && dst.scale2 == 1.0f;
@@ -434,6 +434,7 @@ static void check_real_band(int N, double lo0 = 890.9, double hi0 = 1122.5) {
     s.conj = 1;
     s.n_bands = nb;
     s.bands = bands.data();
+    s.bands_have_tables = 1;  // the host accessor evaluates the mask when no table is attached
     s.freq_scale = freq_scale;
     s.N = N;
     s.M = even ? M : 0;
