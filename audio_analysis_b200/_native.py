@@ -32,6 +32,10 @@ EXPORTED_SYMBOLS = (
     "aa_last_error",
     "aa_device_count",
     "aa_kernel_launch_count",
+    "aa_profile_enable",
+    "aa_profile_collect",
+    "aa_profile_ms",
+    "aa_profile_scopes",
     "aa_peak_index_batch",
     "aa_decay_batch",
     "aa_curve_fits_batch",
@@ -107,6 +111,14 @@ def _declare(lib: C.CDLL) -> None:
     lib.aa_device_count.argtypes = []
     lib.aa_kernel_launch_count.restype = C.c_longlong
     lib.aa_kernel_launch_count.argtypes = []
+    lib.aa_profile_enable.restype = None
+    lib.aa_profile_enable.argtypes = [C.c_int]
+    lib.aa_profile_collect.restype = C.c_int
+    lib.aa_profile_collect.argtypes = []
+    lib.aa_profile_ms.restype = C.c_double
+    lib.aa_profile_ms.argtypes = [C.c_char_p]
+    lib.aa_profile_scopes.restype = C.c_longlong
+    lib.aa_profile_scopes.argtypes = [C.c_char_p]
     lib.aa_peak_index_batch.restype = C.c_int
     lib.aa_peak_index_batch.argtypes = [vp, i64, vp, i32, vp, vp]
     lib.aa_decay_batch.restype = C.c_int

@@ -12,6 +12,22 @@ namespace aa {
 void set_error(const char* fmt, ...);
 void count_launch();  // every kernel launch of this library is counted (aa_kernel_launch_count)
 
+// Optional per-stage device timing for bench.py (aa_profile_* in the C ABI): when enabled, launch sites wrap a
+// kernel (or a short group of kernels) in a ProfScope, which records CUDA events on the launching stream.
+bool prof_enabled();
+void prof_begin(const char* name, cudaStream_t stream);
+void prof_end(cudaStream_t stream);
+struct ProfScope {
+    cudaStream_t s;
+    bool on;
+    ProfScope(const char* name, cudaStream_t stream) : s(stream), on(prof_enabled()) {
+        if (on) prof_begin(name, s);
+    }
+    ~ProfScope() {
+        if (on) prof_end(s);
+    }
+};
+
 #define AA_CUDA_TRY(expr)                                                                        \
     do {                                                                                         \
         cudaError_t _e = (expr);                                                                 \

@@ -2,7 +2,11 @@
 #include <stdarg.h>
 
 #include <atomic>
+#include <map>
+#include <mutex>
 #include <stdio.h>
+#include <string>
+#include <vector>
 
 #include "fft.cuh"
 #include "kernels.cuh"
@@ -16,6 +20,36 @@ static thread_local char g_err[512] = "";
 static std::atomic<long long> g_launches{0};
 
 void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
+
+// ---- per-stage timing (off by default) ----------------------------------------------------------
+struct ProfRec {
+    std::string name;
+    cudaEvent_t e0, e1;
+};
+static std::atomic<bool> g_prof_on{false};
+static std::mutex g_prof_mu;
+static std::vector<ProfRec> g_prof_open, g_prof_done;
+static std::map<std::string, std::pair<double, long long>> g_prof_sum;  // name -> (ms, scopes)
+
+bool prof_enabled() { return g_prof_on.load(std::memory_order_relaxed); }
+
+void prof_begin(const char* name, cudaStream_t stream) {
+    ProfRec r;
+    r.name = name;
+    if (cudaEventCreate(&r.e0) != cudaSuccess || cudaEventCreate(&r.e1) != cudaSuccess) return;
+    cudaEventRecord(r.e0, stream);
+    std::lock_guard<std::mutex> lock(g_prof_mu);
+    g_prof_open.push_back(r);
+}
+
+void prof_end(cudaStream_t stream) {
+    std::lock_guard<std::mutex> lock(g_prof_mu);
+    if (g_prof_open.empty()) return;
+    ProfRec r = g_prof_open.back();
+    g_prof_open.pop_back();
+    cudaEventRecord(r.e1, stream);
+    g_prof_done.push_back(r);
+}
 
 void set_error(const char* fmt, ...) {
     va_list ap;
@@ -49,6 +83,45 @@ const char* aa_last_error(void) { return aa::g_err; }
 
 long long aa_kernel_launch_count(void) { return aa::g_launches.load(std::memory_order_relaxed); }
 
+void aa_profile_enable(int on) {
+    std::lock_guard<std::mutex> lock(aa::g_prof_mu);
+    aa::g_prof_on.store(on != 0);
+    for (auto& r : aa::g_prof_done) {
+        cudaEventDestroy(r.e0);
+        cudaEventDestroy(r.e1);
+    }
+    aa::g_prof_done.clear();
+    aa::g_prof_sum.clear();
+}
+
+int aa_profile_collect(void) {
+    std::lock_guard<std::mutex> lock(aa::g_prof_mu);
+    for (auto& r : aa::g_prof_done) {
+        float ms = 0.f;
+        if (cudaEventSynchronize(r.e1) == cudaSuccess && cudaEventElapsedTime(&ms, r.e0, r.e1) == cudaSuccess) {
+            auto& acc = aa::g_prof_sum[r.name];
+            acc.first += (double)ms;
+            acc.second += 1;
+        }
+        cudaEventDestroy(r.e0);
+        cudaEventDestroy(r.e1);
+    }
+    aa::g_prof_done.clear();
+    return (int)aa::g_prof_sum.size();
+}
+
+double aa_profile_ms(const char* name) {
+    std::lock_guard<std::mutex> lock(aa::g_prof_mu);
+    auto it = aa::g_prof_sum.find(name ? name : "");
+    return it == aa::g_prof_sum.end() ? 0.0 : it->second.first;
+}
+
+long long aa_profile_scopes(const char* name) {
+    std::lock_guard<std::mutex> lock(aa::g_prof_mu);
+    auto it = aa::g_prof_sum.find(name ? name : "");
+    return it == aa::g_prof_sum.end() ? 0 : it->second.second;
+}
+
 int aa_device_count(void) {
     int n = 0;
     cudaError_t e = cudaGetDeviceCount(&n);
@@ -72,6 +145,7 @@ int aa_decay_batch(const float* d_x, int64_t row_stride, const int32_t* d_length
                    int32_t* d_status_out, void* stream) {
     AA_REQUIRE(uniform_length >= 0 && uniform_length <= row_stride, AA_ERR_INVALID_ARGUMENT,
                "uniform_length (the maximum row length) must be in [0, row_stride]");
+    aa::ProfScope prof(d_edc_db_out ? "edc" : "edc_metrics", static_cast<cudaStream_t>(stream));
     return aa::launch_edc(d_x, row_stride, d_lengths, uniform_length, uniform_length, n_rows, p, d_start_in, 1, 4,
                           d_edc_db_out, edc_stride, d_start_out, d_fits_out, nullptr, d_early10_out, d_status_out,
                           static_cast<cudaStream_t>(stream));
@@ -110,6 +184,7 @@ int aa_rt60bands_batch(const aa_bands_plan* plan, const float* d_x, int64_t row_
 int aa_csd_batch(const float* d_x, int64_t row_stride, const int32_t* d_lengths, int32_t uniform_length,
                  int32_t n_rows, const int32_t* d_start_idx, const int32_t* d_frame_idx, const int32_t* d_n_slices,
                  int32_t max_slices, const aa_csd_params* p, float* d_out, void* stream) {
+    aa::ProfScope prof("csd", static_cast<cudaStream_t>(stream));
     return aa::launch_csd(d_x, row_stride, d_lengths, uniform_length, n_rows, d_start_idx, d_frame_idx, d_n_slices,
                           max_slices, p, d_out, static_cast<cudaStream_t>(stream));
 }

@@ -252,14 +252,14 @@ __global__ void __launch_bounds__(kFitThreads) band_fit_kernel(BandFitArgs a) {
 #pragma unroll
     for (int q = 0; q < AA_MAX_FITS * 3; ++q) acc[q] = 0.0;
     int ffirst[AA_MAX_FITS], flast[AA_MAX_FITS];
-    double ymid[AA_MAX_FITS];
+    float ymid_f[AA_MAX_FITS];
     int lo = 0x7fffffff, hi = -1;
 #pragma unroll
     for (int f = 0; f < AA_MAX_FITS; ++f) {
         const bool on = f < p.n_fits && sh.fit_valid[f];
         ffirst[f] = on ? sh.fit_first[f] : 0x7fffffff;
         flast[f] = on ? sh.fit_last[f] : -1;
-        ymid[f] = 0.5 * (p.fit_hi[f] + p.fit_lo[f]);
+        ymid_f[f] = (float)(0.5 * (p.fit_hi[f] + p.fit_lo[f]));
         if (on) {
             lo = min(lo, ffirst[f]);
             hi = max(hi, flast[f]);
@@ -267,6 +267,8 @@ __global__ void __launch_bounds__(kFitThreads) band_fit_kernel(BandFitArgs a) {
     }
     if (hi >= lo) {
         const int k_lo = lo / TL, k_hi = min(hi / TL, NT - 1);
+        const double eps = p.eps;
+        const float floor_db = p.floor_db;
         for (int k = k_lo + warp; k <= k_hi; k += kFitWarps) {
             visit_tile_reverse<NS>(y, k, TL, n, carry[k], lane, masks, [&](int j, const TileScan& sc, double after) {
                 const int i0 = k * TL + j * kSub + 4 * lane;
@@ -275,24 +277,31 @@ __global__ void __launch_bounds__(kFitThreads) band_fit_kernel(BandFitArgs a) {
 #pragma unroll
                 for (int f = 0; f < AA_MAX_FITS; ++f) any |= (ffirst[f] <= s_hi && flast[f] >= s_lo);
                 if (!any) return;  // warp-uniform
+                // same arithmetic as phase 2 of edc_body.cuh: float64 ratio rounded once, MUFU log2 on the mantissa,
+                // float sums per step promoted to the float64 accumulators
                 float db[4];
 #pragma unroll
-                for (int c = 0; c < 4; ++c)
-                    db[c] = to_db(after + (double)__fadd_rn(sc.excl, sc.s[c]), p.eps, inv_e0, p.floor_db);
+                for (int c = 0; c < 4; ++c) {
+                    const float r = (float)(fmax(after + (double)__fadd_rn(sc.excl, sc.s[c]), eps) * inv_e0);
+                    db[c] = fmaxf(db10_from_ratio_fast(r), floor_db);
+                }
+                const int in_tile = TL - (j * kSub + 4 * lane);  // samples of this lane that belong to the tile
 #pragma unroll
                 for (int f = 0; f < AA_MAX_FITS; ++f) {
                     if (ffirst[f] <= s_hi && flast[f] >= s_lo) {
+                        float s0 = 0.f, s1 = 0.f, s2 = 0.f;
 #pragma unroll
                         for (int c = 0; c < 4; ++c) {
                             const int i = i0 + c;
-                            if (j * kSub + 4 * lane + c < TL && i >= ffirst[f] && i <= flast[f]) {
-                                const double u2 = (double)(i - ffirst[f]);
-                                const double yc = (double)db[c] - ymid[f];
-                                acc[f * 3 + 0] += yc;
-                                acc[f * 3 + 1] = fma(u2, yc, acc[f * 3 + 1]);
-                                acc[f * 3 + 2] = fma(yc, yc, acc[f * 3 + 2]);
-                            }
+                            const float yc = (c < in_tile && i >= ffirst[f] && i <= flast[f]) ? db[c] - ymid_f[f] : 0.0f;
+                            s0 += yc;
+                            s1 = fmaf((float)c, yc, s1);
+                            s2 = fmaf(yc, yc, s2);
                         }
+                        const double ub = (double)(i0 - ffirst[f]);
+                        acc[f * 3 + 0] += (double)s0;
+                        acc[f * 3 + 1] += fma(ub, (double)s0, (double)s1);
+                        acc[f * 3 + 2] += (double)s2;
                     }
                 }
             });
@@ -315,7 +324,7 @@ __global__ void __launch_bounds__(kFitThreads) band_fit_kernel(BandFitArgs a) {
                 s2 += sh.warp_acc[w][f * 3 + 2];
             }
             double res[AA_FIT_COLS];
-            rt60 = fit_finalize(s0, s1, s2, sh.fit_first[f] - start, sh.fit_last[f] - start, ymid[f], p.sr, sh.fit_ts[f],
+            rt60 = fit_finalize(s0, s1, s2, sh.fit_first[f] - start, sh.fit_last[f] - start, (double)ymid_f[f], p.sr, sh.fit_ts[f],
                                 sh.fit_te[f], res);
         }
         p.rt60_out[(long long)unit * AA_MAX_FITS + f] = rt60;

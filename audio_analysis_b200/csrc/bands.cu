@@ -268,6 +268,7 @@ int rt60bands_batch(const aa_bands_plan* plan, const float* d_x, long long row_s
             rc = c2c_exec(plan->c2c, s, make_dst_complex(d_Z, M, M, 0, 1.0f), rows, d_scr, stream);
             if (rc != AA_OK) return rc;
             dim3 grid((unsigned)((M + 1 + 255) / 256 > 1024 ? 1024 : (M + 1 + 255) / 256), (unsigned)rows);
+            ProfScope prof("untangle", stream);
             untangle_kernel<<<grid, 256, 0, stream>>>(d_Z, d_X, M, plan->x_stride, plan->twN.dev);
             rc = launch_check("untangle_kernel");
             if (rc != AA_OK) return rc;
@@ -324,11 +325,13 @@ int rt60bands_batch(const aa_bands_plan* plan, const float* d_x, long long row_s
         if (tiled) {
             // the rows pass left the energy of every tile of 2 M1 samples next to the signal: suffix-scan those and
             // revisit only the tiles with the start sample, a crossing or fit points
+            ProfScope prof("band_fit", stream);
             rc = launch_band_fit(d_y, plan->y_stride, d_part, (long long)n_tiles * n_groups, n_groups, n_tiles,
                                  2 * tile_c, N, units, &pk, d_start_idx + r0, nb, 8,
                                  d_metrics_out + r0 * nb * AA_MAX_FITS, stream);
             if (rc != AA_OK) return rc;
         } else if (!smoothing) {
+            ProfScope prof("band_edc", stream);
             rc = launch_edc(d_y, plan->y_stride, nullptr, N, N, (int)units, &pk, d_start_idx + r0, nb, 8, nullptr, 0,
                             nullptr, nullptr, d_metrics_out + r0 * nb * AA_MAX_FITS, nullptr, nullptr, stream);
             if (rc != AA_OK) return rc;

@@ -432,6 +432,7 @@ int exec_direct(const C2CPlan* p, const SrcDesc& src, const DstDesc& dst, long l
         AA_REQUIRE(grid < 2147483647LL, AA_ERR_INVALID_ARGUMENT, "fft grid too large");
         const unsigned g = (unsigned)grid;
         const bool use_spec = getenv("AA_FFT_GENERIC") == nullptr && units * (long long)p->M < 2147483647LL;
+        ProfScope prof(src.mode == SRC_BAND_PACKED || src.mode == SRC_BAND_FULL ? "fft_cols_band" : "fft_cols", stream);
         if (use_spec && fast_src && src.mode == SRC_BAND_PACKED && src.conj && src.bands_have_tables &&
             launch_cols_reg<SRC_BAND_PACKED>(p, src, scratch, units, stream)) {
         } else if (use_spec && fast_src && src.mode == SRC_REAL_PACKED && !src.clip && src.n_valid == 2 * p->M &&
@@ -460,6 +461,7 @@ int exec_direct(const C2CPlan* p, const SrcDesc& src, const DstDesc& dst, long l
     const unsigned g = (unsigned)grid;
     const bool src_plain = (src2.mode == SRC_COMPLEX && src2.chirp == nullptr);
     const bool dst_plain = plain_complex_dst(dst);
+    ProfScope prof(dst.energy ? "fft_rows_band" : "fft_rows", stream);
     const bool spec2 = getenv("AA_FFT_GENERIC") == nullptr && p->M1 > 1 && src_plain && dst_plain &&
                        units * (long long)p->M < 2147483647LL &&
                        launch_rows_reg(p, scratch, dst, units, stream);

@@ -123,14 +123,14 @@ def fit_from_row(name: str, range_db: Tuple[float, float], row: np.ndarray) -> O
 
 
 def run_decay(rows: engine.Rows, sample_rate_hz: int, settings: DecayAnalysisSettings, want_edc: bool = True,
-              fit_ranges: Optional[Sequence[Tuple[float, float]]] = None) -> engine.DecayOut:
+              fit_ranges: Optional[Sequence[Tuple[float, float]]] = None, edc_out=None) -> engine.DecayOut:
     """Launch the decay kernels for a device batch (fused path, or the smoothing path of decay.py:161-164)."""
     ranges = [r for _, r in fit_plan(settings)] if fit_ranges is None else list(fit_ranges)
     params = native_params(settings, sample_rate_hz, ranges)
     window = int(settings.edc_smoothing_window_samples or 0)
     if window > 1:
         return engine.decay_smoothed(rows, params, window)
-    return engine.decay(rows, params, want_edc=want_edc)
+    return engine.decay(rows, params, want_edc=want_edc, edc_out=edc_out)
 
 
 def analyse_decay_batch(

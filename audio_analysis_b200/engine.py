@@ -184,7 +184,8 @@ def decay_params(sample_rate_hz: int, trim_to_peak: bool, ignore_leading_seconds
 
 
 def decay(rows: Rows, params: nat.DecayParams, want_edc: bool = True,
-          start_in: Optional[torch.Tensor] = None) -> DecayOut:
+          start_in: Optional[torch.Tensor] = None, edc_out: Optional[torch.Tensor] = None) -> DecayOut:
+    """`edc_out`: optional [B, stride] float32 device buffer (same pitch as the rows) to receive the curves."""
     lib = nat.load()
     dev = rows.x.device
     b = rows.n_rows
@@ -192,7 +193,15 @@ def decay(rows: Rows, params: nat.DecayParams, want_edc: bool = True,
     fits = torch.empty((b, nat.AA_MAX_FITS, nat.AA_FIT_COLS), dtype=torch.float64, device=dev)
     early = torch.empty(b, dtype=torch.float64, device=dev)
     status = torch.empty(b, dtype=torch.int32, device=dev)
-    edc = torch.empty((b, rows.stride), dtype=torch.float32, device=dev) if want_edc else None
+    edc = None
+    if want_edc:
+        if edc_out is not None:
+            if (edc_out.dtype != torch.float32 or not edc_out.is_cuda or tuple(edc_out.shape) != (b, rows.stride)
+                    or edc_out.stride(1) != 1 or (b > 1 and edc_out.stride(0) != rows.stride)):
+                raise ValueError("edc_out must be a float32 device tensor [rows, stride] with the rows' pitch")
+            edc = edc_out
+        else:
+            edc = torch.empty((b, rows.stride), dtype=torch.float32, device=dev)
     with torch.cuda.device(dev):
         nat.check(lib.aa_decay_batch(
             _ptr(rows.x), rows.stride, _ptr(rows.lengths), rows.n, b, C.byref(params), _ptr(start_in), _ptr(edc),

@@ -200,6 +200,7 @@ def run_ours(args):
     launches0 = lib.aa_kernel_launch_count()
     sampler = ClockSampler(local)
     sampler.start()
+    lib.aa_profile_enable(1)   # CUDA events around every library kernel, on the launching stream
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     e0.record()
@@ -209,6 +210,11 @@ def run_ours(args):
     barrier()
     clocks = sampler.stop()
     ms_total = e0.elapsed_time(e1)
+    lib.aa_profile_collect()
+    stage_names = ["edc", "fft_cols", "fft_rows", "untangle", "fft_cols_band", "fft_rows_band", "band_fit", "band_edc", "csd"]
+    stage_ms = {k: lib.aa_profile_ms(k.encode()) / args.steps for k in stage_names}
+    stage_scopes = {k: int(lib.aa_profile_scopes(k.encode())) // args.steps for k in stage_names}
+    lib.aa_profile_enable(0)
     launches = (lib.aa_kernel_launch_count() - launches0) // max(1, args.steps)
     t = torch.tensor([ms_total], dtype=torch.float64, device=dev)
     if world > 1:
@@ -218,69 +224,78 @@ def run_ours(args):
     ir_seconds_per_step = world * rows_n * (n / SR)
     value = ir_seconds_per_step / (ms_step / 1e3)
 
-    # ---- per-kernel timings for the roofline objects (CUDA events on the launching stream)
-    def time_call(fn, reps=5):
-        fn()
-        torch.cuda.synchronize()
-        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        a.record()
-        for _ in range(reps):
-            fn()
-        b.record()
-        torch.cuda.synchronize()
-        return a.elapsed_time(b) / reps
-
+    # ---- roofline objects: per-kernel device time (summed over the launches of one step, measured above inside the
+    # timed region) against each kernel's ALGORITHMIC bytes
     peak, peak_src = measured_peak_gbs()
-    ms_decay = time_call(lambda: decay.run_decay(rows, SR, ds, want_edc=True))
-    start_idx = out.decay.start
-    ms_bands = time_call(lambda: rt60bands.run_rt60_bands(rows, SR, bs, start_idx=start_idx), reps=2)
-    ms_csd = time_call(lambda: waterfall.run_waterfall(rows, SR, ws, peaks=start_idx, validate=False))
     n_bins = int(out.csd.shape[2])
-    bytes_decay = 8.0 * rows_n * n                                   # read x + write edc_db
-    bytes_bands = 4.0 * rows_n * n                                   # read x once; outputs negligible
-    bytes_csd = rows_n * (18 * 4096 * 4.0 + 18 * n_bins * 4.0)       # selected frames in, slices out
-    def roof(nbytes, ms):
-        gbs = nbytes / (ms / 1e3) / 1e9
-        return {"achieved": round(gbs, 1), "frac": round(gbs / peak, 4), "ms": round(ms, 4)}
-    roofline = {"bound": "hbm", "kernel": "edc_kernel<true> (aa_decay_batch: fused EDC + crossings + fits)",
-                **roof(bytes_decay, ms_decay), "peak": peak, "peak_source": peak_src, "unit": "GB/s",
-                "algorithmic_bytes_per_launch": bytes_decay, "traffic": None,
-                "share_of_step": round(ms_decay / ms_step, 4)}
-    by_kernel = {
-        "decay_edc_fits": {**roof(bytes_decay, ms_decay), "bound": "hbm", "share_of_step": round(ms_decay / ms_step, 4)},
-        "rt60bands_third_octave": {**roof(bytes_bands, ms_bands), "bound": "fp32 ALU / L2 (SURVEY D7), not HBM",
-                                   "share_of_step": round(ms_bands / ms_step, 4)},
-        "csd_waterfall": {**roof(bytes_csd, ms_csd), "bound": "hbm", "share_of_step": round(ms_csd / ms_step, 4)},
+    n_bands = int(out.band_metrics.shape[1])
+    units = rows_n * n_bands
+    stage_bytes = {
+        # read x + write edc_db (8 B/sample)
+        "edc": (8.0 * rows_n * n, "hbm", "edc_kernel<true>: fused EDC + crossings + fits (aa_decay_batch)"),
+        # forward transform of every row: each pass reads and writes the row once
+        "fft_cols": (8.0 * rows_n * n, "hbm", "fft_cols_reg: first pass of the forward real FFT"),
+        "fft_rows": (8.0 * rows_n * n, "hbm", "fft_rows_reg: second pass of the forward real FFT"),
+        "untangle": (8.0 * rows_n * n, "hbm", "untangle_kernel: packed spectrum -> half spectrum"),
+        # per (row, band) unit: the masked spectrum is generated on the fly, the pass writes N/2 complex values
+        "fft_cols_band": (4.0 * units * n, "fp32 issue (band source + butterflies); writes 4 B/sample/band",
+                          "fft_cols_reg<band>: first pass of the masked inverse FFT"),
+        # per unit: reads N/2 complex, writes N real samples + the energy partials
+        "fft_rows_band": (8.0 * units * n + 4.0 * units * (n // 16), "hbm",
+                          "fft_rows_reg<energy>: second pass of the masked inverse FFT + tile energies"),
+        "band_fit": (4.0 * units * (n // 16), "latency (reads the partials and ~10% of the band signal)",
+                     "band_fit_kernel: band EDC suffix scan + crossings + fits"),
+        "band_edc": (4.0 * units * n, "hbm", "edc_kernel<false> on band signals (generic lengths)"),
+        "csd": (rows_n * (18 * 4096 * 4.0 + 18 * n_bins * 4.0), "hbm",
+                "csd_tma_kernel: TMA-staged frames, FFT, dB, on-chip normalisation"),
     }
+    def roof(nbytes, ms):
+        gbs = nbytes / (ms / 1e3) / 1e9 if ms > 0 else 0.0
+        return {"achieved": round(gbs, 1), "frac": round(gbs / peak, 4), "ms": round(ms, 4)}
+    by_kernel = {}
+    for k in stage_names:
+        if stage_ms[k] <= 0:
+            continue
+        nbytes, bound, what = stage_bytes[k]
+        by_kernel[k] = {**roof(nbytes, stage_ms[k]), "bound": bound, "kernel": what, "launches_per_step": stage_scopes[k],
+                        "algorithmic_bytes_per_step": nbytes, "share_of_step": round(stage_ms[k] / ms_step, 4)}
+    dominant = max(by_kernel, key=lambda k: by_kernel[k]["ms"])
+    dk = by_kernel[dominant]
+    roofline = {"bound": "hbm", "kernel": dk["kernel"], "stage": dominant, "achieved": dk["achieved"], "frac": dk["frac"],
+                "ms": dk["ms"], "launches_per_step": dk["launches_per_step"],
+                "ms_per_launch": round(dk["ms"] / max(1, dk["launches_per_step"]), 4),
+                "peak": peak, "peak_source": peak_src, "unit": "GB/s",
+                "algorithmic_bytes_per_launch": dk["algorithmic_bytes_per_step"] / max(1, dk["launches_per_step"]),
+                "traffic": None, "share_of_step": dk["share_of_step"],
+                "note": "dominant kernel by device time inside the timed region; the band stage as a whole has 4 B/sample "
+                        "of algorithmic traffic (SURVEY 8d) and is bound by fp32 issue, not HBM (SURVEY D7): see "
+                        "roofline_by_kernel"}
+    ms_bands = sum(stage_ms[k] for k in ("fft_cols", "fft_rows", "untangle", "fft_cols_band", "fft_rows_band", "band_fit",
+                                          "band_edc"))
+    by_kernel["rt60bands_stage"] = {**roof(4.0 * rows_n * n, ms_bands), "bound": "fp32 issue / intermediate traffic",
+                                    "kernel": "whole band stage against SURVEY 8d's 4 B/sample (read x once)",
+                                    "share_of_step": round(ms_bands / ms_step, 4)}
 
-    # ---- end to end through the public batch API: pinned host input -> H2D -> kernels -> tables D2H
+    # ---- end to end through the public batch API: pinned host input -> chunked H2D overlapped with the kernels ->
+    # tables and CSD slices D2H (run_hot_path_host)
+    from audio_analysis_b200.pipeline import run_hot_path_host
     e2e = None
     try:
         x_host = torch.empty((rows_n, n), dtype=torch.float32, pin_memory=True)
         x_host.copy_(x_dev)
         torch.cuda.synchronize()
-        keep = {}
+        chunk = int(os.environ.get("AA_BENCH_E2E_CHUNK", "512"))
 
         def step_e2e():
-            r = engine.make_rows(x_host, device=dev)             # H2D from pinned memory
-            o = run_hot_path(r, SR, ds, bs, ws, want_edc=True)
-            res = {"start": o.decay.start, "fits": o.decay.fits, "early10": o.decay.early10,
-                   "status": o.decay.status, "band_rt60": o.band_metrics, "csd": o.csd}
-            nbytes = 0
-            for k, v in res.items():
-                if k not in keep:
-                    keep[k] = torch.empty(v.shape, dtype=v.dtype, pin_memory=True)
-                keep[k].copy_(v, non_blocking=True)               # D2H of the result tables + CSD slices
-                nbytes += v.numel() * v.element_size()
-            return nbytes
+            return run_hot_path_host(x_host, SR, ds, bs, ws, chunk_rows=chunk, want_edc=True)
 
-        d2h = step_e2e()
+        res = step_e2e()
         barrier()
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         steps_e2e = max(1, min(args.steps, 3))
         a.record()
         for _ in range(steps_e2e):
-            d2h = step_e2e()
+            res = step_e2e()
         b.record()
         barrier()
         t2 = torch.tensor([a.elapsed_time(b)], dtype=torch.float64, device=dev)
@@ -288,9 +303,11 @@ def run_ours(args):
             dist.all_reduce(t2, op=dist.ReduceOp.MAX)
         ms_e2e = float(t2.item()) / steps_e2e
         e2e = {"value": round(ir_seconds_per_step / (ms_e2e / 1e3), 1), "unit": UNIT, "ms_per_step": round(ms_e2e, 3),
-               "h2d_bytes_per_step": int(rows_n * n * 4), "d2h_bytes_per_step": int(d2h),
-               "note": "EDC curves stay in HBM (plot data on demand); metric tables and CSD slices are copied back"}
-        del x_host
+               "h2d_bytes_per_step": int(res.h2d_bytes), "d2h_bytes_per_step": int(res.d2h_bytes),
+               "chunk_rows": chunk,
+               "note": "pipeline.run_hot_path_host: chunked H2D / kernels / D2H on three streams; EDC curves stay in "
+                       "HBM (plot data on demand); metric tables and CSD slices are copied back"}
+        del x_host, res
     except Exception as exc:  # pinned allocation can fail on small hosts
         e2e = {"value": None, "unit": UNIT, "error": str(exc)[:200]}
 

@@ -106,6 +106,19 @@ int aa_device_count(void);
 long long aa_kernel_launch_count(void);
 
 /*
+ * Optional per-stage device timing (used by bench.py for the roofline objects).  While enabled, the library
+ * brackets its kernels with CUDA events on the caller's stream under these names:
+ *   "edc" (fused EDC + fits kernel), "fft_cols_band" / "fft_cols" (first FFT pass, band-masked source / other),
+ *   "fft_rows" (second FFT pass), "untangle", "band_fit", "band_edc", "csd".
+ * aa_profile_enable(1) starts a fresh measurement, aa_profile_collect() waits for the recorded events and sums
+ * them per name, aa_profile_ms / aa_profile_scopes read the sums.  Not for concurrent use from several threads.
+ */
+void aa_profile_enable(int on);
+int aa_profile_collect(void);
+double aa_profile_ms(const char* name);
+long long aa_profile_scopes(const char* name);
+
+/*
  * aa_peak_index_batch - first index of max|x| per row.
  * Replaces np.argmax(np.abs(x)) at analyse/decay.py:136, rt60bands.py:335,
  * waterfall.py:359.  d_peak_out[b] = index (0 for an empty row).
