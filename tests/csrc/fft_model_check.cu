@@ -153,9 +153,16 @@ static void emu_reg_unit(const HostC2C& p, const SrcDesc& src, const DstDesc& ds
     for (int cta = 0; cta < M1 / G2; ++cta) {
         const int row0 = cta * G2;
         for (int t = 0; t < P2::kThreads; ++t) reg_rows_stage_a<P2>(t, scratch.data(), row0, buf.data());
-        for (int t = 0; t < P2::kThreads; ++t)
+        for (int t = 0; t < P2::kThreads; ++t) {
+            float e[P2::RB];
             reg_rows_stage_b<P2>(t, buf.data(), tws.data(), (float2*)dst.base + u * dst.unit_stride, M1, row0, dst.n_valid,
-                                 dst.conj1, dst.scale1);
+                                 dst.conj1, dst.scale1, dst.energy ? e : nullptr);
+            if (dst.energy && t < P2::kThreadsB) {  // the kernel reduces over the 8 rows of the group with shuffles
+                const int jb = t / P2::G;
+                for (int q = 0; q < P2::RB; ++q)
+                    dst.energy[u * dst.energy_stride + (long long)cta * P2::L + jb + q * P2::RA] += e[q];
+            }
+        }
     }
     *used = 1;
 }
@@ -451,7 +458,28 @@ static void check_real_band(int N, double lo0 = 890.9, double hi0 = 1122.5) {
         d.scale1 = 1.0f / (float)N;
         d.scale2 = 1.0f;
     }
+    std::vector<float> energy;
+    int e_m1 = 0, e_m2 = 0;
+    if (even && !ep.top.bluestein && reg_split_for(M, &e_m1, &e_m2)) {  // tile energies next to the band signal
+        energy.assign((size_t)nb * (size_t)(e_m1 / 8) * (size_t)e_m2, 0.f);
+        d.energy = energy.data();
+        d.energy_stride = (long long)(e_m1 / 8) * e_m2;
+    }
     emu_exec(ep, s, d, nb);
+    if (!energy.empty()) {
+        double worst_e = 0;
+        for (int bi = 0; bi < nb; ++bi)
+            for (int k2 = 0; k2 < e_m2; k2 += 7) {
+                double got = 0, want = 0;
+                for (int g = 0; g < e_m1 / 8; ++g) got += energy[(size_t)bi * d.energy_stride + (size_t)g * e_m2 + k2];
+                for (int i = 0; i < 2 * e_m1; ++i) {
+                    const double v = y[(size_t)bi * N + (size_t)k2 * 2 * e_m1 + i];
+                    want += v * v;
+                }
+                if (want > 0) worst_e = fmax(worst_e, fabs(got - want) / want);
+            }
+        report("  tile energy partials", N, worst_e, 2e-5);
+    }
     // direct evaluation of irfft(X * mask) at a few samples, from the double-precision spectrum of x
     for (int bi = 0; bi < nb; ++bi) {
         BandDev open = bands[(size_t)bi];

@@ -364,6 +364,64 @@ def test_full_size_properties_config5_rows():
     assert torch.equal(torch.nan_to_num(sub[0]), torch.nan_to_num(metrics[1]))
 
 
+def test_host_streaming_pipeline_equals_resident_batch():
+    """run_hot_path_host (chunked H2D / kernels / D2H on three streams) returns exactly what the resident batch
+    returns, for a chunk size that does not divide the batch."""
+    import torch
+    from audio_analysis_b200 import decay, engine, rt60bands as rb, waterfall as wf
+    from audio_analysis_b200.pipeline import run_hot_path, run_hot_path_host
+    from audio_analysis_b200.synth import synth_batch_torch
+    n = 96000
+    x = synth_batch_torch(11, n, SR, device="cuda")
+    ds = decay.DecayAnalysisSettings(compute_edt=True)
+    bs = rb.Rt60BandsAnalysisSettings(band_mode="third", decay_settings=ds)
+    ws = wf.WaterfallAnalysisSettings()
+    ref = run_hot_path(engine.make_rows(x), SR, ds, bs, ws, want_edc=True)
+    xh = torch.empty((11, n), dtype=torch.float32, pin_memory=True)
+    xh.copy_(x)
+    torch.cuda.synchronize()
+    got = run_hot_path_host(xh, SR, ds, bs, ws, chunk_rows=4, want_edc=True)
+    got.wait()
+    torch.cuda.synchronize()
+    assert got.h2d_bytes == 11 * n * 4 and got.d2h_bytes > 0
+    assert torch.equal(got.start, ref.decay.start.cpu())
+    assert torch.equal(torch.nan_to_num(got.fits), torch.nan_to_num(ref.decay.fits.cpu()))
+    assert torch.equal(torch.nan_to_num(got.early10), torch.nan_to_num(ref.decay.early10.cpu()))
+    assert torch.equal(torch.nan_to_num(got.band_rt60), torch.nan_to_num(ref.band_metrics.cpu()))
+    assert torch.equal(got.csd, ref.csd.cpu())
+    st = ref.decay.start.cpu().numpy()
+    for b in range(11):
+        assert torch.equal(got.edc_db[b, st[b]:n], ref.decay.edc_db[b, st[b]:n])
+    # numpy input (pageable) goes through the same path
+    got2 = run_hot_path_host(xh.numpy().copy(), SR, ds, bs, ws, chunk_rows=16, want_edc=False, do_csd=False)
+    got2.wait()
+    torch.cuda.synchronize()
+    assert got2.edc_db is None and got2.csd is None
+    assert torch.equal(torch.nan_to_num(got2.band_rt60), torch.nan_to_num(ref.band_metrics.cpu()))
+
+
+def test_stage_profiler_reports_kernel_times():
+    """aa_profile_*: CUDA-event time per library stage (what bench.py's roofline objects are built from)."""
+    import torch
+    from audio_analysis_b200 import _native as nat, decay, engine, rt60bands as rb
+    from audio_analysis_b200.synth import synth_batch_torch
+    lib = nat.load()
+    x = synth_batch_torch(8, 288000, SR, device="cuda")
+    rows = engine.make_rows(x)
+    lib.aa_profile_enable(1)
+    out = decay.run_decay(rows, SR, decay.DecayAnalysisSettings())
+    rb.run_rt60_bands(rows, SR, rb.Rt60BandsAnalysisSettings(band_mode="third"), start_idx=out.start)
+    torch.cuda.synchronize()
+    assert lib.aa_profile_collect() >= 4
+    for name in (b"edc", b"fft_cols_band", b"fft_rows_band", b"band_fit"):
+        assert lib.aa_profile_ms(name) > 0.0 and lib.aa_profile_scopes(name) >= 1, name
+    assert lib.aa_profile_ms(b"no_such_stage") == 0.0
+    lib.aa_profile_enable(0)
+    decay.run_decay(rows, SR, decay.DecayAnalysisSettings())
+    torch.cuda.synchronize()
+    assert lib.aa_profile_collect() == 0
+
+
 # ------------------------------------------------------------------------------------ PCM16, deconvolution, CLI
 
 
