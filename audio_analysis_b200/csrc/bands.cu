@@ -56,6 +56,17 @@ __global__ void band_mask_kernel(const BandDev* __restrict__ bands, double freq_
         out[k - b.k_first] = band_mask_value(b, (float)((double)k * freq_scale));
 }
 
+// The band table travels to the device as a kernel ARGUMENT, not through the copy engine: a host-to-device copy
+// on the compute stream would queue behind the bulk input transfer of the next chunk (pipeline.run_hot_path_host)
+// and stall the kernels that follow it.
+constexpr int kBandsPerStore = 32;
+struct BandTableArg {
+    BandDev b[kBandsPerStore];
+};
+__global__ void band_table_kernel(BandTableArg tab, BandDev* __restrict__ out, int n) {
+    if ((int)threadIdx.x < n) out[threadIdx.x] = tab.b[threadIdx.x];
+}
+
 // Host mirror of _make_lowpass_mask / _make_highpass_mask / _make_bandpass_mask edge handling
 // (analyse/rt60bands.py:127-167); python floats are doubles, numpy rounds them to float32 when they
 // meet the float32 frequency array.
@@ -117,8 +128,15 @@ int upload_bands(const aa_band* bands, int nb, double tw_oct, double nyq, double
         if (support > 0) mask_off += (size_t)support;
         if (support > widest) widest = support;
     }
-    // pageable-memory async copies are staged before returning, so the host vector may go out of scope
-    AA_CUDA_TRY(cudaMemcpyAsync(d_bands, hb.data(), sizeof(BandDev) * (size_t)nb, cudaMemcpyHostToDevice, stream));
+    for (int i0 = 0; i0 < nb; i0 += kBandsPerStore) {
+        BandTableArg arg;
+        const int cnt = (nb - i0 < kBandsPerStore) ? (nb - i0) : kBandsPerStore;
+        memset(&arg, 0, sizeof(arg));
+        for (int i = 0; i < cnt; ++i) arg.b[i] = hb[(size_t)(i0 + i)];
+        band_table_kernel<<<1, kBandsPerStore, 0, stream>>>(arg, d_bands + i0, cnt);
+        int rc = launch_check("band_table_kernel");
+        if (rc != AA_OK) return rc;
+    }
     if (widest > 0) {
         int bx = (widest + 255) / 256;
         if (bx > 64) bx = 64;

@@ -78,37 +78,54 @@ def run_hot_path_host(x_host, sample_rate_hz: int,
                       bands_settings: Optional[Rt60BandsAnalysisSettings] = None,
                       waterfall_settings: Optional[WaterfallAnalysisSettings] = None,
                       chunk_rows: int = 256, want_edc: bool = True, do_bands: bool = True, do_csd: bool = True,
-                      device=None) -> HostPathOut:
-    """The hot path for a HOST batch [B, N] float32 (numpy array or torch CPU tensor, ideally pinned).
+                      device=None, reuse: Optional[HostPathOut] = None) -> HostPathOut:
+    """The hot path for a HOST batch [B, N] (numpy array or torch CPU tensor, ideally pinned): float32 samples, or
+    int16 mono PCM as it sits in the reference's WAV inputs (decoded on the device with io.py:46-64's rule,
+    sample / 32768; half the bytes over PCIe).
 
     The batch is streamed through the device in chunks of `chunk_rows` rows on three streams: the
     host-to-device copy of chunk i + 1 and the device-to-host copy of chunk i - 1's tables and CSD slices
     overlap the kernels of chunk i, so for large batches the transfer cost disappears behind the compute.
     Nothing blocks the host: call `.wait()` (or synchronise the device) before reading the host tensors.
+    `reuse`: a previous result whose pinned host tensors (and device EDC buffer) are overwritten instead of
+    allocating new ones - pinning a gigabyte of host memory costs more than analysing it.
     """
     import numpy as np
 
     dev = engine._device(device)
     xh = torch.from_numpy(x_host) if isinstance(x_host, np.ndarray) else x_host
-    if xh.dim() != 2 or xh.dtype != torch.float32 or xh.is_cuda:
-        raise ValueError("expected a [rows, samples] float32 host array")
+    if xh.dim() != 2 or xh.dtype not in (torch.float32, torch.int16) or xh.is_cuda:
+        raise ValueError("expected a [rows, samples] float32 or int16 host array")
+    pcm = xh.dtype == torch.int16
     b, n = int(xh.shape[0]), int(xh.shape[1])
     pitch = max(4, engine.round_up4(n))
     chunk = max(1, min(int(chunk_rows), b))
     ds = decay_settings or DecayAnalysisSettings()
     main = torch.cuda.current_stream(dev)
     s_in, s_out = torch.cuda.Stream(dev), torch.cuda.Stream(dev)
-    bufs = [torch.zeros((chunk, pitch), dtype=torch.float32, device=dev) for _ in range(2)]
+    bufs = [torch.zeros((chunk, pitch), dtype=torch.int16 if pcm else torch.float32, device=dev) for _ in range(2)]
     free_ev = [None, None]          # kernels that read buffer k have finished
-    edc_all = torch.empty((b, pitch), dtype=torch.float32, device=dev) if want_edc else None
+    edc_all = None
+    if want_edc:
+        if reuse is not None and reuse.edc_db is not None and tuple(reuse.edc_db.shape) == (b, pitch):
+            edc_all = reuse.edc_db
+        else:
+            edc_all = torch.empty((b, pitch), dtype=torch.float32, device=dev)
     host = {}
+    if reuse is not None:
+        reuse.wait()
+        for name in ("start", "fits", "early10", "status", "band_rt60", "csd"):
+            t = getattr(reuse, name)
+            if t is not None and int(t.shape[0]) == b:
+                host[name] = t
     bands = None
     d2h = 0
     hl = np.full(chunk, n, dtype=np.int64)
 
     def pinned_like(name, t, rows_total):
-        if name not in host:
-            host[name] = torch.empty((rows_total,) + tuple(t.shape[1:]), dtype=t.dtype, pin_memory=True)
+        want = (rows_total,) + tuple(t.shape[1:])
+        if name not in host or tuple(host[name].shape) != want or host[name].dtype != t.dtype:
+            host[name] = torch.empty(want, dtype=t.dtype, pin_memory=True)
         return host[name]
 
     n_chunks = (b + chunk - 1) // chunk
@@ -132,7 +149,10 @@ def run_hot_path_host(x_host, sample_rate_hz: int,
         k = i & 1
         r0, r1 = i * chunk, min(b, (i + 1) * chunk)
         main.wait_event(in_ready[i])
-        rows = engine.Rows(x=bufs[k][: r1 - r0], lengths=None, n=n, host_lengths=hl[: r1 - r0])
+        if pcm:
+            rows = engine.pcm16_to_rows(bufs[k][: r1 - r0], n, 1, False)
+        else:
+            rows = engine.Rows(x=bufs[k][: r1 - r0], lengths=None, n=n, host_lengths=hl[: r1 - r0])
         smoothing = int(ds.edc_smoothing_window_samples or 0) > 1
         out = run_hot_path(rows, sample_rate_hz, ds, bands_settings, waterfall_settings, want_edc=want_edc,
                            do_bands=do_bands, do_csd=do_csd, validate=False,
@@ -159,5 +179,6 @@ def run_hot_path_host(x_host, sample_rate_hz: int,
     done.record(s_out)
     main.wait_stream(s_out)
     return HostPathOut(start=host["start"], fits=host["fits"], early10=host["early10"], status=host["status"],
-                       band_rt60=host.get("band_rt60"), csd=host.get("csd"), edc_db=edc_all, bands=bands,
-                       h2d_bytes=b * n * 4, d2h_bytes=d2h, done=done)
+                       band_rt60=host.get("band_rt60") if do_bands else None, csd=host.get("csd") if do_csd else None,
+                       edc_db=edc_all, bands=bands,
+                       h2d_bytes=b * n * (2 if pcm else 4), d2h_bytes=d2h, done=done)

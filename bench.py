@@ -286,16 +286,17 @@ def run_ours(args):
         torch.cuda.synchronize()
         chunk = int(os.environ.get("AA_BENCH_E2E_CHUNK", "512"))
 
-        def step_e2e():
-            return run_hot_path_host(x_host, SR, ds, bs, ws, chunk_rows=chunk, want_edc=True)
+        def step_e2e(prev=None):
+            return run_hot_path_host(x_host, SR, ds, bs, ws, chunk_rows=chunk, want_edc=True, reuse=prev)
 
         res = step_e2e()
+        res = step_e2e(res)     # warm: pinned result buffers exist and are reused from here on
         barrier()
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         steps_e2e = max(1, min(args.steps, 3))
         a.record()
         for _ in range(steps_e2e):
-            res = step_e2e()
+            res = step_e2e(res)
         b.record()
         barrier()
         t2 = torch.tensor([a.elapsed_time(b)], dtype=torch.float64, device=dev)
@@ -307,6 +308,28 @@ def run_ours(args):
                "chunk_rows": chunk,
                "note": "pipeline.run_hot_path_host: chunked H2D / kernels / D2H on three streams; EDC curves stay in "
                        "HBM (plot data on demand); metric tables and CSD slices are copied back"}
+        # the same batch as 16-bit PCM (the reference's WAV sample format, decoded on the device): half the PCIe bytes
+        try:
+            x_pcm = torch.empty((rows_n, n), dtype=torch.int16, pin_memory=True)
+            x_pcm.copy_((x_dev * 32767.0).round().clamp_(-32768, 32767).to(torch.int16))
+            torch.cuda.synchronize()
+            res = run_hot_path_host(x_pcm, SR, ds, bs, ws, chunk_rows=chunk, want_edc=True, reuse=res)
+            barrier()
+            a.record()
+            for _ in range(steps_e2e):
+                res = run_hot_path_host(x_pcm, SR, ds, bs, ws, chunk_rows=chunk, want_edc=True, reuse=res)
+            b.record()
+            barrier()
+            t3 = torch.tensor([a.elapsed_time(b)], dtype=torch.float64, device=dev)
+            if world > 1:
+                dist.all_reduce(t3, op=dist.ReduceOp.MAX)
+            ms_pcm = float(t3.item()) / steps_e2e
+            e2e["pcm16_input"] = {"value": round(ir_seconds_per_step / (ms_pcm / 1e3), 1), "unit": UNIT,
+                                  "ms_per_step": round(ms_pcm, 3), "h2d_bytes_per_step": int(res.h2d_bytes),
+                                  "d2h_bytes_per_step": int(res.d2h_bytes)}
+            del x_pcm
+        except Exception as exc:
+            e2e["pcm16_input"] = {"value": None, "error": str(exc)[:200]}
         del x_host, res
     except Exception as exc:  # pinned allocation can fail on small hosts
         e2e = {"value": None, "unit": UNIT, "error": str(exc)[:200]}

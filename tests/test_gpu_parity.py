@@ -398,6 +398,16 @@ def test_host_streaming_pipeline_equals_resident_batch():
     torch.cuda.synchronize()
     assert got2.edc_db is None and got2.csd is None
     assert torch.equal(torch.nan_to_num(got2.band_rt60), torch.nan_to_num(ref.band_metrics.cpu()))
+    # 16-bit PCM host input: decoded on the device exactly like io.py:46-64 (sample / 32768)
+    pcm = (x * 32767.0).round().clamp(-32768, 32767).to(torch.int16).cpu()
+    want = run_hot_path(engine.make_rows(pcm.to(torch.float32).cuda() / 32768.0), SR, ds, bs, ws, want_edc=False)
+    got3 = run_hot_path_host(pcm, SR, ds, bs, ws, chunk_rows=5, want_edc=False)
+    got3.wait()
+    torch.cuda.synchronize()
+    assert got3.h2d_bytes == 11 * n * 2
+    assert torch.equal(got3.start, want.decay.start.cpu())
+    assert torch.equal(torch.nan_to_num(got3.band_rt60), torch.nan_to_num(want.band_metrics.cpu()))
+    assert torch.equal(got3.csd, want.csd.cpu())
 
 
 def test_stage_profiler_reports_kernel_times():
