@@ -306,7 +306,8 @@ __global__ void __launch_bounds__(P::kThreads) fft_rows_reg(const float2* __rest
                                                             const float2* __restrict__ tw_full, float* __restrict__ energy,
                                                             long long energy_stride) {
     static_assert(M1 % P::G == 0, "rows must split evenly over CTAs");
-    static_assert(!kEnergy || (P::G == 8 && P::kThreadsB % 32 == 0), "energy partials reduce over 8-lane groups");
+    static_assert(!kEnergy || ((P::G == 8 || P::G == 16) && P::kThreadsB % 32 == 0),
+                  "energy partials reduce over aligned groups of 8 or 16 lanes");
     constexpr int groups = M1 / P::G;
     extern __shared__ float2 smem[];
     float2* buf = smem;
@@ -320,7 +321,7 @@ __global__ void __launch_bounds__(P::kThreads) fft_rows_reg(const float2* __rest
     if (kEnergy) {
         float e[P::RB];
         reg_rows_stage_b<P>((int)threadIdx.x, buf, tws, out + (size_t)unit * out_stride, M1, row0, n_valid, conj, scale, e);
-        // sum over the 8 rows of the group: g is the low 3 bits of the lane index
+        // sum over the G rows of the group: g is the low 3 (4) bits of the lane index
         float* __restrict__ dst = energy + (size_t)unit * energy_stride + (size_t)rg * P::L;
         const int jb = (int)threadIdx.x / P::G, g = (int)threadIdx.x - jb * P::G;
 #pragma unroll
@@ -329,6 +330,7 @@ __global__ void __launch_bounds__(P::kThreads) fft_rows_reg(const float2* __rest
             v += __shfl_xor_sync(0xffffffffu, v, 1);
             v += __shfl_xor_sync(0xffffffffu, v, 2);
             v += __shfl_xor_sync(0xffffffffu, v, 4);
+            if (P::G == 16) v += __shfl_xor_sync(0xffffffffu, v, 8);
             if (g == 0 && threadIdx.x < P::kThreadsB) dst[jb + q * P::RA] = v;
         }
     } else {
@@ -507,11 +509,11 @@ int build_direct(int M, C2CPlan* p) {
 bool is_smooth(long long n) { return is_smooth_host(n); }
 
 // Tiles of the energy partials a DstDesc may request from c2c_exec: rows are transformed in groups of 8, so a
-// transform's outputs fall into M2 tiles of M1 consecutive complex values and M1 / 8 partial sums per tile.
+// transform's outputs fall into M2 tiles of M1 consecutive complex values and M1 / G2 partial sums per tile.
 bool c2c_energy_layout(const C2CPlan* p, int* tile_complex, int* n_tiles, int* n_groups) {
     if (p->bluestein || p->M1 <= 1 || getenv("AA_FFT_GENERIC") != nullptr) return false;
 #define X(ra1, rb1, g1, ra2, rb2, g2)                                              \
-    if (p->M1 == (ra1) * (rb1) && p->M2 == (ra2) * (rb2) && (g2) == 8) {           \
+    if (p->M1 == (ra1) * (rb1) && p->M2 == (ra2) * (rb2) && ((g2) == 8 || (g2) == 16)) { \
         *tile_complex = p->M1;                                                     \
         *n_tiles = p->M2;                                                          \
         *n_groups = p->M1 / (g2);                                                  \

@@ -459,11 +459,15 @@ static void check_real_band(int N, double lo0 = 890.9, double hi0 = 1122.5) {
         d.scale2 = 1.0f;
     }
     std::vector<float> energy;
-    int e_m1 = 0, e_m2 = 0;
+    int e_m1 = 0, e_m2 = 0, e_g = 0;
     if (even && !ep.top.bluestein && reg_split_for(M, &e_m1, &e_m2)) {  // tile energies next to the band signal
-        energy.assign((size_t)nb * (size_t)(e_m1 / 8) * (size_t)e_m2, 0.f);
+#define X(ra1, rb1, g1, ra2, rb2, g2) \
+    if (e_m1 == (ra1) * (rb1) && e_m2 == (ra2) * (rb2)) e_g = (g2);
+        AA_REG_LIST(X)
+#undef X
+        energy.assign((size_t)nb * (size_t)(e_m1 / e_g) * (size_t)e_m2, 0.f);
         d.energy = energy.data();
-        d.energy_stride = (long long)(e_m1 / 8) * e_m2;
+        d.energy_stride = (long long)(e_m1 / e_g) * e_m2;
     }
     emu_exec(ep, s, d, nb);
     if (!energy.empty()) {
@@ -471,7 +475,7 @@ static void check_real_band(int N, double lo0 = 890.9, double hi0 = 1122.5) {
         for (int bi = 0; bi < nb; ++bi)
             for (int k2 = 0; k2 < e_m2; k2 += 7) {
                 double got = 0, want = 0;
-                for (int g = 0; g < e_m1 / 8; ++g) got += energy[(size_t)bi * d.energy_stride + (size_t)g * e_m2 + k2];
+                for (int g = 0; g < e_m1 / e_g; ++g) got += energy[(size_t)bi * d.energy_stride + (size_t)g * e_m2 + k2];
                 for (int i = 0; i < 2 * e_m1; ++i) {
                     const double v = y[(size_t)bi * N + (size_t)k2 * 2 * e_m1 + i];
                     want += v * v;
