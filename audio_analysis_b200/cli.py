@@ -1,15 +1,16 @@
-"""Command line for the accelerated path: `decay`, `rt60bands`, `waterfall`, `bundle`.
+"""Command line for the accelerated path: `decay`, `rt60bands`, `waterfall`, `bundle`, `spectrogram`.
 
     python -m analyse.cli decay --input ir.wav --no_show
     python -m analyse.cli rt60bands --input ir.wav --mono --band_mode third --no_show
     python -m analyse.cli waterfall --input ir.wav --no_show
     python -m analyse.cli bundle --input analysis_runs/20250101_120000
+    python -m analyse.cli spectrogram --input ir.wav --no_show
 
 Argument names, defaults and quirks follow the reference's `analyse/cli.py`
-(decay :461-531, rt60bands :536-636, waterfall :1010-1100, bundle :377-388), including
+(decay :461-531, rt60bands :536-636, waterfall :1010-1100, bundle :377-388, spectrogram :842-917), including
 `decay --compute_edt` defaulting to true, `rt60bands --trim_to_peak` being impossible to
 switch off, and the tri-state `rt60bands --legend_values`.  Each command prints the same
-summary text as the reference.  The reference's other ten subcommands are outside this
+summary text as the reference.  The reference's other nine subcommands are outside this
 build and are rejected by argparse.
 """
 
@@ -23,6 +24,8 @@ from .bundle import BundleRunSettings, run_bundle_report
 from .decay import DecayAnalysisSettings, DecayPlotSettings, plot_decay_from_wav_file, summarise_decay_results_text
 from .rt60bands import (Rt60BandsAnalysisSettings, Rt60BandsPlotSettings, plot_rt60_bands_from_wav_file,
                         summarise_rt60_bands_results_text)
+from .spectrogram import (SpectrogramAnalysisSettings, SpectrogramPlotSettings, plot_spectrogram_from_wav_file,
+                          summarise_spectrogram_results_text)
 from .waterfall import (WaterfallAnalysisSettings, WaterfallPlotSettings, plot_waterfall_from_wav_file,
                         summarise_waterfall_results_text)
 
@@ -115,6 +118,25 @@ def build_parser() -> argparse.ArgumentParser:
     wf.add_argument("--elev_deg", type=float, default=30.0)
     wf.add_argument("--azim_deg", type=float, default=-60.0)
     wf.add_argument("--ridge_offset_db", type=float, default=6.0)
+
+    sp = sub.add_parser("spectrogram", help="Plot time–frequency magnitude spectrogram (log-frequency).")
+    _io_arguments(sp, "PNG(s): <basename>_spectrogram_<CH>.png")
+    sp.add_argument("--mono", dest="use_mono_downmix", action="store_true",
+                    help="If set, downmix stereo to mono before analysis.")
+    sp.add_argument("--trim_to_peak", action=BoolOpt, default=True,
+                    help="If true, start analysis at the absolute peak sample (default: true).")
+    sp.add_argument("--ignore-leading", dest="ignore_leading_seconds", type=float, default=0.0,
+                    help="Ignore this many seconds after trim point (default: 0.0).")
+    sp.add_argument("--duration", dest="analysis_duration_seconds", type=float, default=None,
+                    help="If set, analyse only this many seconds from the analysed segment.")
+    sp.add_argument("--n_fft", type=int, default=4096, help="STFT FFT size (default: 4096).")
+    sp.add_argument("--hop_length", type=int, default=512, help="STFT hop length (default: 512).")
+    sp.add_argument("--no_hann_window", action="store_true", help="If set, do not apply a Hann window to each frame.")
+    sp.add_argument("--floor_db", type=float, default=-120.0, help="Magnitude floor in dB (default: -120).")
+    sp.add_argument("--f_min_hz", type=float, default=20.0, help="Min frequency to display (default: 20).")
+    sp.add_argument("--f_max_hz", type=float, default=20000.0, help="Max frequency to display (default: 20000).")
+    sp.add_argument("--dynamic_range_db", type=float, default=90.0,
+                    help="Color scale range below max (default: 90). Use 0 to disable and use percentiles.")
     return top
 
 
@@ -208,6 +230,31 @@ def run_waterfall_command(a: argparse.Namespace) -> str:
     return summarise_waterfall_results_text(results)
 
 
+def run_spectrogram_command(a: argparse.Namespace) -> str:
+    dyn = float(a.dynamic_range_db)
+    analysis = SpectrogramAnalysisSettings(
+        use_mono_downmix_for_stereo=bool(a.use_mono_downmix),
+        trim_to_peak=bool(a.trim_to_peak),
+        ignore_leading_seconds=float(a.ignore_leading_seconds),
+        analysis_duration_seconds=a.analysis_duration_seconds,
+        n_fft=int(a.n_fft),
+        hop_length=int(a.hop_length),
+        use_hann_window=not bool(a.no_hann_window),
+        floor_db=float(a.floor_db),
+        f_min_hz=float(a.f_min_hz),
+        f_max_hz=float(a.f_max_hz),
+        dynamic_range_db=None if dyn <= 0.0 else dyn,   # reference cli.py:1402-1406
+    )
+    results = plot_spectrogram_from_wav_file(
+        input_wav_file_path=str(a.input_wav_file_path),
+        analysis_settings=analysis,
+        plot_settings=SpectrogramPlotSettings(),
+        output_basename=_basename(a),
+        show_interactive=not bool(a.no_show),
+    )
+    return summarise_spectrogram_results_text(results)
+
+
 def run_bundle_command(a: argparse.Namespace) -> str:
     index = run_bundle_report(str(a.bundle_root), settings=BundleRunSettings(reports_subdir=str(a.reports_subdir)))
     return f"Wrote bundle report index: {index}"
@@ -218,6 +265,7 @@ COMMANDS = {
     "rt60bands": run_rt60bands_command,
     "waterfall": run_waterfall_command,
     "bundle": run_bundle_command,
+    "spectrogram": run_spectrogram_command,
 }
 
 

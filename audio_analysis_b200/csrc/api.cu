@@ -181,6 +181,14 @@ int aa_rt60bands_batch(const aa_bands_plan* plan, const float* d_x, int64_t row_
                                static_cast<cudaStream_t>(stream));
 }
 
+int aa_stft_db_batch(const float* d_x, int64_t row_stride, const int32_t* d_lengths, int32_t uniform_length,
+                     int32_t n_rows, const int32_t* d_start_idx, const int32_t* d_span, int32_t n_fft, int32_t hop_length,
+                     int32_t use_hann_window, double floor_db, int32_t frames_max, float* d_out, void* stream) {
+    aa::ProfScope prof("stft", static_cast<cudaStream_t>(stream));
+    return aa::launch_stft_db(d_x, row_stride, d_lengths, uniform_length, n_rows, d_start_idx, d_span, n_fft, hop_length,
+                              use_hann_window, floor_db, frames_max, d_out, static_cast<cudaStream_t>(stream));
+}
+
 int aa_csd_batch(const float* d_x, int64_t row_stride, const int32_t* d_lengths, int32_t uniform_length,
                  int32_t n_rows, const int32_t* d_start_idx, const int32_t* d_frame_idx, const int32_t* d_n_slices,
                  int32_t max_slices, const aa_csd_params* p, float* d_out, void* stream) {

@@ -451,6 +451,110 @@ int csd_tma_dispatch(const CsdArgs& a, int n_rows, cudaStream_t stream) {
     }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Dense STFT magnitude in dB (analyse/spectrogram.py:107-160, the same loop as waterfall.py:188-230 but every
+// frame is kept).  A CTA takes a run of consecutive frames of one row: the frames overlap (hop < n_fft), so the
+// whole run is staged by ONE bulk copy and each sample is read from HBM once; every frame is windowed,
+// transformed with the compile-time radix chain and written as n_fft/2 + 1 float32 dB values, frame-major.
+// ---------------------------------------------------------------------------------------------
+struct StftArgs {
+    const float* x;
+    long long row_stride;
+    const int* lengths;
+    int uniform_len;
+    const int* start_idx;
+    const int* span;        // analysed samples per row (after trim / ignore / duration)
+    int n_fft, hop, use_hann;
+    int frames_per_cta, frames_max;
+    float floor_lin_sq;
+    float* out;             // [row][frames_max][n_fft/2 + 1]
+    SubPlanDev sp;
+    const float2* twN;
+    const float* hann;
+    const float2* twc;
+};
+
+template <int M, int... Rs>
+__global__ void __launch_bounds__(kCsdThreads) stft_db_kernel(StftArgs a) {
+    using Cfg = TmaCfg<M>;
+    extern __shared__ __align__(16) unsigned char dyn_smem[];
+    float2* fa = reinterpret_cast<float2*>(dyn_smem);
+    float2* fb = fa + Cfg::kFftElems;
+    float* raw = reinterpret_cast<float*>(dyn_smem + Cfg::kFftBytes);   // (frames_per_cta - 1) * hop + n_fft + 8
+    __shared__ unsigned long long bar;
+
+    const int row = blockIdx.y;
+    const int len = a.lengths ? a.lengths[row] : a.uniform_len;
+    const int start = a.start_idx[row];
+    const int span = min(a.span[row], len - start);
+    const int n_frames = (span >= a.n_fft) ? min(1 + (span - a.n_fft) / a.hop, a.frames_max) : 0;
+    const int j0 = blockIdx.x * a.frames_per_cta;
+    if (j0 >= n_frames) return;
+    const int nf = min(a.frames_per_cta, n_frames - j0);
+    const float* __restrict__ x = a.x + (long long)row * a.row_stride;
+    const int len4 = (len + 3) & ~3;
+    const int f0 = start + j0 * a.hop;
+    const int a0 = f0 & ~3;
+    const int shift = f0 - a0;
+    const int nvec = ((nf - 1) * a.hop + a.n_fft + shift + 3) >> 2;
+    const bool bulk = f0 >= 0 && a0 + 4 * nvec <= len4;
+    if (bulk) {
+        if (threadIdx.x == 0) {
+            mbar_init(&bar, 1);
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            mbar_expect_tx(&bar, 16u * (unsigned)nvec);
+            bulk_g2s(raw, x + a0, 16u * (unsigned)nvec, &bar);
+        }
+        __syncthreads();
+        mbar_wait(&bar, 0);
+    } else {
+        for (int q = threadIdx.x; q < nvec; q += kCsdThreads) {
+            const int g = a0 + 4 * q;
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (g >= 0 && g + 4 <= len4) v = ldg_f4(x + g);
+            reinterpret_cast<float4*>(raw)[q] = v;
+        }
+        __syncthreads();
+    }
+    float* __restrict__ out_row = a.out + ((long long)row * a.frames_max + j0) * (M + 1);
+    for (int r = 0; r < nf; ++r) {
+        const float* rb = raw + shift + r * a.hop;
+        for (int m = threadIdx.x; m < M; m += kCsdThreads) {
+            float x0 = rb[2 * m], x1 = rb[2 * m + 1];
+            if (a.use_hann) {
+                const float2 w = __ldg(reinterpret_cast<const float2*>(a.hann) + m);
+                x0 *= w.x;
+                x1 *= w.y;
+            }
+            fa[pad_index<kTmaPad>(m)] = make_float2(x0, x1);
+        }
+        __syncthreads();
+        float2* pa = fa;
+        float2* pb = fb;
+        spec_stages<kCsdThreads, kTmaPad, M, 1, Cfg::kFftElems, 1, Rs...>(pa, pb, a.twc, a.sp.tw);
+        float* __restrict__ o = out_row + (long long)r * (M + 1);
+        for (int k = threadIdx.x; k <= M; k += kCsdThreads) {
+            const float2 zk = pa[pad_index<kTmaPad>(k == M ? 0 : k)];
+            const float2 zm = pa[pad_index<kTmaPad>((M - k) == M ? 0 : (M - k))];
+            const float2 X = untangle_half_spectrum(zk, zm, __ldg(a.twN + k));
+            const float p = fmaxf(X.x * X.x + X.y * X.y, a.floor_lin_sq);
+            __stcs(o + k, 3.010299956639812f * log2f(p));   // 20 log10 |X|  (spectrogram.py:154-155)
+        }
+        __syncthreads();
+    }
+}
+
+template <int M, int... Rs>
+int launch_stft(const StftArgs& a, int n_rows, cudaStream_t stream) {
+    auto kern = stft_db_kernel<M, Rs...>;
+    const size_t smem = TmaCfg<M>::kFftBytes + sizeof(float) * ((size_t)(a.frames_per_cta - 1) * a.hop + a.n_fft + 8);
+    AA_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    dim3 grid((unsigned)((a.frames_max + a.frames_per_cta - 1) / a.frames_per_cta), (unsigned)n_rows);
+    kern<<<grid, kCsdThreads, smem, stream>>>(a);
+    return launch_check("stft_db_kernel");
+}
+
 __global__ void pcm16_kernel(const short* __restrict__ pcm, long long pcm_stride, int n_frames, int n_channels,
                              int mode, float* __restrict__ out, long long out_stride) {
     const int file = blockIdx.y;
@@ -518,6 +622,52 @@ int launch_csd(const float* d_x, long long row_stride, const int* d_lengths, int
     AA_CUDA_TRY(cudaFuncSetAttribute(csd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 1024));
     csd_kernel<<<n_rows, kCsdThreads, smem, stream>>>(a);
     return launch_check("csd_kernel");
+}
+
+int launch_stft_db(const float* d_x, long long row_stride, const int* d_lengths, int uniform_len, int n_rows,
+                   const int* d_start_idx, const int* d_span, int n_fft, int hop, int use_hann, double floor_db,
+                   int frames_max, float* d_out, cudaStream_t stream) {
+    AA_REQUIRE(d_x && d_start_idx && d_span && d_out, AA_ERR_INVALID_ARGUMENT, "null argument");
+    AA_REQUIRE(row_stride % 4 == 0 && (reinterpret_cast<uintptr_t>(d_x) & 15) == 0, AA_ERR_INVALID_ARGUMENT,
+               "rows must be 16-byte aligned (row_stride % 4 == 0)");
+    AA_REQUIRE(n_fft == 1024 || n_fft == 2048 || n_fft == 4096 || n_fft == 8192, AA_ERR_UNSUPPORTED,
+               "dense STFT kernel: n_fft must be 1024, 2048, 4096 or 8192");
+    AA_REQUIRE(hop > 0, AA_ERR_INVALID_ARGUMENT, "hop_length must be positive");
+    AA_REQUIRE(n_rows <= 65535, AA_ERR_INVALID_ARGUMENT, "at most 65535 rows per call");
+    if (n_rows <= 0 || frames_max <= 0) return AA_OK;
+    CsdTables t;
+    int rc = get_tables(n_fft, &t);
+    if (rc != AA_OK) return rc;
+    StftArgs a{};
+    a.x = d_x;
+    a.row_stride = row_stride;
+    a.lengths = d_lengths;
+    a.uniform_len = uniform_len;
+    a.start_idx = d_start_idx;
+    a.span = d_span;
+    a.n_fft = n_fft;
+    a.hop = hop;
+    a.use_hann = use_hann;
+    a.frames_max = frames_max;
+    const double fl = pow(10.0, floor_db / 20.0);  // spectrogram.py:154
+    a.floor_lin_sq = (float)(fl * fl);
+    a.out = d_out;
+    a.sp = t.sp;
+    a.twN = t.d_twN;
+    a.hann = t.d_hann;
+    a.twc = t.d_twc;
+    // as many overlapping frames per CTA as fit ~64 KB of staged samples (at most 16)
+    long long fpc = 1 + ((long long)(64 * 1024 / 4) - n_fft - 8) / hop;
+    if (fpc < 1) fpc = 1;
+    if (fpc > 16) fpc = 16;
+    if (fpc > frames_max) fpc = frames_max;
+    a.frames_per_cta = (int)fpc;
+    switch (n_fft) {
+        case 1024: return launch_stft<512, 8, 8, 8>(a, n_rows, stream);
+        case 2048: return launch_stft<1024, 4, 4, 8, 8>(a, n_rows, stream);
+        case 4096: return launch_stft<2048, 4, 8, 8, 8>(a, n_rows, stream);
+        default: return launch_stft<4096, 8, 8, 8, 8>(a, n_rows, stream);
+    }
 }
 
 int launch_pcm16(const int16_t* d_pcm, long long pcm_stride, int n_files, int n_frames, int n_channels, int mode,

@@ -17,6 +17,10 @@ int launch_csd(const float* d_x, long long row_stride, const int* d_lengths, int
                const int* d_start_idx, const int* d_frame_idx, const int* d_n_slices, int max_slices,
                const aa_csd_params* p, float* d_out, cudaStream_t stream);
 
+int launch_stft_db(const float* d_x, long long row_stride, const int* d_lengths, int uniform_len, int n_rows,
+                   const int* d_start_idx, const int* d_span, int n_fft, int hop, int use_hann, double floor_db,
+                   int frames_max, float* d_out, cudaStream_t stream);
+
 int launch_pcm16(const int16_t* d_pcm, long long pcm_stride, int n_files, int n_frames, int n_channels, int mode,
                  float* d_out, long long out_stride, cudaStream_t stream);
 

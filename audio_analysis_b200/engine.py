@@ -395,6 +395,27 @@ def csd(rows: Rows, start_idx: torch.Tensor, frame_idx: torch.Tensor, n_slices: 
 # --------------------------------------------------------------------------------------
 
 
+def stft_db(rows: Rows, start_idx: torch.Tensor, span: torch.Tensor, n_fft: int, hop_length: int,
+            use_hann_window: bool, floor_db: float, frames_max: int) -> torch.Tensor:
+    """Dense STFT magnitude in dB, [B, frames_max, n_fft/2 + 1] float32 (frame-major; frames a row does not have
+    stay zero).  n_fft in {1024, 2048, 4096, 8192} (aa_stft_db_batch)."""
+    lib = nat.load()
+    dev = rows.x.device
+    b = rows.n_rows
+    out = torch.zeros((b, int(frames_max), int(n_fft) // 2 + 1), dtype=torch.float32, device=dev)
+    if b == 0 or frames_max <= 0:
+        return out
+    with torch.cuda.device(dev):
+        for r0 in range(0, b, 65535):   # grid.y limit
+            r1 = min(b, r0 + 65535)
+            x = rows.x[r0:r1]
+            nat.check(lib.aa_stft_db_batch(
+                _ptr(x), rows.stride, _ptr(rows.lengths[r0:r1]) if rows.lengths is not None else None, rows.n, r1 - r0,
+                _ptr(start_idx[r0:r1]), _ptr(span[r0:r1]), int(n_fft), int(hop_length), 1 if use_hann_window else 0,
+                float(floor_db), int(frames_max), _ptr(out[r0:r1]), _stream_ptr()))
+    return out
+
+
 def pcm16_to_rows(pcm: torch.Tensor, n_frames: int, n_channels: int, mono_downmix: bool) -> Rows:
     """pcm: [files, n_frames*n_channels] int16 on the device -> float32 rows (io.py:46-95)."""
     lib = nat.load()

@@ -221,6 +221,20 @@ int aa_csd_batch(const float* d_x, int64_t row_stride, const int32_t* d_lengths,
                  void* stream);
 
 /*
+ * aa_stft_db_batch - dense STFT magnitude in dB: every frame of the analysed segment of every row
+ * (replaces _compute_stft_magnitude_db of analyse/spectrogram.py:107-160).
+ *  d_start_idx[n_rows] : first analysed sample (peak + ignore), d_span[n_rows]: analysed samples from there
+ *  frames of row r    : span >= n_fft ? 1 + (span - n_fft) / hop_length : 0, capped at frames_max
+ *  d_out[n_rows][frames_max][n_fft/2 + 1]: 20 log10 max(|rfft(frame * window)|, 10^(floor_db/20)), float32,
+ *                        frame-major (the reference stores (F, T): transpose on the host); entries of frames a
+ *                        row does not have are left untouched
+ *  n_fft in {1024, 2048, 4096, 8192}; other powers of two go through aa_csd_batch with AA_DBREF_NONE.
+ */
+int aa_stft_db_batch(const float* d_x, int64_t row_stride, const int32_t* d_lengths, int32_t uniform_length,
+                     int32_t n_rows, const int32_t* d_start_idx, const int32_t* d_span, int32_t n_fft, int32_t hop_length,
+                     int32_t use_hann_window, double floor_db, int32_t frames_max, float* d_out, void* stream);
+
+/*
  * aa_pcm16_to_float_batch - int16 interleaved PCM -> planar float32 rows.
  * Replaces _convert_integer_pcm_to_float32 + clip + channel split/downmix
  * (analyse/io.py:46-64, :98-113, :66-95) for the bundle wire format written by

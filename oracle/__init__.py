@@ -29,5 +29,7 @@ from .ref_port import (  # noqa: F401
     pick_slices,
     csd_slices,
     waterfall,
+    SpectrogramParams,
+    spectrogram,
     deconvolve,
 )

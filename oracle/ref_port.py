@@ -498,6 +498,49 @@ def waterfall(x: np.ndarray, sr: int, p: CsdParams, only_selected_frames: bool =
 
 
 # ----------------------------------------------------------------------------
+# spectrogram
+# ----------------------------------------------------------------------------
+
+
+@dataclass
+class SpectrogramParams:
+    """analyse/spectrogram.py:37-64 (the fields that reach the numbers)."""
+
+    trim_to_peak: bool = True
+    ignore_leading_seconds: float = 0.0
+    analysis_duration_seconds: Optional[float] = None
+    n_fft: int = 4096
+    hop_length: int = 512
+    use_hann_window: bool = True
+    floor_db: float = -120.0
+
+
+def spectrogram(x: np.ndarray, sr: int, p: SpectrogramParams) -> dict:
+    """analyse/spectrogram.py:163-216 (analyse_spectrogram_for_channel) on top of :107-160, which is the same
+    STFT loop as analyse/waterfall.py:188-230 (`stft_db`) with every frame kept."""
+    if x.ndim != 1:
+        raise ValueError("analyse_spectrogram_for_channel expects a 1D mono array.")
+    seg = x.astype(np.float64, copy=False)
+    start = 0
+    if p.trim_to_peak:                      # :176-179
+        start = int(np.argmax(np.abs(seg)))
+        seg = seg[start:]
+    if p.ignore_leading_seconds > 0.0:      # :181-185
+        skip = int(round(float(p.ignore_leading_seconds) * float(sr)))
+        skip = max(0, min(skip, seg.size))
+        start += skip
+        seg = seg[skip:]
+    if p.analysis_duration_seconds is not None:   # :187-190
+        keep = int(round(float(p.analysis_duration_seconds) * float(sr)))
+        seg = seg[: max(0, min(keep, seg.size))]
+    seg32 = seg.astype(np.float32)          # :192
+    if seg32.size < p.n_fft:
+        raise ValueError("Not enough samples after trimming/selection for spectrogram (need at least n_fft).")
+    times, freq, mag = stft_db(seg32, sr, int(p.n_fft), int(p.hop_length), bool(p.use_hann_window), float(p.floor_db))
+    return {"start": int(start), "length": int(seg32.size), "times": times, "freq": freq, "mag_db": mag}
+
+
+# ----------------------------------------------------------------------------
 # deconvolution (input producer for config 4; SURVEY.md section 8f N1)
 # ----------------------------------------------------------------------------
 

@@ -327,6 +327,71 @@ def test_waterfall_errors():
         wf.analyse_waterfall_for_channel(x, SR, "m", wf.WaterfallAnalysisSettings(analysis_duration_seconds=0.09))
 
 
+# ------------------------------------------------------------------------------------ spectrogram
+
+
+def _spec_golden(case: str, variant: str) -> dict:
+    from conftest import GOLDEN_DIR
+    with np.load(GOLDEN_DIR / "spectrogram.npz") as z:
+        return {k.split("/", 2)[2]: z[k] for k in z.files if k.startswith(f"{case}/{variant}/")}
+
+
+@pytest.mark.parametrize("variant", ["default", "n1024", "n256"])
+def test_spectrogram_matches_reference_fixtures(golden, variant):
+    """Dense STFT (TMA-staged frame runs for n_fft >= 1024, the slice kernel below) against the reference's own
+    output: stored columns within the CSD tolerance, every other frame through its column sum."""
+    from audio_analysis_b200 import spectrogram as sp
+    settings = {
+        "default": sp.SpectrogramAnalysisSettings(),
+        "n1024": sp.SpectrogramAnalysisSettings(n_fft=1024, hop_length=256, use_hann_window=False,
+                                                ignore_leading_seconds=0.01, analysis_duration_seconds=0.5,
+                                                floor_db=-100.0),
+        "n256": sp.SpectrogramAnalysisSettings(n_fft=256, hop_length=200, trim_to_peak=False),
+    }[variant]
+    g = _spec_golden(golden["name"], variant)
+    r = sp.analyse_spectrogram_for_channel(golden["x"], SR, "mono", settings)
+    assert r.analysis_start_sample_index == int(g["start"]) and r.analysis_length_samples == int(g["length"])
+    assert r.magnitude_db.shape == (settings.n_fft // 2 + 1, int(g["n_frames"]))
+    assert r.magnitude_db.dtype == np.float32 and r.time_seconds.dtype == np.float32
+    assert r.time_seconds[-1] == g["time_last"]
+    assert np.array_equal(r.frequency_hz, np.fft.rfftfreq(settings.n_fft, 1.0 / SR).astype(np.float32))
+    err = float(np.max(np.abs(r.magnitude_db[:, g["cols"]].astype(np.float64) - g["mag_db_cols"])))
+    note(f"spectrogram_db_max_abs_err[{variant}]", err)
+    # bins at the floor sit on a cliff of the log; compare those in linear magnitude instead
+    lin_g = 10.0 ** (r.magnitude_db[:, g["cols"]].astype(np.float64) / 20.0)
+    lin_w = 10.0 ** (g["mag_db_cols"].astype(np.float64) / 20.0)
+    scale = lin_w.max(axis=0, keepdims=True)
+    rel = float(np.max(np.abs(lin_g - lin_w) / np.maximum(lin_w, 1e-4 * scale)))
+    note("spectrogram_lin_rel_err", rel)
+    assert rel <= 1e-4 or err <= CSD_TOL_DB, (variant, rel, err)
+    sums = r.magnitude_db.astype(np.float64).sum(axis=0)
+    assert np.max(np.abs(sums - g["col_sums"])) <= 0.05 * r.magnitude_db.shape[0] ** 0.5
+    assert sp.summarise_spectrogram_results_text([r]) == str(g["summary"])
+
+
+def test_spectrogram_batch_oracle_and_errors():
+    from audio_analysis_b200 import spectrogram as sp
+    rng = np.random.default_rng(5)
+    n = 70000
+    chans = np.stack([rng.standard_normal(n).astype(np.float32) * np.exp(-np.arange(n) / (4000.0 * (i + 1))).astype(np.float32)
+                      for i in range(3)])
+    s = sp.SpectrogramAnalysisSettings(n_fft=2048, hop_length=300, ignore_leading_seconds=0.02)
+    res = sp.analyse_spectrogram_batch(chans, SR, ["a", "b", "c"], s)
+    for i, r in enumerate(res):
+        o = oracle.spectrogram(chans[i], SR, oracle.SpectrogramParams(n_fft=2048, hop_length=300,
+                                                                      ignore_leading_seconds=0.02))
+        assert r.analysis_start_sample_index == o["start"] and r.magnitude_db.shape == o["mag_db"].shape
+        lin_g = 10.0 ** (r.magnitude_db.astype(np.float64) / 20.0)
+        lin_w = 10.0 ** (o["mag_db"].astype(np.float64) / 20.0)
+        rel = float(np.max(np.abs(lin_g - lin_w) / np.maximum(lin_w, 1e-4 * lin_w.max())))
+        note("spectrogram_lin_rel_err", rel)
+        assert rel <= 1e-4
+    with pytest.raises(ValueError, match="need at least n_fft"):
+        sp.analyse_spectrogram_for_channel(np.ones(3000, np.float32), SR, "m", sp.SpectrogramAnalysisSettings())
+    with pytest.raises(ValueError, match="expects a 1D mono array"):
+        sp.analyse_spectrogram_for_channel(np.ones((2, 5000), np.float32), SR, "m", sp.SpectrogramAnalysisSettings())
+
+
 # ------------------------------------------------------------------------------------ size-independent properties
 
 
@@ -485,6 +550,12 @@ def test_cli_end_to_end(tmp_path, capsys):
     cli.main(["waterfall", "--input", str(wav), "--no_show"])
     text = capsys.readouterr().out
     assert "slices=18  f_bins=1705" in text and text.count("\n") == 2
+    cli.main(["spectrogram", "--input", str(wav), "--no_show", "--mono", "--n_fft", "2048"])
+    text = capsys.readouterr().out
+    mono = (0.5 * (a["x"] + b["x"])).astype(np.float32)
+    want = oracle.spectrogram(mono, SR, oracle.SpectrogramParams(n_fft=2048))
+    assert text.strip() == (f"[mono] start_sample={want['start']}  len_samples={want['length']}  "
+                            f"dur={want['length'] / SR:.3f}s  stft(n_fft=2048, frames={want['mag_db'].shape[1]})")
 
 
 def test_bundle_end_to_end(tmp_path):

@@ -132,6 +132,9 @@ def test_cli_surface_matches_the_reference_arguments():
     assert a.n_fft == 4096 and a.hop_length == 512 and a.num_slices == 18 and a.no_hann_window and a.style == "3d"
     a = cli.parse_arguments(["bundle", "--input", "run"])
     assert a.bundle_root == "run" and a.reports_subdir == "reports"
+    a = cli.parse_arguments(["spectrogram", "--input", "x.wav", "--duration", "1.5", "--no_hann_window"])
+    assert a.n_fft == 4096 and a.hop_length == 512 and a.floor_db == -120.0 and a.dynamic_range_db == 90.0
+    assert a.analysis_duration_seconds == 1.5 and a.no_hann_window and a.trim_to_peak is True
     with pytest.raises(SystemExit):
         cli.parse_arguments(["zplane", "--input", "x.wav"])  # outside the accelerated path
     out = subprocess.run([sys.executable, "-m", "analyse.cli", "--help"], capture_output=True, text=True, cwd=ROOT)
@@ -142,6 +145,7 @@ def test_analyse_package_aliases_the_reference_module_names():
     import analyse.decay
     import analyse.rt60bands
     import analyse.waterfall
+    import analyse.spectrogram
     import analyse.bundle
     import analyse.io
     import audio_analysis_b200.decay
@@ -155,6 +159,10 @@ def test_analyse_package_aliases_the_reference_module_names():
     for name in ("analyse_waterfall_for_channel", "analyse_waterfall_from_wav_file", "plot_waterfall_from_wav_file",
                  "summarise_waterfall_results_text"):
         assert hasattr(analyse.waterfall, name)
+    for name in ("SpectrogramAnalysisSettings", "ChannelSpectrogramResult", "analyse_spectrogram_for_channel",
+                 "analyse_spectrogram_from_wav_file", "plot_spectrogram_from_wav_file",
+                 "summarise_spectrogram_results_text"):
+        assert hasattr(analyse.spectrogram, name)
     assert hasattr(analyse.bundle, "run_bundle_report") and hasattr(analyse, "load_wav_file")
 
 

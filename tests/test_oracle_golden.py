@@ -150,3 +150,26 @@ def test_error_cases():
     # all-zero IR: flat 0 dB curve, no fits (decay.py:154 clamps to epsilon)
     d = oracle.decay_metrics(np.zeros(1000, np.float32), SR, oracle.DecayParams(compute_edt=True))
     assert np.all(d["edc_db"] == 0.0) and d["fits"] == {} and d["early10"] is None
+
+
+# ---- spectrogram (fixtures from tests/golden/make_golden_next.py) ----------------------------
+
+SPEC_VARIANTS = {
+    "default": oracle.SpectrogramParams(),
+    "n1024": oracle.SpectrogramParams(n_fft=1024, hop_length=256, use_hann_window=False, ignore_leading_seconds=0.01,
+                                      analysis_duration_seconds=0.5, floor_db=-100.0),
+    "n256": oracle.SpectrogramParams(n_fft=256, hop_length=200, trim_to_peak=False),
+}
+
+
+@pytest.mark.parametrize("variant", sorted(SPEC_VARIANTS))
+def test_spectrogram_matches_reference(golden, variant):
+    from conftest import GOLDEN_DIR
+
+    with np.load(GOLDEN_DIR / "spectrogram.npz") as z:
+        g = {k.split("/", 2)[2]: z[k] for k in z.files if k.startswith(f"{golden['name']}/{variant}/")}
+    r = oracle.spectrogram(golden["x"], SR, SPEC_VARIANTS[variant])
+    assert r["start"] == int(g["start"]) and r["length"] == int(g["length"])
+    assert r["mag_db"].shape[1] == int(g["n_frames"]) and r["times"][-1] == g["time_last"]
+    assert np.array_equal(r["mag_db"][:, g["cols"]], g["mag_db_cols"])          # bit-exact float32 columns
+    assert np.array_equal(r["mag_db"].astype(np.float64).sum(axis=0), g["col_sums"])   # every frame pinned
