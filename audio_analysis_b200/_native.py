@@ -47,6 +47,7 @@ EXPORTED_SYMBOLS = (
     "aa_rt60bands_batch",
     "aa_csd_batch",
     "aa_stft_db_batch",
+    "aa_modal_cloud_batch",
     "aa_pcm16_to_float_batch",
     "aa_deconv_plan_create",
     "aa_deconv_plan_destroy",
@@ -143,6 +144,9 @@ def _declare(lib: C.CDLL) -> None:
     lib.aa_csd_batch.argtypes = [vp, i64, vp, i32, i32, vp, vp, vp, i32, C.POINTER(CsdParams), vp, vp]
     lib.aa_stft_db_batch.restype = C.c_int
     lib.aa_stft_db_batch.argtypes = [vp, i64, vp, i32, i32, vp, vp, i32, i32, i32, C.c_double, i32, vp, vp]
+    lib.aa_modal_cloud_batch.restype = C.c_int
+    lib.aa_modal_cloud_batch.argtypes = [vp, i32, i32, i32, vp, vp, i32, i32, i32, C.c_double, C.c_double, C.c_double,
+                                         i32, C.c_double, C.c_double, vp, vp, vp]
     lib.aa_pcm16_to_float_batch.restype = C.c_int
     lib.aa_pcm16_to_float_batch.argtypes = [vp, i64, i32, i32, i32, i32, vp, i64, vp]
     lib.aa_deconv_plan_create.restype = C.c_int

@@ -1,16 +1,17 @@
-"""Command line for the accelerated path: `decay`, `rt60bands`, `waterfall`, `bundle`, `spectrogram`.
+"""Command line for the accelerated path: `decay`, `rt60bands`, `waterfall`, `bundle`, `spectrogram`, `modalcloud`.
 
     python -m analyse.cli decay --input ir.wav --no_show
     python -m analyse.cli rt60bands --input ir.wav --mono --band_mode third --no_show
     python -m analyse.cli waterfall --input ir.wav --no_show
     python -m analyse.cli bundle --input analysis_runs/20250101_120000
     python -m analyse.cli spectrogram --input ir.wav --no_show
+    python -m analyse.cli modalcloud --input ir.wav --no_show
 
 Argument names, defaults and quirks follow the reference's `analyse/cli.py`
-(decay :461-531, rt60bands :536-636, waterfall :1010-1100, bundle :377-388, spectrogram :842-917), including
+(decay :461-531, rt60bands :536-636, waterfall :1010-1100, bundle :377-388, spectrogram :842-917, modalcloud :1105-1145), including
 `decay --compute_edt` defaulting to true, `rt60bands --trim_to_peak` being impossible to
 switch off, and the tri-state `rt60bands --legend_values`.  Each command prints the same
-summary text as the reference.  The reference's other nine subcommands are outside this
+summary text as the reference.  The reference's other eight subcommands are outside this
 build and are rejected by argparse.
 """
 
@@ -22,6 +23,8 @@ from typing import Optional, Sequence
 
 from .bundle import BundleRunSettings, run_bundle_report
 from .decay import DecayAnalysisSettings, DecayPlotSettings, plot_decay_from_wav_file, summarise_decay_results_text
+from .modalcloud import (ModalCloudAnalysisSettings, ModalCloudPlotSettings, plot_modal_cloud_from_wav_file,
+                         summarise_modal_cloud_results_text)
 from .rt60bands import (Rt60BandsAnalysisSettings, Rt60BandsPlotSettings, plot_rt60_bands_from_wav_file,
                         summarise_rt60_bands_results_text)
 from .spectrogram import (SpectrogramAnalysisSettings, SpectrogramPlotSettings, plot_spectrogram_from_wav_file,
@@ -137,6 +140,32 @@ def build_parser() -> argparse.ArgumentParser:
     sp.add_argument("--f_max_hz", type=float, default=20000.0, help="Max frequency to display (default: 20000).")
     sp.add_argument("--dynamic_range_db", type=float, default=90.0,
                     help="Color scale range below max (default: 90). Use 0 to disable and use percentiles.")
+
+    mc = sub.add_parser("modalcloud", help="Modal cloud: frequency vs RT60 points from per-bin STFT decay fits.")
+    mc.add_argument("--input", dest="input_wav_file_path", type=str, required=True)
+    mc.add_argument("--output", dest="output_basename", type=str, default=None)
+    mc.add_argument("--no_show", action="store_true")
+    mc.add_argument("--mono", dest="use_mono_downmix", action="store_true")
+    mc.add_argument("--trim_to_peak", action=BoolOpt, default=True)
+    mc.add_argument("--ignore-leading", dest="ignore_leading_seconds", type=float, default=0.0)
+    mc.add_argument("--duration", dest="analysis_duration_seconds", type=float, default=None)
+    mc.add_argument("--n_fft", type=int, default=8192)
+    mc.add_argument("--hop_length", type=int, default=512)
+    mc.add_argument("--no_hann_window", action="store_true")
+    mc.add_argument("--f_min_hz", type=float, default=20.0)
+    mc.add_argument("--f_max_hz", type=float, default=20000.0)
+    mc.add_argument("--metric", type=str, choices=["t30", "t20", "edt"], default="t30",
+                    help="Which decay fit window to use per bin (default: t30).")
+    mc.add_argument("--log_bins_per_octave", type=int, default=24)
+    mc.add_argument("--min_bins", type=int, default=24)
+    mc.add_argument("--fit_lower_limit_db", type=float, default=-80.0)
+    mc.add_argument("--min_fit_points", type=int, default=10)
+    mc.add_argument("--min_peak_db_above_floor", type=float, default=20.0)
+    mc.add_argument("--floor_db", type=float, default=-120.0)
+    mc.add_argument("--show_median_curve", action=BoolOpt, default=True)
+    mc.add_argument("--median_octave_window", type=float, default=0.25)
+    mc.add_argument("--ylim_seconds_min", type=float, default=None)
+    mc.add_argument("--ylim_seconds_max", type=float, default=None)
     return top
 
 
@@ -255,6 +284,40 @@ def run_spectrogram_command(a: argparse.Namespace) -> str:
     return summarise_spectrogram_results_text(results)
 
 
+def run_modalcloud_command(a: argparse.Namespace) -> str:
+    analysis = ModalCloudAnalysisSettings(
+        use_mono_downmix_for_stereo=bool(a.use_mono_downmix),
+        trim_to_peak=bool(a.trim_to_peak),
+        ignore_leading_seconds=float(a.ignore_leading_seconds),
+        analysis_duration_seconds=a.analysis_duration_seconds,
+        n_fft=int(a.n_fft),
+        hop_length=int(a.hop_length),
+        use_hann_window=not bool(a.no_hann_window),
+        f_min_hz=float(a.f_min_hz),
+        f_max_hz=float(a.f_max_hz),
+        log_bins_per_octave=int(a.log_bins_per_octave),
+        min_bins=int(a.min_bins),
+        metric=str(a.metric),
+        fit_lower_limit_db=float(a.fit_lower_limit_db),
+        min_fit_points=int(a.min_fit_points),
+        min_peak_db_above_floor=float(a.min_peak_db_above_floor),
+        floor_db=float(a.floor_db),
+    )
+    ylim = None
+    if a.ylim_seconds_min is not None and a.ylim_seconds_max is not None:
+        ylim = (float(a.ylim_seconds_min), float(a.ylim_seconds_max))
+    plot = ModalCloudPlotSettings(show_median_curve=bool(a.show_median_curve),
+                                  median_octave_window=float(a.median_octave_window), ylim_seconds=ylim)
+    results = plot_modal_cloud_from_wav_file(
+        input_wav_file_path=str(a.input_wav_file_path),
+        analysis_settings=analysis,
+        plot_settings=plot,
+        output_basename=_basename(a),
+        show_interactive=not bool(a.no_show),
+    )
+    return summarise_modal_cloud_results_text(results)
+
+
 def run_bundle_command(a: argparse.Namespace) -> str:
     index = run_bundle_report(str(a.bundle_root), settings=BundleRunSettings(reports_subdir=str(a.reports_subdir)))
     return f"Wrote bundle report index: {index}"
@@ -266,6 +329,7 @@ COMMANDS = {
     "waterfall": run_waterfall_command,
     "bundle": run_bundle_command,
     "spectrogram": run_spectrogram_command,
+    "modalcloud": run_modalcloud_command,
 }
 
 

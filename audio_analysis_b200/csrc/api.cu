@@ -189,6 +189,16 @@ int aa_stft_db_batch(const float* d_x, int64_t row_stride, const int32_t* d_leng
                               use_hann_window, floor_db, frames_max, d_out, static_cast<cudaStream_t>(stream));
 }
 
+int aa_modal_cloud_batch(const float* d_mag_db, int32_t n_rows, int32_t frames_max, int32_t n_freq,
+                         const int32_t* d_n_frames, const int32_t* d_bin_ranges, int32_t n_bins, int32_t hop_length,
+                         int32_t sample_rate_hz, double range_hi_db, double range_lo_db, double fit_lower_limit_db,
+                         int32_t min_fit_points, double floor_db, double min_peak_db_above_floor, float* d_curve_ws,
+                         double* d_out, void* stream) {
+    return aa::launch_modal_cloud(d_mag_db, n_rows, frames_max, n_freq, d_n_frames, d_bin_ranges, n_bins, hop_length,
+                                  sample_rate_hz, range_hi_db, range_lo_db, fit_lower_limit_db, min_fit_points, floor_db,
+                                  min_peak_db_above_floor, d_curve_ws, d_out, static_cast<cudaStream_t>(stream));
+}
+
 int aa_csd_batch(const float* d_x, int64_t row_stride, const int32_t* d_lengths, int32_t uniform_length,
                  int32_t n_rows, const int32_t* d_start_idx, const int32_t* d_frame_idx, const int32_t* d_n_slices,
                  int32_t max_slices, const aa_csd_params* p, float* d_out, void* stream) {

@@ -45,3 +45,13 @@ int launch_band_fit(const float* d_y, long long y_stride, const float* d_part, l
                     const int* d_start_idx, int start_div, int min_samples, double* d_rt60_out, cudaStream_t stream);
 
 }  // namespace aa
+
+namespace aa {
+
+// modal cloud (modal.cu): log-bin aggregation of the dense STFT + per-bin decay fits
+int launch_modal_cloud(const float* d_mag_db, int n_rows, int frames_max, int n_freq, const int* d_n_frames,
+                       const int* d_bin_ranges, int n_bins, int hop, int sr, double hi_db, double lo_db,
+                       double fit_lower_limit_db, int min_points, double floor_db, double min_peak_above_floor,
+                       float* d_curve_ws, double* d_out, cudaStream_t stream);
+
+}  // namespace aa

@@ -416,6 +416,26 @@ def stft_db(rows: Rows, start_idx: torch.Tensor, span: torch.Tensor, n_fft: int,
     return out
 
 
+def modal_cloud(mag_db: torch.Tensor, n_frames: torch.Tensor, bin_ranges: torch.Tensor, hop_length: int,
+                sample_rate_hz: int, range_db: Tuple[float, float], fit_lower_limit_db: float, min_fit_points: int,
+                floor_db: float, min_peak_db_above_floor: float) -> torch.Tensor:
+    """[B, n_bins, 2] float64 (rt60 seconds, r^2; NaN = no point) from a dense STFT [B, T_max, F] (aa_modal_cloud_batch)."""
+    lib = nat.load()
+    dev = mag_db.device
+    b, t_max, f = (int(v) for v in mag_db.shape)
+    n_bins = int(bin_ranges.shape[0])
+    out = torch.full((b, n_bins, 2), float("nan"), dtype=torch.float64, device=dev)
+    if b == 0 or t_max == 0:
+        return out
+    ws = torch.empty((b * n_bins * t_max,), dtype=torch.float32, device=dev)
+    with torch.cuda.device(dev):
+        nat.check(lib.aa_modal_cloud_batch(
+            _ptr(mag_db), b, t_max, f, _ptr(n_frames), _ptr(bin_ranges), n_bins, int(hop_length), int(sample_rate_hz),
+            float(range_db[0]), float(range_db[1]), float(fit_lower_limit_db), int(min_fit_points), float(floor_db),
+            float(min_peak_db_above_floor), _ptr(ws), _ptr(out), _stream_ptr()))
+    return out
+
+
 def pcm16_to_rows(pcm: torch.Tensor, n_frames: int, n_channels: int, mono_downmix: bool) -> Rows:
     """pcm: [files, n_frames*n_channels] int16 on the device -> float32 rows (io.py:46-95)."""
     lib = nat.load()

@@ -235,6 +235,22 @@ int aa_stft_db_batch(const float* d_x, int64_t row_stride, const int32_t* d_leng
                      int32_t use_hann_window, double floor_db, int32_t frames_max, float* d_out, void* stream);
 
 /*
+ * aa_modal_cloud_batch - per log-frequency bin decay fits over the dense STFT
+ * (replaces _aggregate_to_log_bins + the per-bin loop of analyse/modalcloud.py:176-207, :339-371).
+ *  d_mag_db[n_rows][frames_max][n_freq] : aa_stft_db_batch output (frame-major dB)
+ *  d_n_frames[n_rows]                   : frames each row has
+ *  d_bin_ranges[n_bins][2]              : rfft-bin range [k0, k1) of every log bin (k0 == k1: empty -> no point)
+ *  range_hi_db / range_lo_db            : the fit range of the chosen metric, e.g. (-5, -35)
+ *  d_curve_ws[n_rows * n_bins * frames_max] float32 scratch (the per-bin decay curves in dB)
+ *  d_out[n_rows][n_bins][2] (double)    : rt60 seconds, r^2; NaN = the bin yields no point
+ */
+int aa_modal_cloud_batch(const float* d_mag_db, int32_t n_rows, int32_t frames_max, int32_t n_freq,
+                         const int32_t* d_n_frames, const int32_t* d_bin_ranges, int32_t n_bins, int32_t hop_length,
+                         int32_t sample_rate_hz, double range_hi_db, double range_lo_db, double fit_lower_limit_db,
+                         int32_t min_fit_points, double floor_db, double min_peak_db_above_floor, float* d_curve_ws,
+                         double* d_out, void* stream);
+
+/*
  * aa_pcm16_to_float_batch - int16 interleaved PCM -> planar float32 rows.
  * Replaces _convert_integer_pcm_to_float32 + clip + channel split/downmix
  * (analyse/io.py:46-64, :98-113, :66-95) for the bundle wire format written by

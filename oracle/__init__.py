@@ -31,5 +31,10 @@ from .ref_port import (  # noqa: F401
     waterfall,
     SpectrogramParams,
     spectrogram,
+    ModalParams,
+    modal_log_bins,
+    modal_aggregate,
+    modal_fit,
+    modal_cloud,
     deconvolve,
 )

@@ -541,6 +541,135 @@ def spectrogram(x: np.ndarray, sr: int, p: SpectrogramParams) -> dict:
 
 
 # ----------------------------------------------------------------------------
+# modal cloud
+# ----------------------------------------------------------------------------
+
+
+@dataclass
+class ModalParams:
+    """analyse/modalcloud.py:45-84 (the fields that reach the numbers)."""
+
+    trim_to_peak: bool = True
+    ignore_leading_seconds: float = 0.0
+    analysis_duration_seconds: Optional[float] = None
+    n_fft: int = 8192
+    hop_length: int = 512
+    use_hann_window: bool = True
+    f_min_hz: float = 20.0
+    f_max_hz: float = 20000.0
+    log_bins_per_octave: int = 24
+    min_bins: int = 24
+    floor_db: float = -120.0
+    fit_lower_limit_db: float = -80.0
+    t30_range_db: Tuple[float, float] = (-5.0, -35.0)
+    t20_range_db: Tuple[float, float] = (-5.0, -25.0)
+    edt_range_db: Tuple[float, float] = (0.0, -10.0)
+    metric: str = "t30"
+    min_fit_points: int = 10
+    min_peak_db_above_floor: float = 20.0
+
+
+def modal_log_bins(f_min: float, f_max: float, per_octave: int, min_bins: int) -> np.ndarray:
+    """analyse/modalcloud.py:168-173."""
+    import math
+
+    lo = float(max(1.0, f_min))
+    hi = float(max(lo * 1.001, f_max))
+    octs = float(math.log2(hi / lo))
+    n = int(max(min_bins, math.ceil(octs * float(max(4, per_octave)))))
+    return (lo * (2.0 ** (np.linspace(0.0, octs, n + 1, dtype=np.float64)))).astype(np.float32)
+
+
+def modal_aggregate(freq: np.ndarray, mag_db: np.ndarray, edges_f32: np.ndarray):
+    """analyse/modalcloud.py:176-207: mean of linear magnitudes per log bin, back to dB; NaN rows for empty bins."""
+    edges = edges_f32.astype(np.float64)
+    centres = np.sqrt(edges[:-1] * edges[1:]).astype(np.float32)
+    lin = 10.0 ** (mag_db.astype(np.float64) / 20.0)
+    out = np.full((centres.size, mag_db.shape[1]), np.nan, dtype=np.float32)
+    for b in range(centres.size):
+        sel = (freq >= float(edges[b])) & (freq < float(edges[b + 1]))
+        if not np.any(sel):
+            continue
+        m = np.maximum(np.mean(lin[sel, :], axis=0), 1e-30)
+        out[b, :] = (20.0 * np.log10(m)).astype(np.float32)
+    return centres, out
+
+
+def modal_fit(t: np.ndarray, curve: np.ndarray, range_db, lower_limit_db: float, min_points: int):
+    """analyse/modalcloud.py:239-281.  (slope, intercept, r2, rt60) or None."""
+    hi, lo = float(range_db[0]), float(range_db[1])
+    if lo > hi:
+        raise ValueError("range_db should be (higher_db, lower_db), e.g. (-5, -35).")
+    t0 = crossing_time(t, curve, hi)
+    t1 = crossing_time(t, curve, max(lo, float(lower_limit_db)))
+    if t0 is None or t1 is None or t1 <= t0:
+        return None
+    sel = (t >= t0) & (t <= t1)
+    if int(np.sum(sel)) < int(min_points):
+        return None
+    tt = t[sel].astype(np.float64)
+    yy = curve[sel].astype(np.float64)
+    coeffs, _, _, _ = np.linalg.lstsq(np.column_stack([tt, np.ones_like(tt)]), yy, rcond=None)
+    slope, icpt = float(coeffs[0]), float(coeffs[1])
+    if slope >= 0.0:
+        return None
+    pred = slope * tt + icpt
+    ss_res = float(np.sum((yy - pred) ** 2))
+    ss_tot = float(np.sum((yy - np.mean(yy)) ** 2))
+    r2 = 1.0 - (ss_res / ss_tot) if ss_tot > 0.0 else 0.0
+    return slope, icpt, r2, float(-60.0 / slope)
+
+
+def modal_cloud(x: np.ndarray, sr: int, p: ModalParams) -> dict:
+    """analyse/modalcloud.py:284-391 (analyse_modal_cloud_for_channel)."""
+    seg = x.astype(np.float64, copy=False)
+    start = 0
+    if p.trim_to_peak:
+        start = int(np.argmax(np.abs(seg)))
+        seg = seg[start:]
+    if p.ignore_leading_seconds > 0.0:
+        skip = int(round(float(p.ignore_leading_seconds) * float(sr)))
+        skip = max(0, min(skip, seg.size))
+        start += skip
+        seg = seg[skip:]
+    if p.analysis_duration_seconds is not None:
+        keep = int(round(float(p.analysis_duration_seconds) * float(sr)))
+        seg = seg[: max(0, min(keep, seg.size))]
+    seg32 = seg.astype(np.float32)
+    if seg32.size < p.n_fft:
+        raise ValueError("Not enough samples after trimming/selection for modal cloud (need at least n_fft).")
+    times, freq, mag = stft_db(seg32, sr, int(p.n_fft), int(p.hop_length), bool(p.use_hann_window), float(p.floor_db))
+    nyq = 0.5 * float(sr)
+    f_lo = float(np.clip(p.f_min_hz, 1.0, nyq))
+    f_hi = float(np.clip(p.f_max_hz, f_lo, nyq))
+    keep_f = (freq >= f_lo) & (freq <= f_hi)                      # :324-327
+    edges = modal_log_bins(f_lo, f_hi, int(p.log_bins_per_octave), int(p.min_bins))
+    centres, curves = modal_aggregate(freq[keep_f], mag[keep_f, :], edges)
+    metric = str(p.metric).lower()
+    if metric == "t20":
+        rng = p.t20_range_db
+    elif metric == "edt":
+        rng = p.edt_range_db
+    else:
+        metric, rng = "t30", p.t30_range_db
+    points = []
+    for b in range(centres.size):
+        curve = curves[b, :]
+        if not np.all(np.isfinite(curve)):
+            continue
+        peak = float(np.max(curve))
+        if (peak - float(p.floor_db)) < float(p.min_peak_db_above_floor):
+            continue
+        rel = (curve - peak).astype(np.float32)
+        fit = modal_fit(times, rel, rng, float(p.fit_lower_limit_db), int(p.min_fit_points))
+        if fit is None:
+            continue
+        points.append((float(centres[b]), float(fit[3]), float(fit[2])))
+    points.sort(key=lambda q: q[0])
+    return {"start": int(start), "length": int(seg32.size), "metric": metric, "points": points}
+
+
+# ----------------------------------------------------------------------------
 # deconvolution (input producer for config 4; SURVEY.md section 8f N1)
 # ----------------------------------------------------------------------------
 

@@ -1,5 +1,6 @@
 #!/usr/bin/env python
-"""Golden vectors for the rows SURVEY.md 8f marks "next" (N2 spectrogram), from the UNMODIFIED reference.
+"""Golden vectors for the rows SURVEY.md 8f marks "next" (N2 spectrogram, N3 modal cloud), from the UNMODIFIED
+reference.
 
 Run in the build container only (needs /root/reference):
 
@@ -55,6 +56,43 @@ def main():
         print("spectrogram", name, {k.split("/", 1)[1]: getattr(v, "shape", None) for k, v in store.items()
                                     if k.startswith(name) and k.endswith("mag_db_cols")})
     np.savez_compressed(HERE / "spectrogram.npz", **store)
+
+    # ---- N3 modal cloud (analyse/modalcloud.py:284): the 0.3 s fixtures are short for n_fft 8192, so the cloud is
+    # also taken with n_fft 2048 / hop 128 and from two longer synthetic tails
+    import analyse.modalcloud as rmc
+    from make_golden import synth_pcm16
+
+    modal = {}
+    inputs = {}
+    for name, *_ in CASES:
+        with np.load(HERE / f"{name}.npz") as z:
+            inputs[name] = z["pcm"]
+    inputs["long_96000"] = synth_pcm16(96000, sr, 0.8, 9000, 201)
+    inputs["long_144000"] = synth_pcm16(144000, sr, 1.4, 12000, 202, floor_db=-70.0)
+    modal["long_96000/pcm"] = inputs["long_96000"]
+    modal["long_144000/pcm"] = inputs["long_144000"]
+    for name, pcm in inputs.items():
+        x = (pcm.astype(np.float32) / 32768.0).astype(np.float32)
+        variants = {
+            "n2048": rmc.ModalCloudAnalysisSettings(n_fft=2048, hop_length=128),
+            "n2048_t20": rmc.ModalCloudAnalysisSettings(n_fft=2048, hop_length=128, metric="t20", log_bins_per_octave=12,
+                                                        ignore_leading_seconds=0.005, min_fit_points=6),
+            "n1024_edt": rmc.ModalCloudAnalysisSettings(n_fft=1024, hop_length=64, metric="edt", f_min_hz=100.0,
+                                                        f_max_hz=12000.0, use_hann_window=False),
+        }
+        if pcm.size >= 90000:
+            variants["default"] = rmc.ModalCloudAnalysisSettings()
+        for tag, settings in variants.items():
+            r = rmc.analyse_modal_cloud_for_channel(x, sr, "mono", settings)
+            key = f"{name}/{tag}"
+            modal[f"{key}/start"] = np.int64(r.analysis_start_sample_index)
+            modal[f"{key}/length"] = np.int64(r.analysis_length_samples)
+            modal[f"{key}/metric"] = np.array(r.metric)
+            modal[f"{key}/points"] = np.array([[q.centre_hz, q.rt60_seconds, q.r_squared] for q in r.points],
+                                              dtype=np.float64).reshape(-1, 3)
+            modal[f"{key}/summary"] = np.array(rmc.summarise_modal_cloud_results_text([r]))
+            print("modalcloud", key, "points", len(r.points))
+    np.savez_compressed(HERE / "modalcloud.npz", **modal)
     print("done")
 
 

@@ -392,6 +392,75 @@ def test_spectrogram_batch_oracle_and_errors():
         sp.analyse_spectrogram_for_channel(np.ones((2, 5000), np.float32), SR, "m", sp.SpectrogramAnalysisSettings())
 
 
+# ------------------------------------------------------------------------------------ modal cloud
+
+
+def _modal_compare(tag, got_points, want: np.ndarray):
+    """Points are matched by bin centre.  A bin's curve is a noisy STFT magnitude, so "first frame <= target" can
+    move by a frame when a value differs in the 4th decimal of a dB: most points agree to 1e-5, a few move."""
+    got = {round(p.centre_hz, 3): p for p in got_points}
+    ref = {round(float(c), 3): (float(rt), float(r2)) for c, rt, r2 in want}
+    both = sorted(set(got) & set(ref))
+    only = len(set(got) ^ set(ref))
+    rel = np.array([abs(got[c].rt60_seconds - ref[c][0]) / ref[c][0] for c in both])
+    note(f"modal_points_missing_or_extra_frac[{tag}]", only / max(1, len(ref)))
+    note(f"modal_rt60_rel_err_median[{tag}]", float(np.median(rel)) if rel.size else 0.0)
+    note(f"modal_rt60_frac_outside_0.5pct[{tag}]", float(np.mean(rel > FIT_REL)) if rel.size else 0.0)
+    assert only <= max(2, 0.03 * len(ref)), (tag, only, len(ref))
+    assert rel.size and float(np.median(rel)) <= 1e-4, (tag, float(np.median(rel)))
+    assert float(np.mean(rel > FIT_REL)) <= 0.03, (tag, float(np.mean(rel > FIT_REL)))
+    r2 = np.array([abs(got[c].r_squared - ref[c][1]) for c in both])
+    assert float(np.median(r2)) <= 1e-4
+
+
+FIT_REL = 0.005
+
+
+@pytest.mark.parametrize("case,variant", [("smooth_48000", "n2048"), ("odd_45001", "n2048_t20"),
+                                          ("prime_factor_50022", "n1024_edt"), ("long_96000", "default"),
+                                          ("long_144000", "default"), ("long_144000", "n2048_t20")])
+def test_modal_cloud_matches_reference_fixtures(case, variant):
+    from conftest import GOLDEN_DIR
+    from audio_analysis_b200 import modalcloud as mc
+    with np.load(GOLDEN_DIR / "modalcloud.npz") as z:
+        g = {k: z[k] for k in z.files}
+    pcm = g[f"{case}/pcm"] if f"{case}/pcm" in g else load_golden(case)["pcm"]
+    x = (pcm.astype(np.float32) / 32768.0).astype(np.float32)
+    settings = {
+        "default": mc.ModalCloudAnalysisSettings(),
+        "n2048": mc.ModalCloudAnalysisSettings(n_fft=2048, hop_length=128),
+        "n2048_t20": mc.ModalCloudAnalysisSettings(n_fft=2048, hop_length=128, metric="t20", log_bins_per_octave=12,
+                                                   ignore_leading_seconds=0.005, min_fit_points=6),
+        "n1024_edt": mc.ModalCloudAnalysisSettings(n_fft=1024, hop_length=64, metric="edt", f_min_hz=100.0,
+                                                   f_max_hz=12000.0, use_hann_window=False),
+    }[variant]
+    key = f"{case}/{variant}"
+    r = mc.analyse_modal_cloud_for_channel(x, SR, "mono", settings)
+    assert r.analysis_start_sample_index == int(g[f"{key}/start"]) and r.analysis_length_samples == int(g[f"{key}/length"])
+    assert r.metric == str(g[f"{key}/metric"])
+    _modal_compare(key, r.points, g[f"{key}/points"])
+    text = mc.summarise_modal_cloud_results_text([r])
+    assert text.splitlines()[0].rsplit(" points=", 1)[0] == str(g[f"{key}/summary"]).splitlines()[0].rsplit(" points=", 1)[0]
+
+
+def test_modal_cloud_batch_and_errors():
+    from audio_analysis_b200 import modalcloud as mc
+    rng = np.random.default_rng(11)
+    n = 120000
+    chans = np.stack([(rng.standard_normal(n) * 10.0 ** (-3.0 * np.arange(n) / (SR * (0.6 + 0.3 * i)))).astype(np.float32)
+                      for i in range(2)])
+    s = mc.ModalCloudAnalysisSettings(n_fft=4096, hop_length=256)
+    res = mc.analyse_modal_cloud_batch(chans, SR, ["a", "b"], s)
+    for i, r in enumerate(res):
+        o = oracle.modal_cloud(chans[i], SR, oracle.ModalParams(n_fft=4096, hop_length=256))
+        assert r.analysis_start_sample_index == o["start"] and r.metric == "t30"
+        _modal_compare(f"batch{i}", r.points, np.array(o["points"]).reshape(-1, 3))
+        rt = np.median([p.rt60_seconds for p in r.points])
+        assert abs(rt - (0.6 + 0.3 * i)) < 0.15 * (0.6 + 0.3 * i)     # the clouds sit at the synthetic RT60
+    with pytest.raises(ValueError, match="need at least n_fft"):
+        mc.analyse_modal_cloud_for_channel(np.ones(5000, np.float32), SR, "m", mc.ModalCloudAnalysisSettings())
+
+
 # ------------------------------------------------------------------------------------ size-independent properties
 
 
@@ -550,6 +619,9 @@ def test_cli_end_to_end(tmp_path, capsys):
     cli.main(["waterfall", "--input", str(wav), "--no_show"])
     text = capsys.readouterr().out
     assert "slices=18  f_bins=1705" in text and text.count("\n") == 2
+    cli.main(["modalcloud", "--input", str(wav), "--no_show", "--mono", "--n_fft", "2048", "--hop_length", "128"])
+    text = capsys.readouterr().out
+    assert text.startswith("[mono] metric=t30 start_sample=") and "  rt60: median=" in text
     cli.main(["spectrogram", "--input", str(wav), "--no_show", "--mono", "--n_fft", "2048"])
     text = capsys.readouterr().out
     mono = (0.5 * (a["x"] + b["x"])).astype(np.float32)

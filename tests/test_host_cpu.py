@@ -135,6 +135,9 @@ def test_cli_surface_matches_the_reference_arguments():
     a = cli.parse_arguments(["spectrogram", "--input", "x.wav", "--duration", "1.5", "--no_hann_window"])
     assert a.n_fft == 4096 and a.hop_length == 512 and a.floor_db == -120.0 and a.dynamic_range_db == 90.0
     assert a.analysis_duration_seconds == 1.5 and a.no_hann_window and a.trim_to_peak is True
+    a = cli.parse_arguments(["modalcloud", "--input", "x.wav", "--metric", "edt", "--no-show_median_curve"])
+    assert a.n_fft == 8192 and a.hop_length == 512 and a.metric == "edt" and a.log_bins_per_octave == 24
+    assert a.min_fit_points == 10 and a.min_peak_db_above_floor == 20.0 and a.show_median_curve is False
     with pytest.raises(SystemExit):
         cli.parse_arguments(["zplane", "--input", "x.wav"])  # outside the accelerated path
     out = subprocess.run([sys.executable, "-m", "analyse.cli", "--help"], capture_output=True, text=True, cwd=ROOT)
@@ -146,6 +149,7 @@ def test_analyse_package_aliases_the_reference_module_names():
     import analyse.rt60bands
     import analyse.waterfall
     import analyse.spectrogram
+    import analyse.modalcloud
     import analyse.bundle
     import analyse.io
     import audio_analysis_b200.decay
@@ -163,6 +167,10 @@ def test_analyse_package_aliases_the_reference_module_names():
                  "analyse_spectrogram_from_wav_file", "plot_spectrogram_from_wav_file",
                  "summarise_spectrogram_results_text"):
         assert hasattr(analyse.spectrogram, name)
+    for name in ("ModalCloudAnalysisSettings", "ModalPoint", "ChannelModalCloudResult", "analyse_modal_cloud_for_channel",
+                 "analyse_modal_cloud_from_wav_file", "plot_modal_cloud_from_wav_file",
+                 "summarise_modal_cloud_results_text"):
+        assert hasattr(analyse.modalcloud, name)
     assert hasattr(analyse.bundle, "run_bundle_report") and hasattr(analyse, "load_wav_file")
 
 

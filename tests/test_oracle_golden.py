@@ -173,3 +173,41 @@ def test_spectrogram_matches_reference(golden, variant):
     assert r["mag_db"].shape[1] == int(g["n_frames"]) and r["times"][-1] == g["time_last"]
     assert np.array_equal(r["mag_db"][:, g["cols"]], g["mag_db_cols"])          # bit-exact float32 columns
     assert np.array_equal(r["mag_db"].astype(np.float64).sum(axis=0), g["col_sums"])   # every frame pinned
+
+
+# ---- modal cloud ------------------------------------------------------------------------------
+
+MODAL_VARIANTS = {
+    "default": oracle.ModalParams(),
+    "n2048": oracle.ModalParams(n_fft=2048, hop_length=128),
+    "n2048_t20": oracle.ModalParams(n_fft=2048, hop_length=128, metric="t20", log_bins_per_octave=12,
+                                    ignore_leading_seconds=0.005, min_fit_points=6),
+    "n1024_edt": oracle.ModalParams(n_fft=1024, hop_length=64, metric="edt", f_min_hz=100.0, f_max_hz=12000.0,
+                                    use_hann_window=False),
+}
+
+
+def modal_golden():
+    from conftest import GOLDEN_DIR
+
+    with np.load(GOLDEN_DIR / "modalcloud.npz") as z:
+        return {k: z[k] for k in z.files}
+
+
+def modal_input(g: dict, case: str) -> np.ndarray:
+    pcm = g[f"{case}/pcm"] if f"{case}/pcm" in g else load_golden(case)["pcm"]
+    return (pcm.astype(np.float32) / 32768.0).astype(np.float32)
+
+
+@pytest.mark.parametrize("case,variant", [("smooth_48000", "n2048"), ("odd_45001", "n2048_t20"),
+                                          ("prime_factor_50022", "n1024_edt"), ("onset_at_zero_48000", "n2048"),
+                                          ("long_96000", "default"), ("long_144000", "default"),
+                                          ("long_144000", "n2048_t20"), ("radix13_62400", "n1024_edt")])
+def test_modal_cloud_matches_reference(case, variant):
+    g = modal_golden()
+    r = oracle.modal_cloud(modal_input(g, case), SR, MODAL_VARIANTS[variant])
+    key = f"{case}/{variant}"
+    assert r["start"] == int(g[f"{key}/start"]) and r["length"] == int(g[f"{key}/length"])
+    assert r["metric"] == str(g[f"{key}/metric"])
+    got = np.array(r["points"], dtype=np.float64).reshape(-1, 3)
+    assert np.array_equal(got, g[f"{key}/points"])       # same bins, bit-exact RT60 and r^2
