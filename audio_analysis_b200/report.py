@@ -1,10 +1,10 @@
-"""Report writer for the hot-path blocks (decay, rt60bands, waterfall).
+"""Report writer for the accelerated blocks (decay, rt60bands, spectrogram, waterfall, modal cloud).
 
 Mirror of the part of the reference's `analyse/report.py` that lies on the
-accelerated path (report.py:252-287, :339-354): same `ReportSettings` fields,
-same Markdown section layout and text summaries, same output file names.  The
-other six report blocks (impulse-response plots, frequency response, group delay,
-spectrogram, diffusion, modal cloud) are outside this build's scope (SURVEY.md
+accelerated path (report.py:252-287, :322-354, :371-386): same `ReportSettings`
+fields, same Markdown section layout and order, same text summaries, same output
+file names.  The other four report blocks (impulse-response plots, frequency
+response, group delay, diffusion) are outside this build's scope (SURVEY.md
 section 2); their flags are accepted and the report says explicitly that they were
 not run, instead of silently dropping them.
 
@@ -25,8 +25,12 @@ from . import engine
 from .decay import (ChannelDecayAnalysis, DecayAnalysisSettings, DecayPlotSettings, analyse_decay_batch,
                     plot_decay_figure, summarise_decay_results_text)
 from .io import DEFAULT_EXPECTED_SAMPLE_RATE_HZ, LoadedAudio, get_analysis_channels, load_wav_file
+from .modalcloud import (ChannelModalCloudResult, ModalCloudAnalysisSettings, ModalCloudPlotSettings,
+                         analyse_modal_cloud_batch, plot_modal_cloud_figure, summarise_modal_cloud_results_text)
 from .rt60bands import (Rt60BandsAnalysisSettings, Rt60BandsChannelResult, Rt60BandsPlotSettings,
                         analyse_rt60_bands_batch, plot_rt60_bands_figure, summarise_rt60_bands_results_text)
+from .spectrogram import (ChannelSpectrogramResult, SpectrogramAnalysisSettings, SpectrogramPlotSettings,
+                          analyse_spectrogram_batch, plot_spectrogram_figure, summarise_spectrogram_results_text)
 from .waterfall import (ChannelWaterfallResult, WaterfallAnalysisSettings, WaterfallPlotSettings,
                         analyse_waterfall_batch, plot_waterfall_figure, summarise_waterfall_results_text)
 
@@ -34,9 +38,7 @@ OUT_OF_SCOPE_BLOCKS = (
     ("run_impulse_response_plots", "Impulse response"),
     ("run_frequency_response", "Frequency response"),
     ("run_group_delay", "Group delay"),
-    ("run_spectrogram", "Spectrogram"),
     ("run_diffusion", "Diffusion / echo density proxy"),
-    ("run_modal_cloud", "Modal cloud"),
 )
 
 
@@ -68,13 +70,13 @@ class ReportSettings:
     frequency_response_plot_settings: Optional[Any] = None
     group_delay_analysis_settings: Optional[Any] = None
     group_delay_plot_settings: Optional[Any] = None
-    spectrogram_analysis_settings: Optional[Any] = None
-    spectrogram_plot_settings: Optional[Any] = None
+    spectrogram_analysis_settings: Optional[SpectrogramAnalysisSettings] = None
+    spectrogram_plot_settings: Optional[SpectrogramPlotSettings] = None
     waterfall_analysis_settings: Optional[WaterfallAnalysisSettings] = None
     waterfall_plot_settings: Optional[WaterfallPlotSettings] = None
     diffusion_analysis_settings: Optional[Any] = None
-    modal_cloud_analysis_settings: Optional[Any] = None
-    modal_cloud_plot_settings: Optional[Any] = None
+    modal_cloud_analysis_settings: Optional[ModalCloudAnalysisSettings] = None
+    modal_cloud_plot_settings: Optional[ModalCloudPlotSettings] = None
 
 
 @dataclass(frozen=True)
@@ -143,9 +145,26 @@ class _FileJob:
     first_row: int = 0         # index of this file's first channel in the batch
 
 
+def _per_channel_block(parts, have_plots, results, figure_fn, title, stem, alt, base, mono, summary) -> None:
+    """One `<base>_<stem>_<CH>.png` per channel, the left / right image links and the text summary."""
+    from .plotting import finalize_and_show_or_save
+
+    if have_plots:
+        for r in results:
+            finalize_and_show_or_save(figure_fn(r), base.with_name(f"{base.stem}_{stem}_{r.channel_name}.png")
+                                      .with_suffix(".png"), False)
+    parts.append(_section(title))
+    parts.append(_image(base, f"_{stem}_left", f"{alt} (left)"))
+    if not mono:
+        parts.append(_image(base, f"_{stem}_right", f"{alt} (right)"))
+    parts.append(_code(summary))
+
+
 def _render(job: _FileJob, settings: ReportSettings, decay_s, bands_s, water_s,
             decay_r: Optional[List[ChannelDecayAnalysis]], bands_r: Optional[List[Rt60BandsChannelResult]],
-            water_r: Optional[List[ChannelWaterfallResult]]) -> ReportResults:
+            water_r: Optional[List[ChannelWaterfallResult]], spec_s=None,
+            spec_r: Optional[List[ChannelSpectrogramResult]] = None, modal_s=None,
+            modal_r: Optional[List[ChannelModalCloudResult]] = None) -> ReportResults:
     from .plotting import finalize_and_show_or_save, pyplot
 
     have_plots = pyplot() is not None
@@ -171,6 +190,12 @@ def _render(job: _FileJob, settings: ReportSettings, decay_s, bands_s, water_s,
         parts += [_section("RT60 by band"), _image(base, "_rt60bands", "RT60 by frequency band"),
                   _code(summarise_rt60_bands_results_text(bands_r, bool(bands_s.include_t20),
                                                           bool(bands_s.include_edt)))]
+    if spec_r is not None:   # reference report.py:322-337
+        ps = settings.spectrogram_plot_settings or SpectrogramPlotSettings()
+        _per_channel_block(parts, have_plots, spec_r,
+                           lambda r: plot_spectrogram_figure(r, spec_s, ps, title=f"Spectrogram — {job.path} — {r.channel_name}"),
+                           "Spectrogram", "spectrogram", "Spectrogram", base,
+                           settings.common_use_mono_downmix_for_stereo, summarise_spectrogram_results_text(spec_r))
     if water_r is not None:
         if have_plots:
             for r in water_r:
@@ -183,11 +208,17 @@ def _render(job: _FileJob, settings: ReportSettings, decay_s, bands_s, water_s,
         if not settings.common_use_mono_downmix_for_stereo:
             parts.append(_image(base, "_waterfall_right", "Waterfall plot (right)"))
         parts.append(_code(summarise_waterfall_results_text(water_r)))
+    if modal_r is not None:   # reference report.py:371-386
+        ps = settings.modal_cloud_plot_settings or ModalCloudPlotSettings()
+        _per_channel_block(parts, have_plots, modal_r,
+                           lambda r: plot_modal_cloud_figure(r, modal_s, ps, title=f"Modal cloud — {job.path} — {r.channel_name}"),
+                           "Modal cloud", "modalcloud", "Modal cloud", base,
+                           settings.common_use_mono_downmix_for_stereo, summarise_modal_cloud_results_text(modal_r))
     skipped = [title for flag, title in OUT_OF_SCOPE_BLOCKS if getattr(settings, flag)]
     if skipped:
         parts.append(_section("Blocks not run"))
-        parts.append("The B200 build accelerates the decay, RT60-by-band and waterfall blocks only. "
-                     "Not run: " + ", ".join(skipped) + ".\n")
+        parts.append("The B200 build accelerates the decay, RT60-by-band, spectrogram, waterfall and modal-cloud "
+                     "blocks only. Not run: " + ", ".join(skipped) + ".\n")
     text = "".join(parts).rstrip() + "\n"
     md_path = Path(f"{job.basename}_report.md")
     md_path.parent.mkdir(parents=True, exist_ok=True)
@@ -225,13 +256,19 @@ def run_reports_batch(
     decay_r = analyse_decay_batch(rows, sr, names, decay_s) if settings.run_decay else None
     bands_r = analyse_rt60_bands_batch(rows, sr, names, bands_s) if settings.run_rt60_bands else None
     water_r = analyse_waterfall_batch(rows, sr, names, water_s) if settings.run_waterfall else None
+    spec_s = _apply_common_overrides(settings.spectrogram_analysis_settings or SpectrogramAnalysisSettings(), settings)
+    modal_s = _apply_common_overrides(settings.modal_cloud_analysis_settings or ModalCloudAnalysisSettings(), settings)
+    spec_r = analyse_spectrogram_batch(rows, sr, names, spec_s) if settings.run_spectrogram else None
+    modal_r = analyse_modal_cloud_batch(rows, sr, names, modal_s) if settings.run_modal_cloud else None
     out = []
     for job in jobs:
         sl = slice(job.first_row, job.first_row + len(job.names))
         out.append(_render(job, settings, decay_s, bands_s, water_s,
                            None if decay_r is None else decay_r[sl],
                            None if bands_r is None else bands_r[sl],
-                           None if water_r is None else water_r[sl]))
+                           None if water_r is None else water_r[sl],
+                           spec_s, None if spec_r is None else spec_r[sl],
+                           modal_s, None if modal_r is None else modal_r[sl]))
     return out
 
 

@@ -651,4 +651,8 @@ def test_bundle_end_to_end(tmp_path):
     md = (root / "reports" / "tap_000" / "tap_000_report.md").read_text()
     assert "## Decay / EDC" in md and "## RT60 by band" in md and "## Waterfall" in md and "12699Hz" in md
     assert f"[left] analysis_start_sample_index={int(a['decay_start'])}" in md
-    assert "Blocks not run" in md
+    assert "Blocks not run" in md and "Spectrogram" not in md.split("Blocks not run")[1]
+    # section order of the reference's report (report.py:252-386)
+    order = [md.index(h) for h in ("## Decay / EDC", "## RT60 by band", "## Spectrogram", "## Waterfall", "## Modal cloud")]
+    assert order == sorted(order)
+    assert "stft(n_fft=4096, frames=" in md and "] metric=t30 start_sample=" in md
