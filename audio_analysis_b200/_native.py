@@ -43,6 +43,8 @@ EXPORTED_SYMBOLS = (
     "aa_bands_plan_create",
     "aa_bands_plan_destroy",
     "aa_bands_plan_kind",
+    "aa_bands_get_decimation",
+    "aa_bands_set_decimation",
     "aa_bands_workspace_bytes",
     "aa_rt60bands_batch",
     "aa_csd_batch",
@@ -135,6 +137,10 @@ def _declare(lib: C.CDLL) -> None:
     lib.aa_bands_plan_destroy.argtypes = [vp]
     lib.aa_bands_plan_kind.restype = C.c_int
     lib.aa_bands_plan_kind.argtypes = [vp]
+    lib.aa_bands_get_decimation.restype = C.c_int
+    lib.aa_bands_get_decimation.argtypes = []
+    lib.aa_bands_set_decimation.restype = None
+    lib.aa_bands_set_decimation.argtypes = [C.c_int]
     lib.aa_bands_workspace_bytes.restype = sz
     lib.aa_bands_workspace_bytes.argtypes = [vp, i32, i32]
     lib.aa_rt60bands_batch.restype = C.c_int

@@ -36,8 +36,21 @@ struct BandFitArgs {
     const float* part;        // [unit][n_groups][n_tiles]
     long long part_stride;
     int n_groups, n_tiles, tile_len, n;
+    // decimated band signals (bands.cu): y holds every decim-th sample of the band signal, starting AT the analysis
+    // start (the spectrum was time-advanced), so the curve starts at index 0, ends after ceil((full_n - start) /
+    // decim) samples (the rest is the wrapped-around head of the circular signal), and the tail sum of squares is
+    // corrected by the end-point term of the trapezoid rule: E_j = decim * (S_j - kappa y_j^2), kappa = (decim-1)/(2 decim)
+    int decim, full_n;
+    float kappa;
+    int min_fit_points;
     EdcArgs e;                // start_in / start_div / rt60_out / targets / fit ranges / eps / floor / sr / min_samples
 };
+
+// energy of sample c (0..3) of the lane's four from the in-lane suffix sums
+__device__ __forceinline__ float lane_sample_energy(const TileScan& sc, int c) {
+    return (c == 3) ? sc.s[3] : (c == 2) ? __fsub_rn(sc.s[2], sc.s[3]) : (c == 1) ? __fsub_rn(sc.s[1], sc.s[2])
+                                                                                   : __fsub_rn(sc.s[0], sc.s[1]);
+}
 
 struct FitShared {
     double warp_tot[kFitWarps];
@@ -86,13 +99,18 @@ __global__ void __launch_bounds__(kFitThreads) band_fit_kernel(BandFitArgs a) {
     const int unit = blockIdx.x;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const ScanMasks masks = make_scan_masks();
-    const int NT = a.n_tiles, TL = a.tile_len, n = a.n;
+    const int NT = a.n_tiles, TL = a.tile_len;
     double* carry = reinterpret_cast<double*>(dyn_smem);   // [NT] energy after tile k
     float* tsum = reinterpret_cast<float*>(carry + NT);    // [NT] tile energy
     const float* __restrict__ y = a.y + (long long)unit * a.y_stride;
     const float* __restrict__ part = a.part + (long long)unit * a.part_stride;
     const EdcArgs& p = a.e;
-    const int start = min(max(p.start_in[unit / p.start_div], 0), n);
+    int n = a.n, start = min(max(p.start_in[unit / p.start_div], 0), a.decim > 1 ? a.full_n : a.n);
+    if (a.decim > 1) {   // the decimated grid starts at the analysis start and stops before the signal wraps around
+        n = min(a.n, (a.full_n - start + a.decim - 1) / a.decim);
+        start = 0;
+    }
+    const double kappa = (double)a.kappa;
     const int n_an = n - start;
     const float srf = (float)p.sr;
 
@@ -109,10 +127,24 @@ __global__ void __launch_bounds__(kFitThreads) band_fit_kernel(BandFitArgs a) {
         const int k = t0 + q;
         if (k < NT) {
             float s = 0.f;
-            for (int g = 0; g < a.n_groups; ++g) s += __ldg(part + (long long)g * NT + k);
+            if ((long long)k * TL < n)
+                for (int g = 0; g < a.n_groups; ++g) s += __ldg(part + (long long)g * NT + k);
             tsum[k] = s;
-            mine += (double)s;
         }
+    }
+    __syncthreads();
+    const int k_end = (n > 0) ? (n - 1) / TL : 0;   // tile that holds the last analysed sample
+    if (warp == 0 && n % TL != 0 && k_end < NT) {   // partly analysed tile: its energy up to sample n only
+        float tot = 0.f;
+        visit_tile_reverse<NS>(y, k_end, TL, n, 0.0, lane, masks, [&](int j, const TileScan& sc, double after) {
+            tot += __shfl_sync(kFullMask, __fadd_rn(sc.excl, sc.s[0]), 0);
+        });
+        if (lane == 0) tsum[k_end] = tot;
+    }
+    __syncthreads();
+    for (int q = 0; q < per; ++q) {
+        const int k = t0 + q;
+        if (k < NT) mine += (double)tsum[k];
     }
     double inc = mine;
 #pragma unroll
@@ -146,7 +178,7 @@ __global__ void __launch_bounds__(kFitThreads) band_fit_kernel(BandFitArgs a) {
         visit_tile_reverse<NS>(y, ks, TL, n, carry[ks], lane, masks, [&](int j, const TileScan& sc, double after) {
             if (j == pj && lane == pl) {
                 const float sj = (pc == 0) ? sc.s[0] : (pc == 1) ? sc.s[1] : (pc == 2) ? sc.s[2] : sc.s[3];
-                const double e = after + (double)__fadd_rn(sc.excl, sj);
+                const double e = after + (double)__fadd_rn(sc.excl, sj) - kappa * (double)lane_sample_energy(sc, pc);
                 sh.e0 = e;
                 sh.inv_e0 = 1.0 / fmax(e, p.eps);
             }
@@ -191,12 +223,12 @@ __global__ void __launch_bounds__(kFitThreads) band_fit_kernel(BandFitArgs a) {
                     for (int c = 3; c >= 0; --c) {
                         const int off = j * kSub + 4 * lane + c;
                         const int i = k * TL + off;
-                        const double e = after + (double)__fadd_rn(sc.excl, sc.s[c]);
-                        const float d = to_db(e, p.eps, inv_e0, p.floor_db);
+                        const double eu = after + (double)__fadd_rn(sc.excl, sc.s[c]);
+                        const float d = to_db(eu - kappa * (double)lane_sample_energy(sc, c), p.eps, inv_e0, p.floor_db);
                         if (off < TL && i >= start && i < n && d <= tauf) {
                             first_c = c;
                             dbv = d;
-                            ev = e;
+                            ev = eu;
                         }
                     }
                     const unsigned m = __ballot_sync(kFullMask, first_c < 4);
@@ -208,7 +240,7 @@ __global__ void __launch_bounds__(kFitThreads) band_fit_kernel(BandFitArgs a) {
                             pidx = k * TL + j * kSub + 4 * lane + first_c;
                             // value one sample earlier: E[i-1] = E[i] + y[i-1]^2 (i > start because b_first > tau)
                             const float yp = __ldg(y + pidx - 1);
-                            py0 = to_db(ev + (double)__fmul_rn(yp, yp), p.eps, inv_e0, p.floor_db);
+                            py0 = to_db(ev + (1.0 - kappa) * (double)__fmul_rn(yp, yp), p.eps, inv_e0, p.floor_db);
                         }
                         found = 1;
                         idx = __shfl_sync(kFullMask, pidx, fl);
@@ -222,7 +254,7 @@ __global__ void __launch_bounds__(kFitThreads) band_fit_kernel(BandFitArgs a) {
                     idx = (k + 1) * TL;
                     y1 = to_db(carry[k], p.eps, inv_e0, p.floor_db);
                     const float yp = __ldg(y + idx - 1);
-                    y0 = to_db(carry[k] + (double)__fmul_rn(yp, yp), p.eps, inv_e0, p.floor_db);
+                    y0 = to_db(carry[k] + (1.0 - kappa) * (double)__fmul_rn(yp, yp), p.eps, inv_e0, p.floor_db);
                 }
             }
         }
@@ -238,7 +270,8 @@ __global__ void __launch_bounds__(kFitThreads) band_fit_kernel(BandFitArgs a) {
         const int ts_i = 2 + 2 * f, te_i = 3 + 2 * f;
         int first = 0, last = -1;
         const int valid = fit_index_range(sh.cross_ok[ts_i], sh.cross_ok[te_i], sh.cross_t[ts_i], sh.cross_t[te_i],
-                                          sh.cross_idx[ts_i] - start, sh.cross_idx[te_i] - start, srf, &first, &last);
+                                          sh.cross_idx[ts_i] - start, sh.cross_idx[te_i] - start, srf, &first, &last,
+                                          a.min_fit_points);
         sh.fit_valid[f] = valid;
         sh.fit_first[f] = start + first;
         sh.fit_last[f] = start + last;
@@ -282,7 +315,8 @@ __global__ void __launch_bounds__(kFitThreads) band_fit_kernel(BandFitArgs a) {
                 float db[4];
 #pragma unroll
                 for (int c = 0; c < 4; ++c) {
-                    const float r = (float)(fmax(after + (double)__fadd_rn(sc.excl, sc.s[c]), eps) * inv_e0);
+                    const float r = (float)(fmax(after + (double)__fadd_rn(sc.excl, sc.s[c]) -
+                                                 kappa * (double)lane_sample_energy(sc, c), eps) * inv_e0);
                     db[c] = fmaxf(db10_from_ratio_fast(r), floor_db);
                 }
                 const int in_tile = TL - (j * kSub + 4 * lane);  // samples of this lane that belong to the tile
@@ -335,7 +369,8 @@ __global__ void __launch_bounds__(kFitThreads) band_fit_kernel(BandFitArgs a) {
 
 int launch_band_fit(const float* d_y, long long y_stride, const float* d_part, long long part_stride, int n_groups,
                     int n_tiles, int tile_len, int n, long long n_units, const aa_decay_params* p,
-                    const int* d_start_idx, int start_div, int min_samples, double* d_rt60_out, cudaStream_t stream) {
+                    const int* d_start_idx, int start_div, int min_samples, double* d_rt60_out, cudaStream_t stream,
+                    int decim, int full_n) {
     AA_REQUIRE(d_y && d_part && p && d_start_idx && d_rt60_out, AA_ERR_INVALID_ARGUMENT, "null argument");
     AA_REQUIRE(tile_len % 4 == 0 && tile_len >= 4 && tile_len <= kSub * kMaxSub, AA_ERR_UNSUPPORTED,
                "tile length must be a multiple of 4 and at most 1024");
@@ -358,6 +393,15 @@ int launch_band_fit(const float* d_y, long long y_stride, const float* d_part, l
     a.e.start_div = start_div > 0 ? start_div : 1;
     a.e.rt60_out = d_rt60_out;
     a.e.min_samples = min_samples;
+    a.decim = decim > 1 ? decim : 1;
+    a.full_n = full_n;
+    a.kappa = decim > 1 ? (float)(decim - 1) / (float)(2 * decim) : 0.0f;
+    a.min_fit_points = decim > 1 ? (8 + decim - 1) / decim : 8;
+    if (decim > 1) {
+        AA_REQUIRE(p->sample_rate_hz % decim == 0, AA_ERR_INVALID_ARGUMENT, "sample rate not divisible by the decimation");
+        a.e.sr = p->sample_rate_hz / decim;
+        a.e.min_samples = (min_samples + decim - 1) / decim;
+    }
     const size_t smem = (size_t)n_tiles * (sizeof(double) + sizeof(float));
     AA_REQUIRE(smem <= 48 * 1024, AA_ERR_UNSUPPORTED, "too many tiles");
     const unsigned grid = (unsigned)n_units;

@@ -257,6 +257,8 @@ constexpr int reg_pitch(int G, int min_elems) {
     int tp = min_elems;
     if (G == 8) {
         while (tp % 8 != 6) ++tp;
+    } else if (G == 4) {
+        while (tp % 16 != 4) ++tp;
     } else {
         tp |= 1;
     }
@@ -285,6 +287,10 @@ __global__ void __launch_bounds__(P::kThreads) fft_cols_reg(SrcDesc src, float2*
         s.freq_scale = src.freq_scale;
         s.M = src.M;
         s.twN = src.twN;
+        s.shift = src.shift ? src.shift[row] : 0;
+        s.shift_N = src.shift_N;
+        s.shift_rcp = src.shift_N > 0 ? 1.0 / (double)src.shift_N : 0.0;
+        s.twShift = src.twShift;
         reg_cols_stage_a<P>((int)threadIdx.x, s, M2, col0, buf);
     } else if (kSrc == SRC_COMPLEX) {
         RegSrcComplex s{(const float2*)src.base + (size_t)unit * src.unit_stride};
@@ -306,7 +312,7 @@ __global__ void __launch_bounds__(P::kThreads) fft_rows_reg(const float2* __rest
                                                             const float2* __restrict__ tw_full, float* __restrict__ energy,
                                                             long long energy_stride) {
     static_assert(M1 % P::G == 0, "rows must split evenly over CTAs");
-    static_assert(!kEnergy || ((P::G == 8 || P::G == 16) && P::kThreadsB % 32 == 0),
+    static_assert(!kEnergy || ((P::G == 8 || P::G == 16) && P::kThreadsB % P::G == 0 && 32 % P::G == 0),
                   "energy partials reduce over aligned groups of 8 or 16 lanes");
     constexpr int groups = M1 / P::G;
     extern __shared__ float2 smem[];
@@ -319,7 +325,7 @@ __global__ void __launch_bounds__(P::kThreads) fft_rows_reg(const float2* __rest
     reg_fill_twiddles<P>((int)threadIdx.x, P::kThreads, tws, tw_full);  // after stage A's loads are in flight
     __syncthreads();
     if (kEnergy) {
-        float e[P::RB];
+        float e[P::RB] = {};
         reg_rows_stage_b<P>((int)threadIdx.x, buf, tws, out + (size_t)unit * out_stride, M1, row0, n_valid, conj, scale, e);
         // sum over the G rows of the group: g is the low 3 (4) bits of the lane index
         float* __restrict__ dst = energy + (size_t)unit * energy_stride + (size_t)rg * P::L;

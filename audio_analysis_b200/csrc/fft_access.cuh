@@ -85,6 +85,11 @@ struct SrcDesc {
     double freq_scale;      // rfftfreq: f_k = float(k * freq_scale)
     int N, M;               // real length and N/2
     TwoLevelTwiddle twN;    // exp(-2 pi i k / N)
+    // band modes, register-pass kernels only: per-row circular time advance of the band signal, y'[j] = y[j + shift]
+    // (Y_k * exp(+2 pi i k shift / shift_N)); the decimated band path aligns its grid with the analysis start
+    const int* shift;       // [rows] or NULL
+    int shift_N;            // length of the transform the spectrum came from
+    TwoLevelTwiddle twShift;  // exp(-2 pi i m / shift_N)
     // deconvolution: base = Y spectra (float2, per unit), aux = sweep spectrum X (shared)
     const float2* aux;
     const float* eps_ptr;   // device scalar: regularisation (deconvolve.py:156)

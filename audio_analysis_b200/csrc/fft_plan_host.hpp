@@ -20,7 +20,11 @@ constexpr int kTwoLevelShift = 10;
 // (fft_reg.cuh): X(RA1, RB1, G1, RA2, RB2, G2).  host_direct_plan() prefers these splits.
 #define AA_REG_LIST(X)                                        \
     X(18, 20, 8, 20, 20, 8) /* N = 288000: M = 360 x 400 (400 x 360 with rows in groups of 16 measured 10 % slower) */ \
-    X(12, 20, 8, 20, 20, 8) /* N = 192000: M = 240 x 400 */
+    X(12, 20, 8, 20, 20, 8) /* N = 192000: M = 240 x 400 */ \
+    X(18, 20, 8, 10, 20, 8) /* N = 144000 (288000 decimated by 2): M = 360 x 200 */ \
+    X(10, 20, 4, 12, 15, 8) /* N =  72000 (288000 decimated by 4): M = 200 x 180 */ \
+    X(12, 20, 8, 10, 20, 8) /* N =  96000 (192000 decimated by 2): M = 240 x 200 */ \
+    X(10, 12, 8, 10, 20, 8) /* N =  48000 (192000 decimated by 4): M = 120 x 200 */
 
 inline bool reg_split_for(int M, int* M1, int* M2) {
 #define X(ra1, rb1, g1, ra2, rb2, g2)                   \

@@ -64,6 +64,21 @@ struct RegSrcBand {
     double freq_scale;
     int M;
     TwoLevelTwiddle twN;
+    // optional circular time advance by `shift` samples of the length-shift_N signal the spectrum belongs to
+    int shift = 0;
+    int shift_N = 0;
+    double shift_rcp = 0.0;     // 1 / shift_N
+    TwoLevelTwiddle twShift{};  // exp(-2 pi i m / shift_N)
+    AA_HD float2 advance(float2 v, int k) const {
+        if (shift == 0) return v;
+        // (k * shift) mod shift_N without a 64-bit division: the float64 quotient is exact to +-1
+        const long long prod = (long long)k * (long long)shift;
+        long long q = (long long)((double)prod * shift_rcp);
+        long long r = prod - q * (long long)shift_N;
+        if (r < 0) r += shift_N;
+        if (r >= shift_N) r -= shift_N;
+        return cmulc(v, twiddle2(twShift, r));   // * exp(+2 pi i k shift / N)
+    }
     AA_HD float2 masked(int k) const {  // k inside [k_first, k_last]
 #ifdef __CUDA_ARCH__
         // device: the per-call mask table is mandatory here (bands.cu builds it); evaluating the raised cosines
@@ -72,7 +87,7 @@ struct RegSrcBand {
 #else
         const float m = b.mask ? b.mask[k - b.k_first] : band_mask_value(b, (float)((double)k * freq_scale));
 #endif
-        return cscale(load_c(X + k), m);
+        return advance(cscale(load_c(X + k), m), k);
     }
     AA_HD bool get(int idx, float2* v) const {
         const unsigned span = (unsigned)(b.k_last - b.k_first);  // k_last < k_first (empty band) wraps to "never"

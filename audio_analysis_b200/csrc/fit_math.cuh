@@ -23,7 +23,7 @@ __device__ __forceinline__ double crossing_time_rel(int i, float y0f, float y1f,
 // analyse/decay.py:224-228: mask = (time >= start_t) & (time <= end_t) on float32 values, >= 8 points.
 // is / ie are the crossing sample indices (relative) of the range start / end targets.
 __device__ __forceinline__ int fit_index_range(int ok_s, int ok_e, double ts, double te, int is, int ie, float srf,
-                                               int* first, int* last) {
+                                               int* first, int* last, int min_points = 8) {
     *first = 0;
     *last = -1;
     if (!(ok_s && ok_e && te > ts)) return 0;
@@ -34,7 +34,7 @@ __device__ __forceinline__ int fit_index_range(int ok_s, int ok_e, double ts, do
     if (!(rel_time(ie, srf) <= tef)) l = ie - 1;
     *first = f;
     *last = l;
-    return (l - f + 1 >= 8) ? 1 : 0;
+    return (l - f + 1 >= min_points) ? 1 : 0;
 }
 
 // Closed-form least squares over u = 0..n-1 (t = (first + u)/sr) from S0 = sum(yc), S1 = sum(u*yc),

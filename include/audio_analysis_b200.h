@@ -180,6 +180,15 @@ int aa_bands_plan_create(int32_t n, aa_bands_plan** out);
 void aa_bands_plan_destroy(aa_bands_plan* plan);
 /* 0 = direct mixed radix, 1 = Bluestein on n/2, 2 = Bluestein on n (odd n) */
 int aa_bands_plan_kind(const aa_bands_plan* plan);
+/*
+ * Band decimation (register-pass lengths, metrics only): a band whose mask support ends below n / (2 D) is
+ * synthesised on every D-th sample from the analysis start by a length n / D inverse transform - those ARE samples of
+ * the reference's band signal - and its Schroeder integral is taken on that grid with a trapezoid end correction.
+ * D <= max_decimation in {1 (off), 2, 4}; default 4, or the environment variable AA_BANDS_DECIMATION.
+ * Band RT60s move by <= 8e-4 relative against the full-rate path (tolerance 5e-3).
+ */
+int aa_bands_get_decimation(void);
+void aa_bands_set_decimation(int max_decimation);
 /* bytes of workspace needed to process `rows_per_chunk` rows x `n_bands` bands at once */
 size_t aa_bands_workspace_bytes(const aa_bands_plan* plan, int32_t rows_per_chunk, int32_t n_bands);
 

@@ -107,6 +107,8 @@ static constexpr int emu_reg_pitch(int G, int min_elems) {  // mirrors reg_pitch
     int tp = min_elems;
     if (G == 8) {
         while (tp % 8 != 6) ++tp;
+    } else if (G == 4) {
+        while (tp % 16 != 4) ++tp;
     } else {
         tp |= 1;
     }
@@ -134,6 +136,10 @@ static void emu_reg_unit(const HostC2C& p, const SrcDesc& src, const DstDesc& ds
                 s.freq_scale = src.freq_scale;
                 s.M = src.M;
                 s.twN = src.twN;
+                s.shift = src.shift ? src.shift[row] : 0;
+                s.shift_N = src.shift_N;
+                s.shift_rcp = src.shift_N > 0 ? 1.0 / (double)src.shift_N : 0.0;
+                s.twShift = src.twShift;
                 reg_cols_stage_a<P1>(t, s, M2, col0, buf.data());
             } else if (src.mode == SRC_REAL_PACKED) {
                 RegSrcComplex s{(const float2*)((const float*)src.base + u * src.unit_stride)};
@@ -523,6 +529,84 @@ static void check_real_band(int N, double lo0 = 890.9, double hi0 = 1122.5) {
     }
 }
 
+// ---- 2b. decimated band synthesis (bands.cu): length N / D inverse of the time-advanced masked spectrum must
+// return y[(shift + D j) mod N], every D-th sample of the full-rate band signal from the analysis start
+static void check_decimated_band(int N, int D, double lo0, double hi0, int shift) {
+    const double sr = 48000.0;
+    const double freq_scale = 1.0 / ((double)N * (1.0 / sr));
+    const int half = N / 2, Nd = N / D, Md = Nd / 2;
+    std::vector<float> x((size_t)N);
+    for (int n = 0; n < N; ++n) x[(size_t)n] = (float)(urand() * exp(-6.0 * n / N));
+    BandDev band = make_bandpass(lo0, hi0, 1.0 / 6.0, 24000.0, freq_scale, half + 1);
+    if (band.k_last >= Md - 1) {
+        printf("decimated band check: band does not fit D=%d\n", D);
+        ++failures;
+        return;
+    }
+    // double-precision masked spectrum on the band's support
+    std::vector<cd> Y;
+    std::vector<int> ks;
+    double ynorm = 0;
+    std::vector<float2> X((size_t)half + 1, make_float2(0, 0));
+    for (int k = band.k_first; k <= band.k_last; ++k) {
+        cd acc = 0;
+        for (int n = 0; n < N; ++n) {
+            double ang = -2.0 * M_PI * (double)(((long long)n * k) % N) / N;
+            acc += (double)x[(size_t)n] * cd(cos(ang), sin(ang));
+        }
+        X[(size_t)k] = make_float2((float)acc.real(), (float)acc.imag());
+        const double m = band_mask_value(band, (float)((double)k * freq_scale));
+        if (m == 0.0) continue;
+        Y.push_back(acc * m);
+        ks.push_back(k);
+        ynorm += std::norm(acc * m);
+    }
+    ynorm = sqrt(2.0 * ynorm / N);
+    EmuPlan ep;
+    if (!emu_plan(Md, &ep) || ep.top.bluestein) {
+        printf("no direct plan for %d\n", Md);
+        ++failures;
+        return;
+    }
+    HostTwoLevel twNd, twNfull;
+    host_two_level(Nd, &twNd);
+    host_two_level(N, &twNfull);
+    std::vector<float> y((size_t)Nd, 0.f);
+    SrcDesc s{};
+    s.mode = SRC_BAND_PACKED;
+    s.base = X.data();
+    s.unit_stride = half + 1;
+    s.n_valid = Md;
+    s.conj = 1;
+    s.n_bands = 1;
+    s.bands = &band;
+    s.bands_have_tables = 1;
+    s.freq_scale = freq_scale;
+    s.N = Nd;
+    s.M = Md;
+    s.twN = dev_view(twNd);
+    s.shift = &shift;
+    s.shift_N = N;
+    s.twShift = dev_view(twNfull);
+    DstDesc d = dst_complex((float2*)y.data(), Md, Md, 1, 1.0f / ((float)Md * (float)D));
+    emu_exec(ep, s, d, 1);
+    double worst = 0;
+    for (int c = 0; c < 60; ++c) {
+        const int j = (int)((urand() * 0.5 + 0.5) * (Nd - 1));
+        const long long n = ((long long)shift + (long long)D * j) % N;
+        double acc = 0;
+        for (size_t q = 0; q < ks.size(); ++q) {
+            double ang = 2.0 * M_PI * (double)((n * ks[q]) % N) / N;
+            acc += 2.0 * (Y[q] * cd(cos(ang), sin(ang))).real();
+        }
+        acc /= N;
+        worst = fmax(worst, fabs(acc - (double)y[(size_t)j]) / (ynorm / sqrt((double)N) + 1e-30));
+    }
+    char name[64];
+    snprintf(name, sizeof(name), "decimated band D=%d shift=%d (%d bins)", D, shift, (int)ks.size());
+    report(name, N, worst, 2e-4);
+}
+
 // the compile-time chains of fft.cu's AA_SPEC_LIST and csd.cu (radix 6, padded shared-memory layout)
 template <int kPad>
 static void check_chain(int L, std::vector<int> radices) {
@@ -568,12 +652,16 @@ int main() {
     check_chain<4>(4096, {8, 8, 8, 8});
     check_chain<0>(36, {6, 6});
     const int sizes[] = {1, 2, 3, 4, 5, 6, 7, 8, 11, 13, 16, 30, 64, 77, 143, 360, 1001, 2048,
-                         2304, 4096, 24000, 30000, 31200, 65536, 17, 397, 4099, 25011, 45001, 144000, 96000};
+                         2304, 4096, 24000, 30000, 31200, 65536, 17, 397, 4099, 25011, 45001, 144000, 96000, 72000, 36000, 48000, 24000};
     for (int M : sizes) check_c2c(M);
     const int real_sizes[] = {48000, 60000, 62400, 50022, 45001, 4410, 64, 1155};
     for (int N : real_sizes) check_real_band(N);
     check_real_band(288000, 111.4, 140.3);  // the register-pass splits (narrow bands keep the direct sums cheap)
     check_real_band(192000, 7127.2, 7300.0);
+    check_decimated_band(288000, 4, 111.4, 140.3, 17041);
+    check_decimated_band(288000, 2, 5610.0, 5700.0, 23456);
+    check_decimated_band(192000, 4, 222.7, 280.6, 9999);
+    check_decimated_band(192000, 2, 3500.0, 3600.0, 1);
     printf("%s (%d failures)\n", failures ? "FAILED" : "ALL OK", failures);
     return failures ? 1 : 0;
 }

@@ -32,6 +32,11 @@ def _fits_table(fits: dict) -> np.ndarray:
     return out
 
 
+def nat_lib():
+    from audio_analysis_b200 import _native as nat
+    return nat.load()
+
+
 @pytest.fixture(scope="module")
 def dec():
     from audio_analysis_b200 import decay
@@ -327,6 +332,39 @@ def test_waterfall_errors():
         wf.analyse_waterfall_for_channel(x, SR, "m", wf.WaterfallAnalysisSettings(analysis_duration_seconds=0.09))
 
 
+def test_band_decimation_against_oracle_and_switch():
+    """N = 288000 / 192000 rows: the decimated band path (default) and the full-rate path both sit inside the RT60
+    tolerance of the oracle; aa_bands_set_decimation switches between them."""
+    from audio_analysis_b200 import rt60bands as rb
+    from audio_analysis_b200.synth import synth_batch_numpy
+    lib = nat_lib()
+    try:
+        for n in (288000, 192000):
+            x = synth_batch_numpy(2, n, SR, first_index=40)
+            want = []
+            for i in range(2):
+                ob = oracle.band_metrics(x[i], SR, oracle.BandParams(band_mode="third", include_t20=True))
+                want.append(np.array([[np.nan if v is None else v for v in ob["metrics"][b["name"]]] for b in ob["bands"]]))
+            s = rb.Rt60BandsAnalysisSettings(band_mode="third", include_t20=True)
+            got = {}
+            for max_d in (4, 2, 1):
+                lib.aa_bands_set_decimation(max_d)
+                assert lib.aa_bands_get_decimation() == max_d
+                res = rb.analyse_rt60_bands_batch(x, SR, ["a", "b"], s)
+                tab = np.array([[[np.nan if v is None else v for v in
+                                  (r.band_metrics_by_name[b.name].rt60_t30_seconds,
+                                   r.band_metrics_by_name[b.name].rt60_t20_seconds,
+                                   r.band_metrics_by_name[b.name].edt_seconds)] for b in r.band_definitions] for r in res])
+                got[max_d] = tab
+                for i in range(2):
+                    check_band_table(f"decim{max_d}/n{n}", tab[i][:, :2], want[i][:, :2])
+                    err = np.nanmax(np.abs(tab[i][:, :2] - want[i][:, :2]) / want[i][:, :2])
+                    note(f"band_rt60_rel_err[decimation<={max_d}]", err)
+            assert not np.array_equal(got[4], got[1])     # the switch really changes the path
+    finally:
+        lib.aa_bands_set_decimation(4)
+
+
 # ------------------------------------------------------------------------------------ spectrogram (SURVEY 8f N2)
 
 
@@ -494,8 +532,18 @@ def test_full_size_properties_config5_rows():
     total = sig.sum(dim=1)
     assert float((total ** 2).sum()) <= 1.6 * float((x[:2] ** 2).sum())
     # 7. shard invariance (what the multi-GPU path relies on): analysing a sub-batch gives the same table
+    whole = rb.run_rt60_bands(engine.make_rows(x[:3]), SR, rb.Rt60BandsAnalysisSettings(band_mode="third"))[0]
     sub = rb.run_rt60_bands(engine.make_rows(x[1:2]), SR, rb.Rt60BandsAnalysisSettings(band_mode="third"))[0]
-    assert torch.equal(torch.nan_to_num(sub[0]), torch.nan_to_num(metrics[1]))
+    assert torch.equal(torch.nan_to_num(sub[0]), torch.nan_to_num(whole[1]))
+    # 8. band decimation (default) against the full-rate synthesis (what `want_band_signals` forces): the decimated
+    #    grid holds exact samples of the same band signals, only the Schroeder sum is taken on fewer points
+    assert nat_lib().aa_bands_get_decimation() == 4
+    full = metrics.cpu().numpy()[:2, :, 0]
+    dec = whole.cpu().numpy()[:2, :, 0]
+    assert np.array_equal(np.isnan(full), np.isnan(dec))
+    rel = np.nanmax(np.abs(dec - full) / full)
+    note("band_rt60_decimated_vs_full_rel", rel)
+    assert rel <= 2e-3
 
 
 def test_host_streaming_pipeline_equals_resident_batch():

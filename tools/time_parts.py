@@ -8,7 +8,7 @@ sys.path.insert(0, str(Path(__file__).resolve().parent.parent))
 
 import torch  # noqa: E402
 
-from audio_analysis_b200 import decay, engine, rt60bands, waterfall  # noqa: E402
+from audio_analysis_b200 import decay, engine, modalcloud, rt60bands, spectrogram, waterfall  # noqa: E402
 from audio_analysis_b200.synth import synth_batch_torch  # noqa: E402
 
 ap = argparse.ArgumentParser()
@@ -46,3 +46,12 @@ t = timed(lambda: rt60bands.run_rt60_bands(rows, 48000, bs, start_idx=start), a.
 print(f"rt60 third  {t:9.3f} ms  {t * 1e3 / a.rows:8.2f} us/row  {t * 1e3 / a.rows / 26:6.3f} us/band-unit")
 t = timed(lambda: waterfall.run_waterfall(rows, 48000, ws, peaks=start, validate=False), a.reps * 3)
 print(f"csd         {t:9.3f} ms  {t * 1e3 / a.rows:8.2f} us/row  {a.rows * 418e3 / t / 1e6:8.1f} GB/s (418 KB/row)")
+if a.rows <= 256:
+    ss = spectrogram.SpectrogramAnalysisSettings()
+    t = timed(lambda: spectrogram.run_spectrogram(rows, 48000, ss, peaks=start), a.reps)
+    frames = 1 + (a.samples - 16000 - 4096) // 512
+    print(f"spectrogram {t:9.3f} ms  {t * 1e3 / a.rows:8.2f} us/row  {a.rows * (a.samples * 4 + frames * 2049 * 4) / t / 1e6:8.1f} GB/s "
+          f"(x in + ~{frames} x 2049 dB out)")
+    ms = modalcloud.ModalCloudAnalysisSettings()
+    t = timed(lambda: modalcloud.run_modal_cloud(rows, 48000, ms, peaks=start), a.reps)
+    print(f"modal cloud {t:9.3f} ms  {t * 1e3 / a.rows:8.2f} us/row  (n_fft 8192 STFT + 240 log bins x fits)")
