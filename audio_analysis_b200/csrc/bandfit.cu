@@ -40,7 +40,7 @@ struct BandFitArgs {
     // start (the spectrum was time-advanced), so the curve starts at index 0, ends after ceil((full_n - start) /
     // decim) samples (the rest is the wrapped-around head of the circular signal), and the tail sum of squares is
     // corrected by the end-point term of the trapezoid rule: E_j = decim * (S_j - kappa y_j^2), kappa = (decim-1)/(2 decim)
-    int decim, full_n;
+    int decim, full_n, aligned;
     float kappa;
     int min_fit_points;
     EdcArgs e;                // start_in / start_div / rt60_out / targets / fit ranges / eps / floor / sr / min_samples
@@ -105,8 +105,8 @@ __global__ void __launch_bounds__(kFitThreads) band_fit_kernel(BandFitArgs a) {
     const float* __restrict__ y = a.y + (long long)unit * a.y_stride;
     const float* __restrict__ part = a.part + (long long)unit * a.part_stride;
     const EdcArgs& p = a.e;
-    int n = a.n, start = min(max(p.start_in[unit / p.start_div], 0), a.decim > 1 ? a.full_n : a.n);
-    if (a.decim > 1) {   // the decimated grid starts at the analysis start and stops before the signal wraps around
+    int n = a.n, start = min(max(p.start_in[unit / p.start_div], 0), a.aligned ? a.full_n : a.n);
+    if (a.aligned) {   // the (decimated) grid starts at the analysis start and stops before the signal wraps around
         n = min(a.n, (a.full_n - start + a.decim - 1) / a.decim);
         start = 0;
     }
@@ -370,7 +370,7 @@ __global__ void __launch_bounds__(kFitThreads) band_fit_kernel(BandFitArgs a) {
 int launch_band_fit(const float* d_y, long long y_stride, const float* d_part, long long part_stride, int n_groups,
                     int n_tiles, int tile_len, int n, long long n_units, const aa_decay_params* p,
                     const int* d_start_idx, int start_div, int min_samples, double* d_rt60_out, cudaStream_t stream,
-                    int decim, int full_n) {
+                    int decim, int full_n, int aligned) {
     AA_REQUIRE(d_y && d_part && p && d_start_idx && d_rt60_out, AA_ERR_INVALID_ARGUMENT, "null argument");
     AA_REQUIRE(tile_len % 4 == 0 && tile_len >= 4 && tile_len <= kSub * kMaxSub, AA_ERR_UNSUPPORTED,
                "tile length must be a multiple of 4 and at most 1024");
@@ -395,6 +395,7 @@ int launch_band_fit(const float* d_y, long long y_stride, const float* d_part, l
     a.e.min_samples = min_samples;
     a.decim = decim > 1 ? decim : 1;
     a.full_n = full_n;
+    a.aligned = (aligned || decim > 1) ? 1 : 0;
     a.kappa = decim > 1 ? (float)(decim - 1) / (float)(2 * decim) : 0.0f;
     a.min_fit_points = decim > 1 ? (8 + decim - 1) / decim : 8;
     if (decim > 1) {

@@ -55,14 +55,28 @@ constexpr size_t kAlign = 256;
 inline size_t align_up(size_t v) { return (v + kAlign - 1) / kAlign * kAlign; }
 
 __global__ void untangle_kernel(const float2* __restrict__ Z, float2* __restrict__ X, int M, int x_stride,
-                                TwoLevelTwiddle twN) {
+                                TwoLevelTwiddle twN, const int* __restrict__ advance) {
+    // advance != NULL: the half spectrum is stored time-advanced by advance[row] samples,
+    // X'[k] = X[k] exp(+2 pi i k s / N), i.e. the row circularly rotated so that its analysis start sits at
+    // sample 0 - every band signal synthesised from it starts at the analysis start (decimation classes)
     const long long row = blockIdx.y;
     const float2* __restrict__ z = Z + row * (long long)M;
     float2* __restrict__ o = X + row * (long long)x_stride;
+    const int s = advance ? advance[row] : 0;
+    const long long N = 2LL * M;
+    const double rcpN = 1.0 / (double)N;
     for (int k = blockIdx.x * blockDim.x + threadIdx.x; k <= M; k += gridDim.x * blockDim.x) {
         const int km = (k == M) ? 0 : k;
         const int mk = (k == 0) ? 0 : M - k;
-        o[k] = untangle_half_spectrum(__ldg(z + km), __ldg(z + mk), twiddle2(twN, k));
+        float2 v = untangle_half_spectrum(__ldg(z + km), __ldg(z + mk), twiddle2(twN, k));
+        if (s != 0) {
+            const long long prod = (long long)k * (long long)s;
+            long long r = prod - (long long)((double)prod * rcpN) * N;
+            if (r < 0) r += N;
+            if (r >= N) r -= N;
+            v = cmulc(v, twiddle2(twN, r));
+        }
+        o[k] = v;
     }
 }
 
@@ -402,7 +416,8 @@ int rt60bands_batch(const aa_bands_plan* plan, const float* d_x, long long row_s
             if (rc != AA_OK) return rc;
             dim3 grid((unsigned)((M + 1 + 255) / 256 > 1024 ? 1024 : (M + 1 + 255) / 256), (unsigned)rows);
             ProfScope prof("untangle", stream);
-            untangle_kernel<<<grid, 256, 0, stream>>>(d_Z, d_X, M, plan->x_stride, plan->twN.dev);
+            untangle_kernel<<<grid, 256, 0, stream>>>(d_Z, d_X, M, plan->x_stride, plan->twN.dev,
+                                                      one_class ? nullptr : d_start_idx + r0);
             rc = launch_check("untangle_kernel");
             if (rc != AA_OK) return rc;
         } else {
@@ -439,11 +454,7 @@ int rt60bands_batch(const aa_bands_plan* plan, const float* d_x, long long row_s
                 s.N = n_c;
                 s.M = M_c;
                 s.twN = bc.sub ? bc.sub->twN.dev : plan->twN.dev;
-                if (D > 1) {   // y'[j] = y[start + D j]: advance the spectrum by the row's analysis start
-                    s.shift = d_start_idx + r0;
-                    s.shift_N = N;
-                    s.twShift = plan->twN.dev;
-                }
+                // the spectra of this path are stored time-advanced (untangle_kernel): y[j] = band signal at start + D j
                 int tile_c = 0, n_tiles = 0, n_groups = 0;
                 AA_REQUIRE(c2c_energy_layout(c2c, &tile_c, &n_tiles, &n_groups), AA_ERR_UNSUPPORTED,
                            "decimated plan without tile energies");
@@ -457,7 +468,8 @@ int rt60bands_batch(const aa_bands_plan* plan, const float* d_x, long long row_s
                 {
                     ProfScope prof("band_fit", stream);
                     rc = launch_band_fit(d_y, ystride_c, d_part, (long long)n_tiles * n_groups, n_groups, n_tiles,
-                                         2 * tile_c, n_c, units_c, &pk, d_start_idx + r0, nbc, 8, d_tmp_metrics, stream, D, N);
+                                         2 * tile_c, n_c, units_c, &pk, d_start_idx + r0, nbc, 8, d_tmp_metrics, stream, D, N,
+                                         1);
                     if (rc != AA_OK) return rc;
                 }
                 const long long total = units_c * AA_MAX_FITS;

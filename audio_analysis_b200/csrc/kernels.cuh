@@ -43,7 +43,7 @@ namespace aa {
 int launch_band_fit(const float* d_y, long long y_stride, const float* d_part, long long part_stride, int n_groups,
                     int n_tiles, int tile_len, int n, long long n_units, const aa_decay_params* p,
                     const int* d_start_idx, int start_div, int min_samples, double* d_rt60_out, cudaStream_t stream,
-                    int decim = 1, int full_n = 0);
+                    int decim = 1, int full_n = 0, int aligned = 0);
 
 }  // namespace aa
 
