@@ -12,6 +12,7 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <algorithm>
 #include <vector>
 
 #include "fft.cuh"
@@ -212,28 +213,41 @@ struct Layout {
         total;
 };
 
-Layout make_layout(const aa_bands_plan* p, long long rows, int nb, bool smoothing = false) {
+// Largest per-row footprint over the decimation classes of a call (elements per row): the buffers are shared by
+// the classes, which run one after the other, so decimated calls fit several times more rows per chunk.
+struct ClassFootprint {
+    size_t y_floats = 0, scratch_c = 0, part_floats = 0;
+};
+
+Layout make_layout(const aa_bands_plan* p, long long rows, int nb, bool smoothing = false,
+                   const ClassFootprint* fp = nullptr) {
     Layout l{};
     const long long units = rows * nb;
     size_t o = 0;
     l.off_bands = o;  // the call's band table, then one re-ordered copy per decimation class
     o += align_up(sizeof(BandDev) * AA_MAX_BANDS * 2);
+    l.off_mask = o;  // mask tables: at most one value per rfft bin per band (offsets up to here do not depend on rows)
+    o += align_up(sizeof(float) * (size_t)nb * (size_t)(p->n / 2 + 1));
     l.off_tmp_metrics = o;  // per-class RT60 tables before they are scattered into the caller's band order
     o += align_up(sizeof(double) * (size_t)units * AA_MAX_FITS);
-    l.off_mask = o;  // mask tables: at most one value per rfft bin per band
-    o += align_up(sizeof(float) * (size_t)nb * (size_t)(p->n / 2 + 1));
     l.off_X = o;
     o += align_up(sizeof(float2) * (size_t)rows * (size_t)p->x_stride);
     l.off_y = o;  // also the forward transform's packed output Z (rows * M float2 <= units * y_stride floats)
-    size_t ybytes = sizeof(float) * (size_t)units * (size_t)p->y_stride;
+    size_t ybytes = sizeof(float) * (fp ? (size_t)rows * fp->y_floats : (size_t)units * (size_t)p->y_stride);
     size_t zbytes = sizeof(float2) * (size_t)rows * (size_t)p->M;
     o += align_up(ybytes > zbytes ? ybytes : zbytes);
     l.off_scratch = o;
-    o += align_up(sizeof(float2) * c2c_scratch_elems(p->c2c, units));
+    {   // the forward transform of the rows needs rows * M, the masked inverses units * M (or the class maximum)
+        size_t inv = fp ? (size_t)rows * fp->scratch_c : c2c_scratch_elems(p->c2c, units);
+        size_t fwd = c2c_scratch_elems(p->c2c, rows);
+        o += align_up(sizeof(float2) * (inv > fwd ? inv : fwd));
+    }
     {  // per-tile energy partials of the band signals (register-pass lengths; bandfit.cu)
         int tile_c = 0, n_tiles = 0, n_groups = 0;
         l.off_part = o;
-        if (c2c_energy_layout(p->c2c, &tile_c, &n_tiles, &n_groups))
+        if (fp)
+            o += align_up(sizeof(float) * (size_t)rows * fp->part_floats);
+        else if (c2c_energy_layout(p->c2c, &tile_c, &n_tiles, &n_groups))
             o += align_up(sizeof(float) * (size_t)units * (size_t)n_tiles * (size_t)n_groups);
     }
     if (smoothing) {  // dB curves of the band signals, before and after the box filter (decay.py:161-164)
@@ -334,28 +348,13 @@ int rt60bands_batch(const aa_bands_plan* plan, const float* d_x, long long row_s
     const bool smoothing = p->smoothing_window > 1;
     aa_decay_params pk = *p;  // kernel-level parameters: smoothing is applied here, not in the fused kernel
     pk.smoothing_window = 0;
-    // rows per chunk that fit the workspace
-    long long rc_rows = 0;
-    {
-        long long lo = 0, hi = n_rows;
-        while (lo < hi) {
-            long long mid = (lo + hi + 1) / 2;
-            if (make_layout(plan, mid, nb, smoothing).total <= ws_bytes) lo = mid; else hi = mid - 1;
-        }
-        rc_rows = lo;
-    }
-    AA_REQUIRE(rc_rows >= 1, AA_ERR_WORKSPACE, "workspace too small for one row (see aa_bands_workspace_bytes)");
-    const Layout lay = make_layout(plan, rc_rows, nb, smoothing);
     unsigned char* ws = static_cast<unsigned char*>(d_ws);
-    BandDev* d_bands = reinterpret_cast<BandDev*>(ws + lay.off_bands);
-    float2* d_X = reinterpret_cast<float2*>(ws + lay.off_X);
-    float* d_y = reinterpret_cast<float*>(ws + lay.off_y);
-    float2* d_Z = reinterpret_cast<float2*>(ws + lay.off_y);
-    float2* d_scr = reinterpret_cast<float2*>(ws + lay.off_scratch);
-
+    const Layout fixed = make_layout(plan, 1, nb, smoothing);   // band table and mask tables sit at row-independent offsets
+    AA_REQUIRE(fixed.total <= ws_bytes, AA_ERR_WORKSPACE, "workspace too small for one row (see aa_bands_workspace_bytes)");
+    BandDev* d_bands = reinterpret_cast<BandDev*>(ws + fixed.off_bands);
     std::vector<BandDev> hb;
     {
-        int rc = upload_bands(bands, nb, tw_oct, nyq, freq_scale, N, d_bands, reinterpret_cast<float*>(ws + lay.off_mask),
+        int rc = upload_bands(bands, nb, tw_oct, nyq, freq_scale, N, d_bands, reinterpret_cast<float*>(ws + fixed.off_mask),
                               stream, &hb);
         if (rc != AA_OK) return rc;
     }
@@ -397,6 +396,35 @@ int rt60bands_batch(const aa_bands_plan* plan, const float* d_x, long long row_s
             if (!c->bands.empty()) classes.push_back(*c);
     }
     const bool one_class = classes.size() == 1 && classes[0].D == 1;
+    // rows per chunk that fit the workspace; the classes share the signal / scratch / partial buffers
+    ClassFootprint fp;
+    if (!one_class) {
+        for (const BandClass& bc : classes) {
+            const C2CPlan* c2c = bc.sub ? bc.sub->c2c : plan->c2c;
+            int tile_c = 0, n_tiles = 0, n_groups = 0;
+            c2c_energy_layout(c2c, &tile_c, &n_tiles, &n_groups);
+            const size_t nbc = bc.bands.size();
+            fp.y_floats = std::max(fp.y_floats, nbc * (size_t)(bc.sub ? bc.sub->y_stride : plan->y_stride));
+            fp.scratch_c = std::max(fp.scratch_c, nbc * (size_t)(bc.sub ? bc.sub->M : M));
+            fp.part_floats = std::max(fp.part_floats, nbc * (size_t)n_tiles * (size_t)n_groups);
+        }
+    }
+    const ClassFootprint* fpp = one_class ? nullptr : &fp;
+    long long rc_rows = 0;
+    {
+        long long lo = 0, hi = n_rows;
+        while (lo < hi) {
+            long long mid = (lo + hi + 1) / 2;
+            if (make_layout(plan, mid, nb, smoothing, fpp).total <= ws_bytes) lo = mid; else hi = mid - 1;
+        }
+        rc_rows = lo;
+    }
+    AA_REQUIRE(rc_rows >= 1, AA_ERR_WORKSPACE, "workspace too small for one row (see aa_bands_workspace_bytes)");
+    const Layout lay = make_layout(plan, rc_rows, nb, smoothing, fpp);
+    float2* d_X = reinterpret_cast<float2*>(ws + lay.off_X);
+    float* d_y = reinterpret_cast<float*>(ws + lay.off_y);
+    float2* d_Z = reinterpret_cast<float2*>(ws + lay.off_y);
+    float2* d_scr = reinterpret_cast<float2*>(ws + lay.off_scratch);
     BandDev* d_class_bands = d_bands + AA_MAX_BANDS;
     double* d_tmp_metrics = reinterpret_cast<double*>(ws + lay.off_tmp_metrics);
 
