@@ -65,19 +65,18 @@ __global__ void untangle_kernel(const float2* __restrict__ Z, float2* __restrict
     float2* __restrict__ o = X + row * (long long)x_stride;
     const int s = advance ? advance[row] : 0;
     const long long N = 2LL * M;
-    const double rcpN = 1.0 / (double)N;
-    for (int k = blockIdx.x * blockDim.x + threadIdx.x; k <= M; k += gridDim.x * blockDim.x) {
+    // (k s) mod N advances by a constant per grid stride: one 64-bit reduction per thread, adds afterwards
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    long long r = ((long long)(blockIdx.x * blockDim.x + threadIdx.x) * (long long)s) % N;
+    const long long dr = (stride * (long long)s) % N;
+    for (int k = blockIdx.x * blockDim.x + threadIdx.x; k <= M; k += (int)stride) {
         const int km = (k == M) ? 0 : k;
         const int mk = (k == 0) ? 0 : M - k;
         float2 v = untangle_half_spectrum(__ldg(z + km), __ldg(z + mk), twiddle2(twN, k));
-        if (s != 0) {
-            const long long prod = (long long)k * (long long)s;
-            long long r = prod - (long long)((double)prod * rcpN) * N;
-            if (r < 0) r += N;
-            if (r >= N) r -= N;
-            v = cmulc(v, twiddle2(twN, r));
-        }
+        if (s != 0) v = cmulc(v, twiddle2(twN, r));
         o[k] = v;
+        r += dr;
+        if (r >= N) r -= N;
     }
 }
 
@@ -442,7 +441,7 @@ int rt60bands_batch(const aa_bands_plan* plan, const float* d_x, long long row_s
             s.n_valid = N;
             rc = c2c_exec(plan->c2c, s, make_dst_complex(d_Z, M, M, 0, 1.0f), rows, d_scr, stream);
             if (rc != AA_OK) return rc;
-            dim3 grid((unsigned)((M + 1 + 255) / 256 > 1024 ? 1024 : (M + 1 + 255) / 256), (unsigned)rows);
+            dim3 grid((unsigned)((M + 1 + 255) / 256 > 72 ? 72 : (M + 1 + 255) / 256), (unsigned)rows);  // ~8 bins per thread: amortises the index set-up
             ProfScope prof("untangle", stream);
             untangle_kernel<<<grid, 256, 0, stream>>>(d_Z, d_X, M, plan->x_stride, plan->twN.dev,
                                                       one_class ? nullptr : d_start_idx + r0);

@@ -163,6 +163,35 @@ def band_triples(bands: Sequence[BandDefinition]):
     return out
 
 
+def decimation_classes(bands: Sequence[BandDefinition], n: int, sample_rate_hz: int, transition_width_octaves: float,
+                       max_decimation: int = 4) -> List[int]:
+    """Decimation factor the device path uses for each band of an even-length-`n` row (1 = full rate).
+
+    Host mirror of the classification in csrc/bands.cu (for byte accounting and documentation): a band whose
+    raised-cosine mask ends below bin n / (2 D) - 1 is synthesised on every D-th sample.  Only the register-pass
+    lengths (n = 288000, 192000) have decimated plans; other lengths stay at full rate.
+    """
+    if n not in (288000, 192000) or n % 2:
+        return [1] * len(bands)
+    nyq = 0.5 * float(sample_rate_hz)
+    scale = float(sample_rate_hz) / float(n)
+    fac = 2.0 ** float(transition_width_octaves)
+    out = []
+    for b in bands:
+        d_band = 1
+        if b.kind != "highpass":
+            hi = float(np.clip(b.high_edge_hz, 1.0, nyq))
+            stop = min(nyq, hi * fac)
+            if stop <= hi:
+                stop = min(nyq, hi + 1.0)
+            k_last = min(n // 2, int(np.ceil(stop / scale)) + 1)
+            for d in (2, 4):
+                if d <= max_decimation and sample_rate_hz % d == 0 and n % (2 * d) == 0 and k_last < n // (2 * d) - 1:
+                    d_band = d
+        out.append(d_band)
+    return out
+
+
 def run_rt60_bands(rows: engine.Rows, sample_rate_hz: int, settings: Rt60BandsAnalysisSettings,
                    start_idx=None, bands: Optional[Sequence[BandDefinition]] = None, want_band_signals: bool = False):
     """Device-level call: returns (metrics tensor [B, nb, 3], bands, plan, start_idx, band signals or None)."""

@@ -230,6 +230,10 @@ def run_ours(args):
     n_bins = int(out.csd.shape[2])
     n_bands = int(out.band_metrics.shape[1])
     units = rows_n * n_bands
+    # samples synthesised per row over all bands: bands with a low mask are built on every 2nd / 4th sample
+    dec = rt60bands.decimation_classes(out.bands, n, SR, bs.transition_width_octaves, int(lib.aa_bands_get_decimation()))
+    band_samples = float(sum(n // d for d in dec))          # per row, all bands
+    band_units_total = rows_n * band_samples                # replaces units * n below
     stage_bytes = {
         # read x + write edc_db (8 B/sample)
         "edc": (8.0 * rows_n * n, "hbm", "edc_kernel<true>: fused EDC + crossings + fits (aa_decay_batch)"),
@@ -238,12 +242,12 @@ def run_ours(args):
         "fft_rows": (8.0 * rows_n * n, "hbm", "fft_rows_reg: second pass of the forward real FFT"),
         "untangle": (8.0 * rows_n * n, "hbm", "untangle_kernel: packed spectrum -> half spectrum"),
         # per (row, band) unit: the masked spectrum is generated on the fly, the pass writes N/2 complex values
-        "fft_cols_band": (4.0 * units * n, "fp32 issue (band source + butterflies); writes 4 B/sample/band",
+        "fft_cols_band": (4.0 * band_units_total, "fp32 issue (band source + butterflies); writes 4 B per synthesised sample",
                           "fft_cols_reg<band>: first pass of the masked inverse FFT"),
         # per unit: reads N/2 complex, writes N real samples + the energy partials
-        "fft_rows_band": (8.0 * units * n + 4.0 * units * (n // 16), "hbm",
+        "fft_rows_band": (8.0 * band_units_total + 4.0 * band_units_total / 16.0, "hbm",
                           "fft_rows_reg<energy>: second pass of the masked inverse FFT + tile energies"),
-        "band_fit": (4.0 * units * (n // 16), "latency (reads the partials and ~10% of the band signal)",
+        "band_fit": (4.0 * band_units_total / 16.0, "latency (reads the partials and ~10% of the band signal)",
                      "band_fit_kernel: band EDC suffix scan + crossings + fits"),
         "band_edc": (4.0 * units * n, "hbm", "edc_kernel<false> on band signals (generic lengths)"),
         "csd": (rows_n * (18 * 4096 * 4.0 + 18 * n_bins * 4.0), "hbm",
@@ -367,6 +371,8 @@ def run_ours(args):
             "config": {"workload": f"config5 shard: {rows_n} x {n / SR:.0f} s @48 kHz mono IRs per GPU "
                                    f"(third-octave RT60 + broadband EDC/EDT/T20/T30 + CSD 18x{n_bins})",
                        "rows_per_gpu": rows_n, "samples_per_row": n, "bands": 26,
+                       "band_decimation": {"max": int(lib.aa_bands_get_decimation()),
+                                           "bands_per_factor": {str(d): dec.count(d) for d in sorted(set(dec))}},
                        "l2": "inputs (rows*samples*4 B per GPU) are larger than L2; no flush needed"},
             "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
             "roofline": roofline, "roofline_by_kernel": by_kernel, "cpu_baseline": cpu,
