@@ -16,6 +16,7 @@
 #include <vector>
 
 #include "fft.cuh"
+#include "fft_plan_host.hpp"
 #include "kernels.cuh"
 
 struct aa_bands_plan {
@@ -33,22 +34,27 @@ struct aa_bands_plan {
         aa::C2CPlan* c2c = nullptr;
         aa::TwoLevelTable twN;
     };
-    Decim dec[2];   // D = 2, 4
+    static constexpr int kDecims = 5;
+    Decim dec[kDecims];   // D = kDecimList[i]
 };
 
 namespace aa {
 
-// largest decimation the band stage may use (1 = off); AA_BANDS_DECIMATION overrides the default of 4
+// largest decimation the band stage may use (1 = off); AA_BANDS_DECIMATION overrides the default
+constexpr int kDefaultBandDecimation = 16;
+constexpr int kDecimList[aa_bands_plan::kDecims] = {2, 3, 4, 8, 16};
+// largest mask value a bin may have and still be left out when a band's support pokes past its Nyquist zone
+constexpr float kZoneDropMask = 0.02f;
 static int g_band_decimation = -1;
+static int clamp_band_decimation(int v) { return v < 1 ? 1 : (v > 16 ? 16 : v); }
 int band_decimation_limit() {
     if (g_band_decimation < 0) {
         const char* env = getenv("AA_BANDS_DECIMATION");
-        int v = env ? atoi(env) : 4;
-        g_band_decimation = (v >= 4) ? 4 : (v >= 2 ? 2 : 1);
+        g_band_decimation = clamp_band_decimation(env ? atoi(env) : kDefaultBandDecimation);
     }
     return g_band_decimation;
 }
-void set_band_decimation_limit(int max_d) { g_band_decimation = (max_d >= 4) ? 4 : (max_d >= 2 ? 2 : 1); }
+void set_band_decimation_limit(int max_d) { g_band_decimation = clamp_band_decimation(max_d); }
 
 namespace {
 
@@ -261,6 +267,73 @@ Layout make_layout(const aa_bands_plan* p, long long rows, int nb, bool smoothin
     return l;
 }
 
+// ---- decimation classes (register-pass lengths, metrics only).  The samples y[start + D j] of a band signal are
+// the length n / D inverse transform of the band's spectrum folded into [0, n / 2D] (every bin k lands on k mod n/D).
+// A band whose support [k_first, k_last] lies inside ONE Nyquist zone [m n/2D, (m+1) n/2D] of the decimated rate folds
+// without overlap (zone 0 is plain low-pass decimation; odd zones arrive mirrored and conjugated), so those samples
+// ARE samples of the reference's band signal, and the Schroeder integral is taken on that grid with the trapezoid
+// end correction (bandfit.cu).  A support that pokes past the zone edge only with mask values <= kZoneDropMask
+// (the far end of a raised-cosine skirt) is cut at the edge.  Measured effect on the band RT60s: <= 8e-4 relative
+// (tests/test_gpu_parity.py, tools/decimation_error.py), against a tolerance of 5e-3.
+struct BandClass {
+    int D = 1;
+    const aa_bands_plan::Decim* sub = nullptr;
+    std::vector<BandDev> bands;
+    BandMapArg map{};
+};
+
+// zone placement of band b for a decimated transform of complex length Mc; on success *out is the band as the
+// decimated transform sees it (support cut to the zone, z_off / z_neg set)
+bool place_in_zone(const BandDev& b, int Mc, double freq_scale, BandDev* out) {
+    if (b.k_last < b.k_first) return false;
+    const int m = ((b.k_first + b.k_last) / 2) / Mc;
+    const int lo = (m == 0) ? 0 : m * Mc + 1, hi = (m + 1) * Mc - 2;   // bins 0 and Mc of the decimated transform stay real
+    BandDev o = b;
+    if (b.k_first < lo) {
+        if (band_mask_value(b, (float)((double)(lo - 1) * freq_scale)) > kZoneDropMask) return false;
+        o.k_first = lo;
+        if (o.mask) o.mask += lo - b.k_first;
+    }
+    if (b.k_last > hi) {
+        if (band_mask_value(b, (float)((double)(hi + 1) * freq_scale)) > kZoneDropMask) return false;
+        o.k_last = hi;
+    }
+    if (o.k_last < o.k_first) return false;
+    o.z_neg = m & 1;
+    o.z_off = (m & 1) ? (m + 1) * Mc : m * Mc;
+    *out = o;
+    return true;
+}
+
+void classify_bands(const aa_bands_plan* plan, const std::vector<BandDev>& hb, int sample_rate_hz, double freq_scale,
+                    bool metrics_only, std::vector<BandClass>* classes) {
+    int tile_c = 0, n_tiles = 0, n_groups = 0;
+    const int max_d = band_decimation_limit();
+    const bool can = (plan->n % 2) == 0 && metrics_only && c2c_energy_layout(plan->c2c, &tile_c, &n_tiles, &n_groups);
+    BandClass by_d[aa_bands_plan::kDecims + 1];   // [0] full rate, [1 + c] plan->dec[c]
+    for (size_t i = 0; i < hb.size(); ++i) {
+        BandClass* target = &by_d[0];
+        BandDev placed = hb[i];
+        if (can) {
+            for (int c = 0; c < aa_bands_plan::kDecims; ++c) {   // increasing D: the last fit wins
+                const aa_bands_plan::Decim& d = plan->dec[c];
+                BandDev z;
+                if (d.c2c && d.D <= max_d && sample_rate_hz % d.D == 0 && place_in_zone(hb[i], d.M, freq_scale, &z)) {
+                    target = &by_d[1 + c];
+                    target->D = d.D;
+                    target->sub = &d;
+                    placed = z;
+                }
+            }
+        }
+        target->map.map[target->bands.size()] = (int)i;
+        target->bands.push_back(placed);
+    }
+    classes->clear();
+    for (const BandClass& c : by_d)
+        if (!c.bands.empty()) classes->push_back(c);
+}
+
 }  // namespace
 
 int bands_plan_create(int n, aa_bands_plan** out) {
@@ -284,9 +357,9 @@ int bands_plan_create(int n, aa_bands_plan** out) {
     p->kind = even ? (p->c2c->bluestein ? 1 : 0) : 2;
     {
         int tc, nt, ng;
-        if (p->kind == 0 && c2c_energy_layout(p->c2c, &tc, &nt, &ng)) {
-            for (int i = 0; i < 2; ++i) {
-                const int D = 2 << i;
+        if (p->kind == 0 && band_decimation_parent(n) && c2c_energy_layout(p->c2c, &tc, &nt, &ng)) {
+            for (int i = 0; i < aa_bands_plan::kDecims; ++i) {
+                const int D = kDecimList[i];
                 if (n % (2 * D) != 0) continue;
                 aa_bands_plan::Decim& d = p->dec[i];
                 C2CPlan* sub = nullptr;
@@ -318,6 +391,26 @@ void bands_plan_destroy(aa_bands_plan* p) {
         free_two_level(&d.twN);
     }
     delete p;
+}
+
+// decimation factor the band stage uses for each band of a metrics-only call (host only; no device work)
+int bands_classify(const aa_bands_plan* plan, const aa_band* bands, int nb, double tw_oct, int sample_rate_hz,
+                   int* out_decimation) {
+    AA_REQUIRE(plan && bands && out_decimation, AA_ERR_INVALID_ARGUMENT, "null argument");
+    AA_REQUIRE(nb >= 1 && nb <= AA_MAX_BANDS, AA_ERR_INVALID_ARGUMENT, "band count out of range");
+    AA_REQUIRE(sample_rate_hz > 0, AA_ERR_INVALID_ARGUMENT, "sample rate must be positive");
+    const double sr = (double)sample_rate_hz;
+    const double freq_scale = 1.0 / ((double)plan->n * (1.0 / sr));
+    std::vector<BandDev> hb((size_t)nb);
+    for (int i = 0; i < nb; ++i) {
+        int rc = make_band_dev(bands[i], tw_oct, 0.5 * sr, freq_scale, plan->n / 2 + 1, &hb[(size_t)i]);
+        if (rc != AA_OK) return rc;
+    }
+    std::vector<BandClass> classes;
+    classify_bands(plan, hb, sample_rate_hz, freq_scale, true, &classes);
+    for (const BandClass& c : classes)
+        for (size_t j = 0; j < c.bands.size(); ++j) out_decimation[c.map.map[j]] = c.D;
+    return AA_OK;
 }
 
 size_t bands_workspace_bytes(const aa_bands_plan* p, int rows, int nb) {
@@ -357,43 +450,9 @@ int rt60bands_batch(const aa_bands_plan* plan, const float* d_x, long long row_s
                               stream, &hb);
         if (rc != AA_OK) return rc;
     }
-    // ---- decimation classes (register-pass lengths, metrics only): a band whose mask support ends below
-    // n / (2 D) is synthesised on the grid start + D j by a length n / D inverse transform of the time-advanced
-    // spectrum - exactly every D-th sample of the reference's band signal - and its Schroeder integral is taken
-    // on that grid with the trapezoid end correction (bandfit.cu).  Measured effect on the band RT60s: <= 8e-4
-    // relative at D <= 4 (tests/test_gpu_parity.py), against a tolerance of 5e-3.
-    struct BandClass {
-        int D = 1;
-        const aa_bands_plan::Decim* sub = nullptr;
-        std::vector<BandDev> bands;
-        BandMapArg map{};
-    };
+    // decimation classes of this call (classify_bands above)
     std::vector<BandClass> classes;
-    {
-        int tile_c = 0, n_tiles = 0, n_groups = 0;
-        const int max_d = band_decimation_limit();
-        const bool can = even && !smoothing && d_band_signal_out == nullptr &&
-                         c2c_energy_layout(plan->c2c, &tile_c, &n_tiles, &n_groups);
-        BandClass full, half, quarter;
-        half.D = 2;
-        quarter.D = 4;
-        for (int i = 0; i < nb; ++i) {
-            BandClass* target = &full;
-            if (can && hb[(size_t)i].k_last >= hb[(size_t)i].k_first) {
-                for (int c = 0; c < 2; ++c) {
-                    const aa_bands_plan::Decim& d = plan->dec[c];
-                    if (d.c2c && d.D <= max_d && p->sample_rate_hz % d.D == 0 && hb[(size_t)i].k_last < d.M - 1) {
-                        target = (d.D == 2) ? &half : &quarter;
-                        target->sub = &d;
-                    }
-                }
-            }
-            target->map.map[target->bands.size()] = i;
-            target->bands.push_back(hb[(size_t)i]);
-        }
-        for (BandClass* c : {&full, &half, &quarter})
-            if (!c->bands.empty()) classes.push_back(*c);
-    }
+    classify_bands(plan, hb, p->sample_rate_hz, freq_scale, !smoothing && d_band_signal_out == nullptr, &classes);
     const bool one_class = classes.size() == 1 && classes[0].D == 1;
     // rows per chunk that fit the workspace; the classes share the signal / scratch / partial buffers
     ClassFootprint fp;

@@ -29,6 +29,10 @@ struct BandDev {
     int lp_step;
     int k_first, k_last;  // inclusive rfft-bin range outside of which the mask is exactly 0
     const float* mask;    // optional table of band_mask_value() for k in [k_first, k_last] (same float32 arithmetic)
+    // Nyquist zone of a decimated synthesis (bands.cu; register passes only): bin kp of the length n / D transform is
+    // the row's bin z_off + kp (even zone) or the conjugate of bin z_off - kp (odd zone: the spectrum folds back).
+    // 0, 0 = baseband.
+    int z_off, z_neg;
 };
 
 AA_HD float ramp01(float f, float x0, float span, int step, float x1) {

@@ -24,7 +24,18 @@ constexpr int kTwoLevelShift = 10;
     X(18, 20, 8, 10, 20, 8) /* N = 144000 (288000 decimated by 2): M = 360 x 200 */ \
     X(10, 20, 4, 12, 15, 8) /* N =  72000 (288000 decimated by 4): M = 200 x 180 */ \
     X(12, 20, 8, 10, 20, 8) /* N =  96000 (192000 decimated by 2): M = 240 x 200 */ \
-    X(10, 12, 8, 10, 20, 8) /* N =  48000 (192000 decimated by 4): M = 120 x 200 */
+    X(10, 12, 8, 10, 20, 8) /* N =  48000 (192000 decimated by 4): M = 120 x 200 */ \
+    X(10, 12, 10, 10, 15, 8) /* N =  36000 (288000 decimated by 8): M = 120 x 150 */ \
+    X(10, 12, 15, 5, 15, 8) /* N =  18000 (288000 decimated by 16): M = 120 x 75 */ \
+    X(10, 12, 4, 10, 10, 8) /* N =  24000 (192000 decimated by 8): M = 120 x 100 */ \
+    X(10, 12, 10, 5, 10, 8) /* N =  12000 (192000 decimated by 16): M = 120 x 50 */ \
+    X(8, 20, 8, 10, 20, 8) /* N =  64000 (192000 decimated by 3): M = 160 x 200 */
+
+// Row lengths whose band stage may synthesise low bands on a decimated grid (bands.cu): the batch shapes the
+// approximation of the Schroeder sums was validated on (configs 3 and 5).  The sub-lengths in AA_REG_LIST are
+// register-pass lengths in their own right but stay at full rate when they are the row length: short files with
+// the onset at sample 0 wrap the filters' pre-ringing into the tail, where a sub-sampled sum is ill-conditioned.
+inline bool band_decimation_parent(int n) { return n == 288000 || n == 192000; }
 
 inline bool reg_split_for(int M, int* M1, int* M2) {
 #define X(ra1, rb1, g1, ra2, rb2, g2)                   \

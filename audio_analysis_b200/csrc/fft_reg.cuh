@@ -92,14 +92,22 @@ struct RegSrcBand {
     AA_HD bool get(int idx, float2* v) const {
         const unsigned span = (unsigned)(b.k_last - b.k_first);  // k_last < k_first (empty band) wraps to "never"
         const int mk = M - idx;
-        const bool in_k = (unsigned)(idx - b.k_first) <= span && b.k_last >= b.k_first;
-        const bool in_m = (unsigned)(mk - b.k_first) <= span && b.k_last >= b.k_first;
+        // decimated transforms read the row's spectrum through the band's Nyquist zone (BandDev::z_off / z_neg)
+        const int ka = b.z_neg ? b.z_off - idx : b.z_off + idx;
+        const int kb = b.z_neg ? b.z_off - mk : b.z_off + mk;
+        const bool in_k = (unsigned)(ka - b.k_first) <= span && b.k_last >= b.k_first;
+        const bool in_m = (unsigned)(kb - b.k_first) <= span && b.k_last >= b.k_first;
         if (!in_k && !in_m) {
             *v = make_float2(0.f, 0.f);
             return false;
         }
         const float2 zero = make_float2(0.f, 0.f);
-        *v = cconj(pack_half_spectrum(in_k ? masked(idx) : zero, in_m ? masked(mk) : zero, twiddle2(twN, idx)));
+        float2 ya = in_k ? masked(ka) : zero, yb = in_m ? masked(kb) : zero;
+        if (b.z_neg) {
+            ya.y = -ya.y;
+            yb.y = -yb.y;
+        }
+        *v = cconj(pack_half_spectrum(ya, yb, twiddle2(twN, idx)));
         return true;
     }
 };

@@ -329,6 +329,17 @@ def band_array(bands: Sequence[Tuple[int, Optional[float], Optional[float]]]):
     return arr
 
 
+def bands_classify(n: int, dev: torch.device, bands: Sequence[Tuple[int, Optional[float], Optional[float]]],
+                   transition_width_octaves: float, sample_rate_hz: int) -> List[int]:
+    """Decimation factor per band for metrics-only calls on rows of `n` samples (aa_bands_classify)."""
+    lib = nat.load()
+    plan = bands_plan(int(n), dev)
+    out = (C.c_int32 * len(bands))()
+    nat.check(lib.aa_bands_classify(plan.handle, band_array(bands), len(bands), float(transition_width_octaves),
+                                    int(sample_rate_hz), out))
+    return [int(v) for v in out]
+
+
 def rt60bands(rows: Rows, start_idx: torch.Tensor, bands: Sequence[Tuple[int, Optional[float], Optional[float]]],
               transition_width_octaves: float, params: nat.DecayParams, want_band_signals: bool = False,
               workspace_bytes: Optional[int] = None):

@@ -164,32 +164,14 @@ def band_triples(bands: Sequence[BandDefinition]):
 
 
 def decimation_classes(bands: Sequence[BandDefinition], n: int, sample_rate_hz: int, transition_width_octaves: float,
-                       max_decimation: int = 4) -> List[int]:
-    """Decimation factor the device path uses for each band of an even-length-`n` row (1 = full rate).
+                       device=None) -> List[int]:
+    """Decimation factor the device path uses for each band of a length-`n` row in a metrics-only call
+    (1 = full rate), as classified by the library (`aa_bands_classify`, csrc/bands.cu) under the current
+    `aa_bands_set_decimation` limit.  Used for byte accounting (bench.py) and documentation."""
+    import torch
 
-    Host mirror of the classification in csrc/bands.cu (for byte accounting and documentation): a band whose
-    raised-cosine mask ends below bin n / (2 D) - 1 is synthesised on every D-th sample.  Only the register-pass
-    lengths (n = 288000, 192000) have decimated plans; other lengths stay at full rate.
-    """
-    if n not in (288000, 192000) or n % 2:
-        return [1] * len(bands)
-    nyq = 0.5 * float(sample_rate_hz)
-    scale = float(sample_rate_hz) / float(n)
-    fac = 2.0 ** float(transition_width_octaves)
-    out = []
-    for b in bands:
-        d_band = 1
-        if b.kind != "highpass":
-            hi = float(np.clip(b.high_edge_hz, 1.0, nyq))
-            stop = min(nyq, hi * fac)
-            if stop <= hi:
-                stop = min(nyq, hi + 1.0)
-            k_last = min(n // 2, int(np.ceil(stop / scale)) + 1)
-            for d in (2, 4):
-                if d <= max_decimation and sample_rate_hz % d == 0 and n % (2 * d) == 0 and k_last < n // (2 * d) - 1:
-                    d_band = d
-        out.append(d_band)
-    return out
+    dev = torch.device(device) if device is not None else torch.device("cuda", torch.cuda.current_device())
+    return engine.bands_classify(n, dev, band_triples(bands), float(transition_width_octaves), int(sample_rate_hz))
 
 
 def run_rt60_bands(rows: engine.Rows, sample_rate_hz: int, settings: Rt60BandsAnalysisSettings,

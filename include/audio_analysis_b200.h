@@ -181,14 +181,18 @@ void aa_bands_plan_destroy(aa_bands_plan* plan);
 /* 0 = direct mixed radix, 1 = Bluestein on n/2, 2 = Bluestein on n (odd n) */
 int aa_bands_plan_kind(const aa_bands_plan* plan);
 /*
- * Band decimation (register-pass lengths, metrics only): a band whose mask support ends below n / (2 D) is
- * synthesised on every D-th sample from the analysis start by a length n / D inverse transform - those ARE samples of
- * the reference's band signal - and its Schroeder integral is taken on that grid with a trapezoid end correction.
- * D <= max_decimation in {1 (off), 2, 4}; default 4, or the environment variable AA_BANDS_DECIMATION.
- * Band RT60s move by <= 8e-4 relative against the full-rate path (tolerance 5e-3).
+ * Band decimation (rows of 288,000 / 192,000 samples, metrics only): the samples y[start + D j] of a band signal are
+ * the length n / D inverse transform of the band's spectrum folded into [0, n / 2D].  A band whose mask support lies
+ * inside one Nyquist zone [m n/2D, (m+1) n/2D] of the decimated rate folds without overlap, so those samples ARE
+ * samples of the reference's band signal (rt60bands.py:170-175); its Schroeder integral (decay.py:150-158) is taken
+ * on that grid with a trapezoid end correction.  D in {2, 3, 4, 8, 16}, D <= max_decimation (1 = off); default 16,
+ * or the environment variable AA_BANDS_DECIMATION.  Band RT60s move by <= 8e-4 relative against the full-rate path
+ * (tolerance 5e-3).  aa_bands_classify reports the factor chosen for each band (host only, no device work).
  */
 int aa_bands_get_decimation(void);
 void aa_bands_set_decimation(int max_decimation);
+int aa_bands_classify(const aa_bands_plan* plan, const aa_band* bands, int32_t n_bands, double transition_width_octaves,
+                      int32_t sample_rate_hz, int32_t* out_decimation);
 /* bytes of workspace needed to process `rows_per_chunk` rows x `n_bands` bands at once */
 size_t aa_bands_workspace_bytes(const aa_bands_plan* plan, int32_t rows_per_chunk, int32_t n_bands);
 

@@ -347,7 +347,7 @@ def test_band_decimation_against_oracle_and_switch():
                 want.append(np.array([[np.nan if v is None else v for v in ob["metrics"][b["name"]]] for b in ob["bands"]]))
             s = rb.Rt60BandsAnalysisSettings(band_mode="third", include_t20=True)
             got = {}
-            for max_d in (4, 2, 1):
+            for max_d in (16, 8, 4, 2, 1):
                 lib.aa_bands_set_decimation(max_d)
                 assert lib.aa_bands_get_decimation() == max_d
                 res = rb.analyse_rt60_bands_batch(x, SR, ["a", "b"], s)
@@ -360,9 +360,10 @@ def test_band_decimation_against_oracle_and_switch():
                     check_band_table(f"decim{max_d}/n{n}", tab[i][:, :2], want[i][:, :2])
                     err = np.nanmax(np.abs(tab[i][:, :2] - want[i][:, :2]) / want[i][:, :2])
                     note(f"band_rt60_rel_err[decimation<={max_d}]", err)
-            assert not np.array_equal(got[4], got[1])     # the switch really changes the path
+            assert not np.array_equal(got[16], got[1])     # the switch really changes the path
+            assert not np.array_equal(got[16], got[4])
     finally:
-        lib.aa_bands_set_decimation(4)
+        lib.aa_bands_set_decimation(16)
 
 
 # ------------------------------------------------------------------------------------ spectrogram
@@ -537,7 +538,7 @@ def test_full_size_properties_config5_rows():
     assert torch.equal(torch.nan_to_num(sub[0]), torch.nan_to_num(whole[1]))
     # 8. band decimation (default) against the full-rate synthesis (what `want_band_signals` forces): the decimated
     #    grid holds exact samples of the same band signals, only the Schroeder sum is taken on fewer points
-    assert nat_lib().aa_bands_get_decimation() == 4
+    assert nat_lib().aa_bands_get_decimation() == 16
     full = metrics.cpu().numpy()[:2, :, 0]
     dec = whole.cpu().numpy()[:2, :, 0]
     assert np.array_equal(np.isnan(full), np.isnan(dec))
