@@ -525,6 +525,11 @@ int rt60bands_batch(const aa_bands_plan* plan, const float* d_x, long long row_s
                 const int n_c = bc.sub ? bc.sub->n : N;
                 const int M_c = bc.sub ? bc.sub->M : M;
                 const int ystride_c = bc.sub ? bc.sub->y_stride : plan->y_stride;
+                // nested stage timing per class (aa_profile_ms("band_class_d<D>")): the kernels inside keep their own scopes
+                static const char* const kClassNames[17] = {"", "band_class_d1", "band_class_d2", "band_class_d3",
+                                                            "band_class_d4", "", "", "", "band_class_d8", "", "", "",
+                                                            "", "", "", "", "band_class_d16"};
+                ProfScope class_prof(kClassNames[D <= 16 ? D : 0], stream);
                 rc = store_band_table(bc.bands.data(), nbc, d_class_bands, stream);
                 if (rc != AA_OK) return rc;
                 SrcDesc s{};

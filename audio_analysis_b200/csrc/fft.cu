@@ -268,8 +268,17 @@ constexpr int reg_pitch(int G, int min_elems) {
 template <int RA, int RB, int G>
 using RegCfg = RegPass<RA, RB, G, reg_pitch(G, RB * (RA | 1))>;
 
+// resident CTAs per SM the band variant is compiled for: a cap of 64 registers per thread (AA_COLS_REG_CAP; 56 and no cap measured 5 % and 2 % slower) (the band source's
+// batched loads otherwise push it to 70-80 and the occupancy to a third)
+#ifndef AA_COLS_REG_CAP
+#define AA_COLS_REG_CAP 64
+#endif
+constexpr int cols_min_blocks(int threads, int src) {
+    return (src == SRC_BAND_PACKED && AA_COLS_REG_CAP > 0) ? 65536 / (AA_COLS_REG_CAP * threads) : 1;
+}
+
 template <class P, int kSrc, int M2>
-__global__ void __launch_bounds__(P::kThreads) fft_cols_reg(SrcDesc src, float2* __restrict__ scratch, TwoLevelTwiddle twM,
+__global__ void __launch_bounds__(P::kThreads, cols_min_blocks(P::kThreads, kSrc)) fft_cols_reg(SrcDesc src, float2* __restrict__ scratch, TwoLevelTwiddle twM,
                                                             const float2* __restrict__ tw_full) {
     static_assert(M2 % P::G == 0, "columns must split evenly over CTAs");
     constexpr int groups = M2 / P::G;
@@ -287,10 +296,8 @@ __global__ void __launch_bounds__(P::kThreads) fft_cols_reg(SrcDesc src, float2*
         s.freq_scale = src.freq_scale;
         s.M = src.M;
         s.twN = src.twN;
-        s.shift = src.shift ? src.shift[row] : 0;
-        s.shift_N = src.shift_N;
-        s.shift_rcp = src.shift_N > 0 ? 1.0 / (double)src.shift_N : 0.0;
-        s.twShift = src.twShift;
+        // no per-row time advance here: the spectra arrive already advanced (bands.cu: untangle_kernel), and
+        // c2c_exec sends a SrcDesc with a shift to the generic pass
         reg_cols_stage_a<P>((int)threadIdx.x, s, M2, col0, buf);
     } else if (kSrc == SRC_COMPLEX) {
         RegSrcComplex s{(const float2*)src.base + (size_t)unit * src.unit_stride};
@@ -442,7 +449,7 @@ int exec_direct(const C2CPlan* p, const SrcDesc& src, const DstDesc& dst, long l
         const bool use_spec = getenv("AA_FFT_GENERIC") == nullptr && units * (long long)p->M < 2147483647LL;
         ProfScope prof(src.mode == SRC_BAND_PACKED || src.mode == SRC_BAND_FULL ? "fft_cols_band" : "fft_cols", stream);
         if (use_spec && fast_src && src.mode == SRC_BAND_PACKED && src.conj && src.bands_have_tables &&
-            launch_cols_reg<SRC_BAND_PACKED>(p, src, scratch, units, stream)) {
+            src.shift == nullptr && launch_cols_reg<SRC_BAND_PACKED>(p, src, scratch, units, stream)) {
         } else if (use_spec && fast_src && src.mode == SRC_REAL_PACKED && !src.clip && src.n_valid == 2 * p->M &&
                    (src.unit_stride % 2) == 0 && launch_cols_reg<SRC_REAL_PACKED>(p, src, scratch, units, stream)) {
         } else if (use_spec && fast_src && src.mode == SRC_COMPLEX && !src.conj && src.n_valid >= p->M &&

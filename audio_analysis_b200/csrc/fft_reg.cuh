@@ -54,6 +54,14 @@ struct RegSrcComplex {
         *v = load_c(p + idx);
         return true;
     }
+    template <int RA>
+    AA_HD bool get_all(int base, int stride, float2* v) const {
+        static_for<0, RA>([&](auto r_) {
+            constexpr int r = decltype(r_)::value;
+            v[r] = load_c(p + base + r * stride);
+        });
+        return true;
+    }
 };
 
 // Packed, band-masked, conjugated half spectrum of one (row, band) unit (rt60bands.py:170-175):
@@ -70,6 +78,9 @@ struct RegSrcBand {
     double shift_rcp = 0.0;     // 1 / shift_N
     TwoLevelTwiddle twShift{};  // exp(-2 pi i m / shift_N)
     AA_HD float2 advance(float2 v, int k) const {
+#ifdef __CUDA_ARCH__
+        return v;  // device callers store the spectrum already advanced (bands.cu: untangle_kernel); fft.cu rejects a shift
+#else
         if (shift == 0) return v;
         // (k * shift) mod shift_N without a 64-bit division: the float64 quotient is exact to +-1
         const long long prod = (long long)k * (long long)shift;
@@ -78,6 +89,7 @@ struct RegSrcBand {
         if (r < 0) r += shift_N;
         if (r >= shift_N) r -= shift_N;
         return cmulc(v, twiddle2(twShift, r));   // * exp(+2 pi i k shift / N)
+#endif
     }
     AA_HD float2 masked(int k) const {  // k inside [k_first, k_last]
 #ifdef __CUDA_ARCH__
@@ -89,25 +101,74 @@ struct RegSrcBand {
 #endif
         return advance(cscale(load_c(X + k), m), k);
     }
-    AA_HD bool get(int idx, float2* v) const {
-        const unsigned span = (unsigned)(b.k_last - b.k_first);  // k_last < k_first (empty band) wraps to "never"
+    // decimated transforms read the row's spectrum through the band's Nyquist zone (BandDev::z_off / z_neg)
+    AA_HD int zone_bin(int kp) const { return b.z_neg ? b.z_off - kp : b.z_off + kp; }
+    AA_HD bool in_support(int k) const {
+        // k_last < k_first (empty band) is rejected by the second term
+        return (unsigned)(k - b.k_first) <= (unsigned)(b.k_last - b.k_first) && b.k_last >= b.k_first;
+    }
+    // Element idx of the packed, masked, conjugated spectrum, WITHOUT branches: out-of-support bins load the band's
+    // first bin with a zero mask, so that the loads of a whole butterfly can be issued together.  (The per-element
+    // branchy form serialised them: 49 % of the warp stall samples of this kernel were long-scoreboard waits.)
+    AA_HD float2 element(int idx, bool in_k, bool in_m, float2 w /* exp(-2 pi i idx / N) */) const {
         const int mk = M - idx;
-        // decimated transforms read the row's spectrum through the band's Nyquist zone (BandDev::z_off / z_neg)
-        const int ka = b.z_neg ? b.z_off - idx : b.z_off + idx;
-        const int kb = b.z_neg ? b.z_off - mk : b.z_off + mk;
-        const bool in_k = (unsigned)(ka - b.k_first) <= span && b.k_last >= b.k_first;
-        const bool in_m = (unsigned)(kb - b.k_first) <= span && b.k_last >= b.k_first;
-        if (!in_k && !in_m) {
-            *v = make_float2(0.f, 0.f);
-            return false;
-        }
-        const float2 zero = make_float2(0.f, 0.f);
-        float2 ya = in_k ? masked(ka) : zero, yb = in_m ? masked(kb) : zero;
+        const int ka = in_k ? zone_bin(idx) : b.k_first, kb = in_m ? zone_bin(mk) : b.k_first;
+#ifdef __CUDA_ARCH__
+        float ma = load_r(b.mask + (ka - b.k_first)), mb = load_r(b.mask + (kb - b.k_first));
+#else
+        float ma = b.mask ? b.mask[ka - b.k_first] : band_mask_value(b, (float)((double)ka * freq_scale));
+        float mb = b.mask ? b.mask[kb - b.k_first] : band_mask_value(b, (float)((double)kb * freq_scale));
+#endif
+        const float2 xa = load_c(X + ka), xb = load_c(X + kb);
+        ma = in_k ? ma : 0.0f;
+        mb = in_m ? mb : 0.0f;
+        float2 ya = advance(cscale(xa, ma), ka), yb = advance(cscale(xb, mb), kb);
         if (b.z_neg) {
             ya.y = -ya.y;
             yb.y = -yb.y;
         }
-        *v = cconj(pack_half_spectrum(ya, yb, twiddle2(twN, idx)));
+        return cconj(pack_half_spectrum(ya, yb, w));
+    }
+    AA_HD bool get(int idx, float2* v) const {
+        const bool in_k = in_support(zone_bin(idx)), in_m = in_support(zone_bin(M - idx));
+        if (!in_k && !in_m) {
+            *v = make_float2(0.f, 0.f);
+            return false;
+        }
+        *v = element(idx, in_k, in_m, twiddle2(twN, idx));
+        return true;
+    }
+    // the RA inputs base + r * stride of one stage-A butterfly; false = all structurally zero
+    template <int RA>
+    AA_HD bool get_all(int base, int stride, float2* v) const {
+        unsigned bits_k = 0, bits_m = 0;
+        static_for<0, RA>([&](auto r_) {
+            constexpr int r = decltype(r_)::value;
+            const int idx = base + r * stride;
+            bits_k |= in_support(zone_bin(idx)) ? (1u << r) : 0u;
+            bits_m |= in_support(zone_bin(M - idx)) ? (1u << r) : 0u;
+        });
+        if ((bits_k | bits_m) == 0u) {
+            static_for<0, RA>([&](auto r_) { v[decltype(r_)::value] = make_float2(0.f, 0.f); });
+            return false;
+        }
+        // the butterfly's inputs sit N / (2 RA) apart (stride = RB M2, N = 2 RA RB M2), so their packing twiddles are
+        // w(base) times compile-time roots of unity: one table lookup per butterfly instead of RA.  Inputs are built
+        // in groups of four: a group with no bin in the band's support costs one test (narrow bands touch one or two
+        // groups), inside a group everything is branch-free so that its loads are in flight together.
+        const float2 w0 = twiddle2(twN, base);
+        const unsigned bits = bits_k | bits_m;
+        static_for<0, (RA + 3) / 4>([&](auto c_) {
+            constexpr int lo = 4 * decltype(c_)::value, hi = (lo + 4 < RA) ? lo + 4 : RA;
+            if ((bits >> lo) & ((1u << (hi - lo)) - 1u)) {
+                static_for<lo, hi>([&](auto r_) {
+                    constexpr int r = decltype(r_)::value;
+                    v[r] = element(base + r * stride, (bits_k >> r) & 1u, (bits_m >> r) & 1u, mul_root<r, 2 * RA>(w0));
+                });
+            } else {
+                static_for<lo, hi>([&](auto r_) { v[decltype(r_)::value] = make_float2(0.f, 0.f); });
+            }
+        });
         return true;
     }
 };
@@ -119,11 +180,7 @@ AA_HD void reg_cols_stage_a(int t, const Src& src, int M2, int col0, float2* buf
     if (t >= P::kThreadsA) return;
     const int ja = t / P::G, g = t - ja * P::G;
     float2 v[P::RA];
-    bool any = false;
-    static_for<0, P::RA>([&](auto r_) {
-        constexpr int r = decltype(r_)::value;
-        any |= src.get((ja + r * P::RB) * M2 + col0 + g, &v[r]);
-    });
+    const bool any = src.template get_all<P::RA>(ja * M2 + col0 + g, P::RB * M2, v);
     if (any) dft_r<P::RA>(v);
     static_for<0, P::RA>([&](auto r_) {
         constexpr int r = decltype(r_)::value;

@@ -214,6 +214,9 @@ def run_ours(args):
     stage_names = ["edc", "fft_cols", "fft_rows", "untangle", "fft_cols_band", "fft_rows_band", "band_fit", "band_edc", "csd"]
     stage_ms = {k: lib.aa_profile_ms(k.encode()) / args.steps for k in stage_names}
     stage_scopes = {k: int(lib.aa_profile_scopes(k.encode())) // args.steps for k in stage_names}
+    # band stage per decimation class (nested scopes around the class's kernels)
+    class_ms = {f"D{d}": round(lib.aa_profile_ms(f"band_class_d{d}".encode()) / args.steps, 4) for d in (1, 2, 3, 4, 8, 16)}
+    class_ms = {k: v for k, v in class_ms.items() if v > 0.0}
     lib.aa_profile_enable(0)
     launches = (lib.aa_kernel_launch_count() - launches0) // max(1, args.steps)
     t = torch.tensor([ms_total], dtype=torch.float64, device=dev)
@@ -371,7 +374,7 @@ def run_ours(args):
             "config": {"workload": f"config5 shard: {rows_n} x {n / SR:.0f} s @48 kHz mono IRs per GPU "
                                    f"(third-octave RT60 + broadband EDC/EDT/T20/T30 + CSD 18x{n_bins})",
                        "rows_per_gpu": rows_n, "samples_per_row": n, "bands": 26,
-                       "band_decimation": {"max": int(lib.aa_bands_get_decimation()),
+                       "band_decimation": {"max": int(lib.aa_bands_get_decimation()), "ms_per_class": class_ms,
                                            "bands_per_factor": {str(d): dec.count(d) for d in sorted(set(dec))}},
                        "l2": "inputs (rows*samples*4 B per GPU) are larger than L2; no flush needed"},
             "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
