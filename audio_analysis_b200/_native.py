@@ -143,7 +143,7 @@ def _declare(lib: C.CDLL) -> None:
     lib.aa_bands_set_decimation.restype = None
     lib.aa_bands_set_decimation.argtypes = [C.c_int]
     lib.aa_bands_classify.restype = C.c_int
-    lib.aa_bands_classify.argtypes = [vp, C.POINTER(Band), i32, C.c_double, i32, C.POINTER(C.c_int32)]
+    lib.aa_bands_classify.argtypes = [vp, C.POINTER(Band), i32, C.c_double, i32, C.POINTER(DecayParams), C.POINTER(C.c_int32)]
     lib.aa_bands_workspace_bytes.restype = sz
     lib.aa_bands_workspace_bytes.argtypes = [vp, i32, i32]
     lib.aa_rt60bands_batch.restype = C.c_int

@@ -65,7 +65,7 @@ int bands_plan_kind(const aa_bands_plan* p);
 int band_decimation_limit();
 void set_band_decimation_limit(int max_d);
 int bands_classify(const aa_bands_plan* plan, const aa_band* bands, int nb, double tw_oct, int sample_rate_hz,
-                   int* out_decimation);
+                   const aa_decay_params* fits, int* out_decimation);
 int rt60bands_batch(const aa_bands_plan* plan, const float* d_x, long long row_stride, int n_rows,
                     const int* d_start_idx, const aa_band* bands, int nb, double tw_oct, const aa_decay_params* p,
                     double* d_metrics_out, float* d_band_signal_out, void* d_ws, size_t ws_bytes, cudaStream_t stream);
@@ -175,8 +175,8 @@ int aa_bands_plan_kind(const aa_bands_plan* plan) { return aa::bands_plan_kind(p
 int aa_bands_get_decimation(void) { return aa::band_decimation_limit(); }
 void aa_bands_set_decimation(int max_decimation) { aa::set_band_decimation_limit(max_decimation); }
 int aa_bands_classify(const aa_bands_plan* plan, const aa_band* bands, int32_t n_bands, double transition_width_octaves,
-                      int32_t sample_rate_hz, int32_t* out_decimation) {
-    return aa::bands_classify(plan, bands, n_bands, transition_width_octaves, sample_rate_hz, out_decimation);
+                      int32_t sample_rate_hz, const aa_decay_params* fits, int32_t* out_decimation) {
+    return aa::bands_classify(plan, bands, n_bands, transition_width_octaves, sample_rate_hz, fits, out_decimation);
 }
 size_t aa_bands_workspace_bytes(const aa_bands_plan* plan, int32_t rows_per_chunk, int32_t n_bands) {
     return aa::bands_workspace_bytes(plan, rows_per_chunk, n_bands);

@@ -305,10 +305,24 @@ bool place_in_zone(const BandDev& b, int Mc, double freq_scale, BandDev* out) {
     return true;
 }
 
+// Largest decimation the requested fits tolerate.  T20 / T30 (>= 20 dB of a curve that starts at -5 dB) move by
+// <= 6e-4 relative at D = 16; a short or early range such as EDT (0 .. -10 dB) follows the 2 f ripple of a
+// low band's Schroeder curve and moves by up to 6e-3 at D = 16, 1.8e-3 at D = 8, 7e-4 at D <= 4
+// (tools/decimation_error.py), so such fits keep D <= 4.
+int fit_decimation_limit(const aa_decay_params* p) {
+    int lim = 16;
+    if (!p) return lim;
+    for (int f = 0; f < p->n_fits && f < AA_MAX_FITS; ++f) {
+        const double hi = p->fit_hi_db[f], lo = fmax(p->fit_lo_db[f], p->fit_lower_limit_db);
+        if (hi > -2.5 || hi - lo < 15.0) lim = 4;
+    }
+    return lim;
+}
+
 void classify_bands(const aa_bands_plan* plan, const std::vector<BandDev>& hb, int sample_rate_hz, double freq_scale,
-                    bool metrics_only, std::vector<BandClass>* classes) {
+                    bool metrics_only, const aa_decay_params* fits, std::vector<BandClass>* classes) {
     int tile_c = 0, n_tiles = 0, n_groups = 0;
-    const int max_d = band_decimation_limit();
+    const int max_d = std::min(band_decimation_limit(), fit_decimation_limit(fits));
     const bool can = (plan->n % 2) == 0 && metrics_only && c2c_energy_layout(plan->c2c, &tile_c, &n_tiles, &n_groups);
     BandClass by_d[aa_bands_plan::kDecims + 1];   // [0] full rate, [1 + c] plan->dec[c]
     for (size_t i = 0; i < hb.size(); ++i) {
@@ -395,7 +409,7 @@ void bands_plan_destroy(aa_bands_plan* p) {
 
 // decimation factor the band stage uses for each band of a metrics-only call (host only; no device work)
 int bands_classify(const aa_bands_plan* plan, const aa_band* bands, int nb, double tw_oct, int sample_rate_hz,
-                   int* out_decimation) {
+                   const aa_decay_params* fits, int* out_decimation) {
     AA_REQUIRE(plan && bands && out_decimation, AA_ERR_INVALID_ARGUMENT, "null argument");
     AA_REQUIRE(nb >= 1 && nb <= AA_MAX_BANDS, AA_ERR_INVALID_ARGUMENT, "band count out of range");
     AA_REQUIRE(sample_rate_hz > 0, AA_ERR_INVALID_ARGUMENT, "sample rate must be positive");
@@ -407,7 +421,7 @@ int bands_classify(const aa_bands_plan* plan, const aa_band* bands, int nb, doub
         if (rc != AA_OK) return rc;
     }
     std::vector<BandClass> classes;
-    classify_bands(plan, hb, sample_rate_hz, freq_scale, true, &classes);
+    classify_bands(plan, hb, sample_rate_hz, freq_scale, true, fits, &classes);
     for (const BandClass& c : classes)
         for (size_t j = 0; j < c.bands.size(); ++j) out_decimation[c.map.map[j]] = c.D;
     return AA_OK;
@@ -452,7 +466,7 @@ int rt60bands_batch(const aa_bands_plan* plan, const float* d_x, long long row_s
     }
     // decimation classes of this call (classify_bands above)
     std::vector<BandClass> classes;
-    classify_bands(plan, hb, p->sample_rate_hz, freq_scale, !smoothing && d_band_signal_out == nullptr, &classes);
+    classify_bands(plan, hb, p->sample_rate_hz, freq_scale, !smoothing && d_band_signal_out == nullptr, p, &classes);
     const bool one_class = classes.size() == 1 && classes[0].D == 1;
     // rows per chunk that fit the workspace; the classes share the signal / scratch / partial buffers
     ClassFootprint fp;

@@ -330,13 +330,15 @@ def band_array(bands: Sequence[Tuple[int, Optional[float], Optional[float]]]):
 
 
 def bands_classify(n: int, dev: torch.device, bands: Sequence[Tuple[int, Optional[float], Optional[float]]],
-                   transition_width_octaves: float, sample_rate_hz: int) -> List[int]:
-    """Decimation factor per band for metrics-only calls on rows of `n` samples (aa_bands_classify)."""
+                   transition_width_octaves: float, sample_rate_hz: int,
+                   params: Optional[nat.DecayParams] = None) -> List[int]:
+    """Decimation factor per band for metrics-only calls on rows of `n` samples (aa_bands_classify); `params`
+    carries the requested fits (short / early ranges such as EDT keep the decimation at <= 4)."""
     lib = nat.load()
     plan = bands_plan(int(n), dev)
     out = (C.c_int32 * len(bands))()
     nat.check(lib.aa_bands_classify(plan.handle, band_array(bands), len(bands), float(transition_width_octaves),
-                                    int(sample_rate_hz), out))
+                                    int(sample_rate_hz), C.byref(params) if params is not None else None, out))
     return [int(v) for v in out]
 
 

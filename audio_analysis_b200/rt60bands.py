@@ -164,14 +164,18 @@ def band_triples(bands: Sequence[BandDefinition]):
 
 
 def decimation_classes(bands: Sequence[BandDefinition], n: int, sample_rate_hz: int, transition_width_octaves: float,
-                       device=None) -> List[int]:
+                       device=None, settings: Optional[Rt60BandsAnalysisSettings] = None) -> List[int]:
     """Decimation factor the device path uses for each band of a length-`n` row in a metrics-only call
     (1 = full rate), as classified by the library (`aa_bands_classify`, csrc/bands.cu) under the current
     `aa_bands_set_decimation` limit.  Used for byte accounting (bench.py) and documentation."""
     import torch
 
     dev = torch.device(device) if device is not None else torch.device("cuda", torch.cuda.current_device())
-    return engine.bands_classify(n, dev, band_triples(bands), float(transition_width_octaves), int(sample_rate_hz))
+    params = None
+    if settings is not None:
+        params = native_params(settings.decay_settings, sample_rate_hz, [r for _, r in band_fit_plan(settings)],
+                               want_early10=False)
+    return engine.bands_classify(n, dev, band_triples(bands), float(transition_width_octaves), int(sample_rate_hz), params)
 
 
 def run_rt60_bands(rows: engine.Rows, sample_rate_hz: int, settings: Rt60BandsAnalysisSettings,

@@ -234,7 +234,7 @@ def run_ours(args):
     n_bands = int(out.band_metrics.shape[1])
     units = rows_n * n_bands
     # samples synthesised per row over all bands: bands with a low mask are built on every 2nd / 4th sample
-    dec = rt60bands.decimation_classes(out.bands, n, SR, bs.transition_width_octaves)
+    dec = rt60bands.decimation_classes(out.bands, n, SR, bs.transition_width_octaves, settings=bs)
     band_samples = float(sum(n // d for d in dec))          # per row, all bands
     band_units_total = rows_n * band_samples                # replaces units * n below
     stage_bytes = {

@@ -187,12 +187,14 @@ int aa_bands_plan_kind(const aa_bands_plan* plan);
  * samples of the reference's band signal (rt60bands.py:170-175); its Schroeder integral (decay.py:150-158) is taken
  * on that grid with a trapezoid end correction.  D in {2, 3, 4, 8, 16}, D <= max_decimation (1 = off); default 16,
  * or the environment variable AA_BANDS_DECIMATION.  Band RT60s move by <= 8e-4 relative against the full-rate path
- * (tolerance 5e-3).  aa_bands_classify reports the factor chosen for each band (host only, no device work).
+ * (tolerance 5e-3) for fits of >= 15 dB that start below -2.5 dB (T20, T30); calls that ask for a short or early fit
+ * (EDT) keep D <= 4, where EDT moves by <= 7e-4.  aa_bands_classify reports the factor chosen for each band
+ * (host only, no device work).
  */
 int aa_bands_get_decimation(void);
 void aa_bands_set_decimation(int max_decimation);
 int aa_bands_classify(const aa_bands_plan* plan, const aa_band* bands, int32_t n_bands, double transition_width_octaves,
-                      int32_t sample_rate_hz, int32_t* out_decimation);
+                      int32_t sample_rate_hz, const aa_decay_params* fits /* may be NULL */, int32_t* out_decimation);
 /* bytes of workspace needed to process `rows_per_chunk` rows x `n_bands` bands at once */
 size_t aa_bands_workspace_bytes(const aa_bands_plan* plan, int32_t rows_per_chunk, int32_t n_bands);
 

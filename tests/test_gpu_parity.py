@@ -362,6 +362,18 @@ def test_band_decimation_against_oracle_and_switch():
                     note(f"band_rt60_rel_err[decimation<={max_d}]", err)
             assert not np.array_equal(got[16], got[1])     # the switch really changes the path
             assert not np.array_equal(got[16], got[4])
+            # a call that also asks for EDT (0 .. -10 dB: short and early) keeps the decimation at <= 4 and every
+            # metric, EDT included, inside the tolerance
+            lib.aa_bands_set_decimation(16)
+            se = rb.Rt60BandsAnalysisSettings(band_mode="third", include_t20=True, include_edt=True)
+            bands = rb._build_band_definitions(se, SR)
+            assert max(rb.decimation_classes(bands, n, SR, se.transition_width_octaves, settings=se)) == 4
+            assert max(rb.decimation_classes(bands, n, SR, s.transition_width_octaves, settings=s)) == 16
+            res = rb.analyse_rt60_bands_batch(x, SR, ["a", "b"], se)
+            for i in range(2):
+                ob = oracle.band_metrics(x[i], SR, oracle.BandParams(band_mode="third", include_t20=True, include_edt=True))
+                w = np.array([[np.nan if v is None else v for v in ob["metrics"][b["name"]]] for b in ob["bands"]])
+                check_band_table(f"decim_edt/n{n}", _band_table(res[i], [b["name"] for b in ob["bands"]]), w)
     finally:
         lib.aa_bands_set_decimation(16)
 
@@ -498,6 +510,89 @@ def test_modal_cloud_batch_and_errors():
         assert abs(rt - (0.6 + 0.3 * i)) < 0.15 * (0.6 + 0.3 * i)     # the clouds sit at the synthetic RT60
     with pytest.raises(ValueError, match="need at least n_fft"):
         mc.analyse_modal_cloud_for_channel(np.ones(5000, np.float32), SR, "m", mc.ModalCloudAnalysisSettings())
+
+
+# ------------------------------------------------------------------------------------ BASELINE.json configs 3 and 4
+
+
+def _band_table(result, names):
+    return np.array([[np.nan if v is None else v for v in
+                      (result.band_metrics_by_name[n].rt60_t30_seconds, result.band_metrics_by_name[n].rt60_t20_seconds,
+                       result.band_metrics_by_name[n].edt_seconds)] for n in names])
+
+
+def test_config3_bundle_taps_pcm16_stereo():
+    """Config 3 shape: stereo 4 s @48 kHz taps as interleaved PCM16 (recorder.hpp layout), decoded on the device
+    (io.py:46-64 rules), then decay + third-octave rt60bands per channel - against the oracle on the same PCM."""
+    import torch
+    from audio_analysis_b200 import decay, engine, rt60bands as rb
+    from audio_analysis_b200.synth import synth_batch_numpy
+    taps, n = 3, 192000
+    x = synth_batch_numpy(2 * taps, n, SR, first_index=300)
+    pcm = np.clip(np.round(x * 32767.0), -32768, 32767).astype(np.int16).reshape(taps, 2, n).transpose(0, 2, 1)
+    rows = engine.pcm16_to_rows(torch.from_numpy(np.ascontiguousarray(pcm).reshape(taps, -1)).cuda(), n, 2,
+                                mono_downmix=False)
+    ds = decay.DecayAnalysisSettings(compute_edt=True)
+    bs = rb.Rt60BandsAnalysisSettings(band_mode="third", include_t20=True, include_edt=True, decay_settings=ds)
+    dec_out = decay.run_decay(rows, SR, ds)
+    got_bands = rb.analyse_rt60_bands_batch(rows, SR, None, bs)
+    fits = dec_out.fits.cpu().numpy()
+    starts = dec_out.start.cpu().numpy()
+    for r in range(2 * taps):
+        xr = (pcm[r // 2, :, r % 2].astype(np.float32) / 32768.0).astype(np.float32)
+        w = oracle.decay_metrics(xr, SR, oracle.DecayParams(compute_edt=True))
+        assert int(starts[r]) == w["start"]
+        for c, name in enumerate(("EDT", "T20", "T30")):
+            if w["fits"].get(name) is not None:
+                assert seconds_close(fits[r, c, 5], w["fits"][name]["rt60"]), (r, name)
+        wb = oracle.band_metrics(xr, SR, oracle.BandParams(band_mode="third", include_t20=True, include_edt=True))
+        names = [b["name"] for b in wb["bands"]]
+        want = np.array([[np.nan if v is None else v for v in wb["metrics"][nm]] for nm in names])
+        check_band_table(f"config3/row{r}", _band_table(got_bands[r], names), want)
+
+
+def test_config4_sweep_capture_to_bands_and_csd():
+    """Config 4 chain at its real size: a 13 s capture of a 10 s log sweep through a synthetic room is deconvolved at
+    n_fft = 2^20 (deconvolve.py:124-193), and the 624,000-sample IR goes through third-octave rt60bands and the CSD
+    waterfall - every stage against the oracle chain on the same capture."""
+    import torch
+    from audio_analysis_b200 import engine, rt60bands as rb, waterfall as wf
+    from audio_analysis_b200.synth import synth_batch_numpy
+    n, n_sweep, caps = 624000, 480000, 2
+    t = np.arange(n_sweep) / SR
+    f0, f1, dur = 20.0, 20000.0, n_sweep / SR
+    k = np.log(f1 / f0)
+    sweep = np.zeros(n, np.float32)
+    sweep[:n_sweep] = (0.5 * np.sin(2.0 * np.pi * f0 * dur / k * (np.exp(t / dur * k) - 1.0))).astype(np.float32)
+    irs = synth_batch_numpy(caps, 96000, SR, first_index=900)
+    S = np.fft.rfft(sweep.astype(np.float64))
+    rec = np.stack([np.fft.irfft(S * np.fft.rfft(irs[i].astype(np.float64), n=n), n=n) for i in range(caps)])
+    rec = (0.9 * rec / np.max(np.abs(rec))).astype(np.float32)
+    n_fft = 1 << (n - 1).bit_length()
+    assert n_fft == 1 << 20
+    out = engine.deconvolve(engine.make_rows(rec), torch.from_numpy(sweep), n_fft, 1e-10, True, 0.95, 1, n)
+    got_ir = out[:, :n].contiguous()
+    bs = rb.Rt60BandsAnalysisSettings(band_mode="third", include_t20=True)
+    got_bands = rb.analyse_rt60_bands_batch(engine.make_rows(got_ir), SR, None, bs)
+    got_wf = wf.analyse_waterfall_batch(engine.make_rows(got_ir), SR, None, wf.WaterfallAnalysisSettings())
+    ir_host = got_ir.cpu().numpy()
+    for i in range(caps):
+        want_ir = oracle.deconvolve(rec[i].reshape(-1, 1), sweep)[:, 0]
+        err = float(np.max(np.abs(ir_host[i] - want_ir)))
+        note("config4_deconvolve_max_abs_err", err)
+        assert err <= 2e-4 * float(np.max(np.abs(want_ir)))
+        wb = oracle.band_metrics(want_ir, SR, oracle.BandParams(band_mode="third", include_t20=True))
+        names = [b["name"] for b in wb["bands"]]
+        want = np.array([[np.nan if v is None else v for v in wb["metrics"][nm]] for nm in names])
+        check_band_table(f"config4/capture{i}", _band_table(got_bands[i], names)[:, :2], want[:, :2])
+        # CSD: stage parity on the SAME impulse response (the device one).  Chained through the two deconvolutions the
+        # slices differ by ~2e-3 dB in the -70 dB bins, which is the float32-vs-float64 deconvolution error above,
+        # not the STFT's.
+        ww = oracle.waterfall(ir_host[i], SR, oracle.CsdParams())
+        assert oracle.waterfall(want_ir, SR, oracle.CsdParams())["start"] == ww["start"]
+        assert got_wf[i].analysis_start_sample_index == ww["start"]
+        assert np.array_equal(got_wf[i].slice_times_seconds, ww["slice_times"])
+        _check_slices(f"config4/capture{i}", got_wf[i].slice_magnitude_rel_db, ww["rel_db"])
 
 
 # ------------------------------------------------------------------------------------ size-independent properties
