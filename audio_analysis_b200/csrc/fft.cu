@@ -313,6 +313,7 @@ __global__ void __launch_bounds__(P::kThreads, cols_min_blocks(P::kThreads, kSrc
     reg_cols_stage_b<P>((int)threadIdx.x, buf, tws, colq, scratch + (size_t)unit * ((size_t)P::L * M2), M2, col0, twM);
 }
 
+// (a register cap on this kernel - 56 or 48 per thread through a min-blocks bound - measured 2-6 % slower)
 template <class P, int M1, bool kEnergy>
 __global__ void __launch_bounds__(P::kThreads) fft_rows_reg(const float2* __restrict__ scratch, float2* __restrict__ out,
                                                             long long out_stride, int n_valid, int conj, float scale,
