@@ -9,6 +9,7 @@
 //   3. the fused EDC kernel in metrics-only mode on every band signal with the row's shared
 //      start index (rt60bands.py:342,393), writing only the RT60 table.
 #include <math.h>
+#include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
 
@@ -34,7 +35,7 @@ struct aa_bands_plan {
         aa::C2CPlan* c2c = nullptr;
         aa::TwoLevelTable twN;
     };
-    static constexpr int kDecims = 5;
+    static constexpr int kDecims = 8;
     Decim dec[kDecims];   // D = kDecimList[i]
 };
 
@@ -42,11 +43,12 @@ namespace aa {
 
 // largest decimation the band stage may use (1 = off); AA_BANDS_DECIMATION overrides the default
 constexpr int kDefaultBandDecimation = 16;
-constexpr int kDecimList[aa_bands_plan::kDecims] = {2, 3, 4, 8, 16};
+constexpr int kDecimList[aa_bands_plan::kDecims] = {2, 3, 4, 6, 8, 12, 16, 24};
+constexpr int kMaxBandDecimation = 24;
 // largest mask value a bin may have and still be left out when a band's support pokes past its Nyquist zone
 constexpr float kZoneDropMask = 0.02f;
 static int g_band_decimation = -1;
-static int clamp_band_decimation(int v) { return v < 1 ? 1 : (v > 16 ? 16 : v); }
+static int clamp_band_decimation(int v) { return v < 1 ? 1 : (v > kMaxBandDecimation ? kMaxBandDecimation : v); }
 int band_decimation_limit() {
     if (g_band_decimation < 0) {
         const char* env = getenv("AA_BANDS_DECIMATION");
@@ -305,16 +307,19 @@ bool place_in_zone(const BandDev& b, int Mc, double freq_scale, BandDev* out) {
     return true;
 }
 
-// Largest decimation the requested fits tolerate.  T20 / T30 (>= 20 dB of a curve that starts at -5 dB) move by
-// <= 6e-4 relative at D = 16; a short or early range such as EDT (0 .. -10 dB) follows the 2 f ripple of a
-// low band's Schroeder curve and moves by up to 6e-3 at D = 16, 1.8e-3 at D = 8, 7e-4 at D <= 4
-// (tools/decimation_error.py), so such fits keep D <= 4.
+// Largest decimation the requested fits tolerate (tools/decimation_error.py against the oracle, tools/decimation_tail.py
+// over 4096 rows x 26 bands against the full-rate device path).  The sub-sampled Schroeder sum is off by a fraction
+// ~ D / (decay time in samples) of the local energy; a fit whose end points sit on the 2 f staircase of the curve can
+// then pick a neighbouring step.  Metrics outside the 0.5 % / 1 ms tolerance per 106,496:
+//   T30 (30 dB):  1 at D <= 4,  1 at D <= 8,  2 at D <= 16,  11 at D <= 24     -> D <= 16
+//   T20 (20 dB):  0 at D <= 4,  2 at D <= 8, 18 at D <= 16,  79 at D <= 24     -> D <= 4
+//   EDT (10 dB from 0 dB): worst 7e-4 at D <= 4, 6e-3 at D <= 16 (12 rows)     -> D <= 4
 int fit_decimation_limit(const aa_decay_params* p) {
     int lim = 16;
     if (!p) return lim;
     for (int f = 0; f < p->n_fits && f < AA_MAX_FITS; ++f) {
         const double hi = p->fit_hi_db[f], lo = fmax(p->fit_lo_db[f], p->fit_lower_limit_db);
-        if (hi > -2.5 || hi - lo < 15.0) lim = 4;
+        if (hi > -2.5 || hi - lo < 28.0) lim = 4;
     }
     return lim;
 }
@@ -322,7 +327,9 @@ int fit_decimation_limit(const aa_decay_params* p) {
 void classify_bands(const aa_bands_plan* plan, const std::vector<BandDev>& hb, int sample_rate_hz, double freq_scale,
                     bool metrics_only, const aa_decay_params* fits, std::vector<BandClass>* classes) {
     int tile_c = 0, n_tiles = 0, n_groups = 0;
-    const int max_d = std::min(band_decimation_limit(), fit_decimation_limit(fits));
+    // the setter / AA_BANDS_DECIMATION can lower the limit, or raise it to 24 for T30-only calls
+    const int fit_lim = fit_decimation_limit(fits);
+    const int max_d = (fit_lim >= 16) ? band_decimation_limit() : std::min(band_decimation_limit(), fit_lim);
     const bool can = (plan->n % 2) == 0 && metrics_only && c2c_energy_layout(plan->c2c, &tile_c, &n_tiles, &n_groups);
     BandClass by_d[aa_bands_plan::kDecims + 1];   // [0] full rate, [1 + c] plan->dec[c]
     for (size_t i = 0; i < hb.size(); ++i) {
@@ -540,10 +547,10 @@ int rt60bands_batch(const aa_bands_plan* plan, const float* d_x, long long row_s
                 const int M_c = bc.sub ? bc.sub->M : M;
                 const int ystride_c = bc.sub ? bc.sub->y_stride : plan->y_stride;
                 // nested stage timing per class (aa_profile_ms("band_class_d<D>")): the kernels inside keep their own scopes
-                static const char* const kClassNames[17] = {"", "band_class_d1", "band_class_d2", "band_class_d3",
-                                                            "band_class_d4", "", "", "", "band_class_d8", "", "", "",
-                                                            "", "", "", "", "band_class_d16"};
-                ProfScope class_prof(kClassNames[D <= 16 ? D : 0], stream);
+                static char class_names[kMaxBandDecimation + 1][24];
+                if (!class_names[1][0])
+                    for (int d = 0; d <= kMaxBandDecimation; ++d) snprintf(class_names[d], sizeof(class_names[d]), "band_class_d%d", d);
+                ProfScope class_prof(class_names[D <= kMaxBandDecimation ? D : 0], stream);
                 rc = store_band_table(bc.bands.data(), nbc, d_class_bands, stream);
                 if (rc != AA_OK) return rc;
                 SrcDesc s{};

@@ -29,7 +29,10 @@ constexpr int kTwoLevelShift = 10;
     X(10, 12, 15, 5, 15, 8) /* N =  18000 (288000 decimated by 16): M = 120 x 75 */ \
     X(10, 12, 4, 10, 10, 8) /* N =  24000 (192000 decimated by 8): M = 120 x 100 */ \
     X(10, 12, 10, 5, 10, 8) /* N =  12000 (192000 decimated by 16): M = 120 x 50 */ \
-    X(8, 20, 8, 10, 20, 8) /* N =  64000 (192000 decimated by 3): M = 160 x 200 */
+    X(8, 20, 8, 10, 20, 8) /* N =  64000 (192000 decimated by 3): M = 160 x 200 */ \
+    X(8, 20, 4, 10, 10, 8) /* N =  32000 (192000 decimated by 6): M = 160 x 100 */ \
+    X(8, 10, 4, 10, 10, 8) /* N =  16000 (192000 decimated by 12): M = 80 x 100 */ \
+    X(5, 8, 4, 10, 10, 8) /* N =   8000 (192000 decimated by 24): M = 40 x 100 */
 
 // Row lengths whose band stage may synthesise low bands on a decimated grid (bands.cu): the batch shapes the
 // approximation of the Schroeder sums was validated on (configs 3 and 5).  The sub-lengths in AA_REG_LIST are

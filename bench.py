@@ -215,7 +215,7 @@ def run_ours(args):
     stage_ms = {k: lib.aa_profile_ms(k.encode()) / args.steps for k in stage_names}
     stage_scopes = {k: int(lib.aa_profile_scopes(k.encode())) // args.steps for k in stage_names}
     # band stage per decimation class (nested scopes around the class's kernels)
-    class_ms = {f"D{d}": round(lib.aa_profile_ms(f"band_class_d{d}".encode()) / args.steps, 4) for d in (1, 2, 3, 4, 8, 16)}
+    class_ms = {f"D{d}": round(lib.aa_profile_ms(f"band_class_d{d}".encode()) / args.steps, 4) for d in (1, 2, 3, 4, 6, 8, 12, 16, 24)}
     class_ms = {k: v for k, v in class_ms.items() if v > 0.0}
     lib.aa_profile_enable(0)
     launches = (lib.aa_kernel_launch_count() - launches0) // max(1, args.steps)

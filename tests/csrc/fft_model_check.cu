@@ -665,7 +665,7 @@ int main() {
     check_chain<4>(4096, {8, 8, 8, 8});
     check_chain<0>(36, {6, 6});
     const int sizes[] = {1, 2, 3, 4, 5, 6, 7, 8, 11, 13, 16, 30, 64, 77, 143, 360, 1001, 2048,
-                         2304, 4096, 24000, 30000, 31200, 65536, 17, 397, 4099, 25011, 45001, 144000, 96000, 72000, 36000, 48000, 24000, 18000, 9000, 12000, 6000};
+                         2304, 4096, 24000, 30000, 31200, 65536, 17, 397, 4099, 25011, 45001, 144000, 96000, 72000, 36000, 48000, 24000, 18000, 9000, 12000, 6000, 16000, 8000, 4000};
     for (int M : sizes) check_c2c(M);
     const int real_sizes[] = {48000, 60000, 62400, 50022, 45001, 4410, 64, 1155};
     for (int N : real_sizes) check_real_band(N);
@@ -678,6 +678,12 @@ int main() {
     check_decimated_band(288000, 3, 10900.0, 11000.0, 777);    // zone 1 of 8 kHz (mirrored)
     check_decimated_band(288000, 4, 14400.0, 14500.0, 31);     // zone 2 of 6 kHz
     check_decimated_band(192000, 3, 6100.0, 6200.0, 5);        // zone 0, N / 3 = 64000
+    check_decimated_band(288000, 6, 5610.0, 5700.0, 4242);     // zone 1 of 4 kHz
+    check_decimated_band(288000, 12, 2820.0, 2900.0, 99);      // zone 1 of 2 kHz
+    check_decimated_band(288000, 24, 222.7, 280.6, 1234);
+    check_decimated_band(192000, 6, 2400.0, 2500.0, 8);
+    check_decimated_band(192000, 12, 1150.0, 1200.0, 70000);
+    check_decimated_band(192000, 24, 111.4, 140.3, 3);
     check_decimated_band(288000, 8, 111.4, 140.3, 20011);
     check_decimated_band(288000, 16, 157.5, 198.4, 13);
     check_decimated_band(192000, 8, 2227.0, 2300.0, 4321);

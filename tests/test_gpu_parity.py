@@ -334,7 +334,8 @@ def test_waterfall_errors():
 
 def test_band_decimation_against_oracle_and_switch():
     """N = 288000 / 192000 rows: the decimated band path (default) and the full-rate path both sit inside the RT60
-    tolerance of the oracle; aa_bands_set_decimation switches between them."""
+    tolerance of the oracle; aa_bands_set_decimation switches between them; calls that ask for T20 or EDT keep the
+    decimation at <= 4 (csrc/bands.cu: fit_decimation_limit)."""
     from audio_analysis_b200 import rt60bands as rb
     from audio_analysis_b200.synth import synth_batch_numpy
     lib = nat_lib()
@@ -343,37 +344,37 @@ def test_band_decimation_against_oracle_and_switch():
             x = synth_batch_numpy(2, n, SR, first_index=40)
             want = []
             for i in range(2):
-                ob = oracle.band_metrics(x[i], SR, oracle.BandParams(band_mode="third", include_t20=True))
+                ob = oracle.band_metrics(x[i], SR, oracle.BandParams(band_mode="third", include_t20=True, include_edt=True))
                 want.append(np.array([[np.nan if v is None else v for v in ob["metrics"][b["name"]]] for b in ob["bands"]]))
-            s = rb.Rt60BandsAnalysisSettings(band_mode="third", include_t20=True)
+            names = [b["name"] for b in ob["bands"]]
+            s30 = rb.Rt60BandsAnalysisSettings(band_mode="third")
+            bands = rb._build_band_definitions(s30, SR)
             got = {}
-            for max_d in (16, 8, 4, 2, 1):
+            for max_d in (24, 16, 8, 4, 2, 1):
                 lib.aa_bands_set_decimation(max_d)
                 assert lib.aa_bands_get_decimation() == max_d
-                res = rb.analyse_rt60_bands_batch(x, SR, ["a", "b"], s)
-                tab = np.array([[[np.nan if v is None else v for v in
-                                  (r.band_metrics_by_name[b.name].rt60_t30_seconds,
-                                   r.band_metrics_by_name[b.name].rt60_t20_seconds,
-                                   r.band_metrics_by_name[b.name].edt_seconds)] for b in r.band_definitions] for r in res])
+                dec = rb.decimation_classes(bands, n, SR, s30.transition_width_octaves, settings=s30)
+                assert max(dec) <= max_d and (max_d == 1 or max(dec) > 1)
+                res = rb.analyse_rt60_bands_batch(x, SR, ["a", "b"], s30)
+                tab = np.array([_band_table(r, names) for r in res])
                 got[max_d] = tab
                 for i in range(2):
-                    check_band_table(f"decim{max_d}/n{n}", tab[i][:, :2], want[i][:, :2])
-                    err = np.nanmax(np.abs(tab[i][:, :2] - want[i][:, :2]) / want[i][:, :2])
-                    note(f"band_rt60_rel_err[decimation<={max_d}]", err)
+                    check_band_table(f"decim{max_d}/n{n}", tab[i][:, :1], want[i][:, :1])
+                    err = np.nanmax(np.abs(tab[i][:, 0] - want[i][:, 0]) / want[i][:, 0])
+                    note(f"band_t30_rel_err[decimation<={max_d}]", err)
             assert not np.array_equal(got[16], got[1])     # the switch really changes the path
-            assert not np.array_equal(got[16], got[4])
-            # a call that also asks for EDT (0 .. -10 dB: short and early) keeps the decimation at <= 4 and every
-            # metric, EDT included, inside the tolerance
+            assert not np.array_equal(got[16], got[4]) and not np.array_equal(got[24], got[16])
+            # T20 (20 dB) and EDT (10 dB from 0 dB) follow the staircase of a low band's curve more closely: such
+            # calls stay at D <= 4 whatever the limit, and every metric stays inside the tolerance
             lib.aa_bands_set_decimation(16)
-            se = rb.Rt60BandsAnalysisSettings(band_mode="third", include_t20=True, include_edt=True)
-            bands = rb._build_band_definitions(se, SR)
-            assert max(rb.decimation_classes(bands, n, SR, se.transition_width_octaves, settings=se)) == 4
-            assert max(rb.decimation_classes(bands, n, SR, s.transition_width_octaves, settings=s)) == 16
-            res = rb.analyse_rt60_bands_batch(x, SR, ["a", "b"], se)
-            for i in range(2):
-                ob = oracle.band_metrics(x[i], SR, oracle.BandParams(band_mode="third", include_t20=True, include_edt=True))
-                w = np.array([[np.nan if v is None else v for v in ob["metrics"][b["name"]]] for b in ob["bands"]])
-                check_band_table(f"decim_edt/n{n}", _band_table(res[i], [b["name"] for b in ob["bands"]]), w)
+            for se in (rb.Rt60BandsAnalysisSettings(band_mode="third", include_t20=True),
+                       rb.Rt60BandsAnalysisSettings(band_mode="third", include_t20=True, include_edt=True)):
+                assert max(rb.decimation_classes(bands, n, SR, se.transition_width_octaves, settings=se)) == 4
+                res = rb.analyse_rt60_bands_batch(x, SR, ["a", "b"], se)
+                cols = 3 if se.include_edt else 2
+                for i in range(2):
+                    check_band_table(f"decim_t20_edt/n{n}", _band_table(res[i], names)[:, :cols], want[i][:, :cols])
+            assert max(rb.decimation_classes(bands, n, SR, s30.transition_width_octaves, settings=s30)) == 16
     finally:
         lib.aa_bands_set_decimation(16)
 
@@ -639,7 +640,7 @@ def test_full_size_properties_config5_rows():
     assert np.array_equal(np.isnan(full), np.isnan(dec))
     rel = np.nanmax(np.abs(dec - full) / full)
     note("band_rt60_decimated_vs_full_rel", rel)
-    assert rel <= 2e-3
+    assert rel <= 5e-3
 
 
 def test_host_streaming_pipeline_equals_resident_batch():

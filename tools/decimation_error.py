@@ -9,22 +9,28 @@ import audio_analysis_b200._native as nat
 lib = nat.load()
 SR=48000
 for n in (288000, 192000):
-    R=12
+    R = 16
     x = synth_batch_numpy(R, n, SR, first_index=100)
-    want=[]
+    want = []
     for i in range(R):
         ob = oracle.band_metrics(x[i], SR, oracle.BandParams(band_mode="third", include_t20=True, include_edt=True))
         want.append(np.array([[np.nan if v is None else v for v in ob["metrics"][b["name"]]] for b in ob["bands"]]))
-    want=np.array(want)
-    s = rb.Rt60BandsAnalysisSettings(band_mode="third", include_t20=True, include_edt=True)
-    for max_d in (1,2,3,4,8,16):
-        lib.aa_bands_set_decimation(max_d)
-        res = rb.analyse_rt60_bands_batch(x, SR, [str(i) for i in range(R)], s)
-        tab = np.array([[[np.nan if v is None else v for v in (r.band_metrics_by_name[b.name].rt60_t30_seconds, r.band_metrics_by_name[b.name].rt60_t20_seconds, r.band_metrics_by_name[b.name].edt_seconds)] for b in r.band_definitions] for r in res])
-        err = np.abs(tab - want) / want
-        errs = np.abs(tab - want)
-        ok = (err <= 5e-3) | (errs <= 1e-3) | (np.isnan(tab) & np.isnan(want))
-        nanmis = int((np.isnan(tab) != np.isnan(want)).sum())
-        print(n, 'max_d', max_d, 'worst rel T30/T20/EDT', np.array2string(np.nanmax(err, axis=(0, 1)), precision=2),
-              'outside tolerance', int((~ok).sum()), 'nan mismatch', nanmis)
-        print('   EDT per band max:', np.array2string(np.nanmax(err[:, :, 2], axis=0), precision=1, max_line_width=400))
+    want = np.array(want)
+    for with_edt in (False, True):   # a call that asks for EDT keeps D <= 4 (bands.cu: fit_decimation_limit)
+        s = rb.Rt60BandsAnalysisSettings(band_mode="third", include_t20=True, include_edt=with_edt)
+        cols = 3 if with_edt else 2
+        for max_d in (1, 4, 8, 12, 16, 24):
+            lib.aa_bands_set_decimation(max_d)
+            res = rb.analyse_rt60_bands_batch(x, SR, [str(i) for i in range(R)], s)
+            tab = np.array([[[np.nan if v is None else v for v in
+                              (r.band_metrics_by_name[b.name].rt60_t30_seconds, r.band_metrics_by_name[b.name].rt60_t20_seconds,
+                               r.band_metrics_by_name[b.name].edt_seconds)][:cols] for b in r.band_definitions] for r in res])
+            w = want[:, :, :cols]
+            err = np.abs(tab - w) / w
+            ok = (err <= 5e-3) | (np.abs(tab - w) <= 1e-3) | (np.isnan(tab) & np.isnan(w))
+            dec = rb.decimation_classes(res[0].band_definitions, n, SR, s.transition_width_octaves, settings=s)
+            print(n, "edt" if with_edt else "t20", "max_d", max_d, "classes", sorted(set(dec)), "worst rel per metric",
+                  np.array2string(np.nanmax(err, axis=(0, 1)), formatter={"float_kind": lambda v: "%.2e" % v}),
+                  "outside tolerance", int((~ok).sum()), "nan mismatch", int((np.isnan(tab) != np.isnan(w)).sum()))
+            print("   T30 per band max:", np.array2string(np.nanmax(err[:, :, 0], axis=0), precision=1, max_line_width=400))
+lib.aa_bands_set_decimation(16)
