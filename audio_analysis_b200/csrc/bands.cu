@@ -67,22 +67,33 @@ __global__ void untangle_kernel(const float2* __restrict__ Z, float2* __restrict
                                 TwoLevelTwiddle twN, const int* __restrict__ advance) {
     // advance != NULL: the half spectrum is stored time-advanced by advance[row] samples,
     // X'[k] = X[k] exp(+2 pi i k s / N), i.e. the row circularly rotated so that its analysis start sits at
-    // sample 0 - every band signal synthesised from it starts at the analysis start (decimation classes)
+    // sample 0 - every band signal synthesised from it starts at the analysis start (decimation classes).
+    // A thread makes the PAIR X[k], X[M - k] from one load of Z[k] and Z[M - k] (the packed spectrum is read once):
+    // w(M - k) = -conj(w(k)), and ((M - k) s) mod N = (M s mod N) - (k s mod N).
     const long long row = blockIdx.y;
     const float2* __restrict__ z = Z + row * (long long)M;
     float2* __restrict__ o = X + row * (long long)x_stride;
     const int s = advance ? advance[row] : 0;
     const long long N = 2LL * M;
+    const long long half_turn = (s & 1) ? M : 0;   // (M s) mod N
     // (k s) mod N advances by a constant per grid stride: one 64-bit reduction per thread, adds afterwards
     const long long stride = (long long)gridDim.x * blockDim.x;
     long long r = ((long long)(blockIdx.x * blockDim.x + threadIdx.x) * (long long)s) % N;
     const long long dr = (stride * (long long)s) % N;
-    for (int k = blockIdx.x * blockDim.x + threadIdx.x; k <= M; k += (int)stride) {
-        const int km = (k == M) ? 0 : k;
-        const int mk = (k == 0) ? 0 : M - k;
-        float2 v = untangle_half_spectrum(__ldg(z + km), __ldg(z + mk), twiddle2(twN, k));
-        if (s != 0) v = cmulc(v, twiddle2(twN, r));
-        o[k] = v;
+    for (int k = blockIdx.x * blockDim.x + threadIdx.x; 2 * k <= M; k += (int)stride) {
+        const int mk = M - k;                       // k = 0 pairs bin 0 with bin M, both from Z[0]
+        const float2 zk = __ldg(z + k), zm = __ldg(z + (k == 0 ? 0 : mk));
+        const float2 w = twiddle2(twN, k);
+        float2 a = untangle_half_spectrum(zk, zm, w);
+        float2 b = untangle_half_spectrum(zm, zk, make_float2(-w.x, w.y));
+        if (s != 0) {
+            long long rm = half_turn - r;
+            if (rm < 0) rm += N;
+            a = cmulc(a, twiddle2(twN, r));
+            b = cmulc(b, twiddle2(twN, rm));
+        }
+        o[k] = a;
+        o[mk] = b;
         r += dr;
         if (r >= N) r -= N;
     }
@@ -521,7 +532,7 @@ int rt60bands_batch(const aa_bands_plan* plan, const float* d_x, long long row_s
             s.n_valid = N;
             rc = c2c_exec(plan->c2c, s, make_dst_complex(d_Z, M, M, 0, 1.0f), rows, d_scr, stream);
             if (rc != AA_OK) return rc;
-            dim3 grid((unsigned)((M + 1 + 255) / 256 > 72 ? 72 : (M + 1 + 255) / 256), (unsigned)rows);  // ~8 bins per thread: amortises the index set-up
+            dim3 grid((unsigned)((M / 2 + 1 + 255) / 256 > 36 ? 36 : (M / 2 + 1 + 255) / 256), (unsigned)rows);  // ~8 pairs per thread: amortises the index set-up
             ProfScope prof("untangle", stream);
             untangle_kernel<<<grid, 256, 0, stream>>>(d_Z, d_X, M, plan->x_stride, plan->twN.dev,
                                                       one_class ? nullptr : d_start_idx + r0);
