@@ -273,7 +273,7 @@ def run_ours(args):
                 "ms_per_launch": round(dk["ms"] / max(1, dk["launches_per_step"]), 4),
                 "peak": peak, "peak_source": peak_src, "unit": "GB/s",
                 "algorithmic_bytes_per_launch": dk["algorithmic_bytes_per_step"] / max(1, dk["launches_per_step"]),
-                "traffic": None, "share_of_step": dk["share_of_step"],
+                "traffic": traffic, "traffic_source": traffic_note, "share_of_step": dk["share_of_step"],
                 "note": "dominant kernel by device time inside the timed region; the band stage as a whole has 4 B/sample "
                         "of algorithmic traffic (SURVEY 8d) and is bound by fp32 issue, not HBM (SURVEY D7): see "
                         "roofline_by_kernel"}
@@ -358,7 +358,7 @@ def run_ours(args):
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         cores = host_cores()
-        sample = max(8, min(cores, 64))
+        sample = max(8, 4 * min(cores, 64))   # ~25 s of CPU work: four IRs per core
         sample_rows = x_dev[:sample].cpu().numpy()
         v, wall = cpu_throughput(sample_rows, cores=min(cores, sample))
         cpu = {"value": round(v, 2), "unit": UNIT, "cores": min(cores, sample), "kind": "port",
@@ -401,7 +401,7 @@ def run_reference(args):
     from audio_analysis_b200.synth import synth_batch_numpy
 
     cores = host_cores()
-    sample = max(8, min(cores, 64))
+    sample = max(8, 4 * min(cores, 64))   # four IRs per core and step
     rows = synth_batch_numpy(sample, int(args.samples), SR)
     import multiprocessing as mp
 
