@@ -22,14 +22,14 @@ constexpr int kTwoLevelShift = 10;
     X(18, 20, 8, 20, 20, 8) /* N = 288000: M = 360 x 400 (400 x 360 with rows in groups of 16 measured 10 % slower) */ \
     X(12, 20, 8, 20, 20, 8) /* N = 192000: M = 240 x 400 */ \
     X(18, 20, 8, 10, 20, 8) /* N = 144000 (288000 decimated by 2): M = 360 x 200 */ \
-    X(10, 20, 4, 12, 15, 8) /* N =  72000 (288000 decimated by 4): M = 200 x 180 */ \
-    X(12, 20, 8, 10, 20, 8) /* N =  96000 (192000 decimated by 2): M = 240 x 200 */ \
+    X(10, 12, 10, 15, 20, 8) /* N =  72000 (288000 decimated by 4): M = 120 x 300 */ \
+    X(10, 12, 8, 20, 20, 8) /* N =  96000 (288000 / 3, 192000 / 2): M = 120 x 400 - short columns: the issue-bound pass does less, the memory-bound rows pass more */ \
     X(10, 12, 8, 10, 20, 8) /* N =  48000 (192000 decimated by 4): M = 120 x 200 */ \
     X(10, 12, 10, 10, 15, 8) /* N =  36000 (288000 decimated by 8): M = 120 x 150 */ \
     X(5, 8, 15, 15, 15, 8) /* N =  18000 (288000 decimated by 16): M = 40 x 225 (120 x 75 left 40 of 128 threads busy in the rows pass) */ \
     X(10, 12, 4, 10, 10, 8) /* N =  24000 (192000 decimated by 8): M = 120 x 100 */ \
     X(5, 8, 15, 10, 15, 8) /* N =  12000 (192000 decimated by 16): M = 40 x 150 */ \
-    X(8, 20, 8, 10, 20, 8) /* N =  64000 (192000 decimated by 3): M = 160 x 200 */ \
+    X(8, 10, 8, 20, 20, 8) /* N =  64000 (192000 decimated by 3): M = 80 x 400 */ \
     X(8, 20, 4, 10, 10, 8) /* N =  32000 (192000 decimated by 6): M = 160 x 100 */ \
     X(8, 10, 4, 10, 10, 8) /* N =  16000 (192000 decimated by 12): M = 80 x 100 */ \
     X(5, 8, 4, 10, 10, 8) /* N =   8000 (192000 decimated by 24): M = 40 x 100 */

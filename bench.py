@@ -268,6 +268,18 @@ def run_ours(args):
                         "algorithmic_bytes_per_step": nbytes, "share_of_step": round(stage_ms[k] / ms_step, 4)}
     dominant = max(by_kernel, key=lambda k: by_kernel[k]["ms"])
     dk = by_kernel[dominant]
+    # DRAM bytes the kernel really moved, from the committed ncu --set full capture (per analysed row), scaled to the
+    # rows one launch of this run processes; null when the capture is missing or does not cover the stage
+    traffic = None
+    traffic_note = None
+    try:
+        tj = json.loads((Path(__file__).resolve().parent / "profiles" / "r01_traffic.json").read_text())
+        per_row = tj["stages"][dominant]["dram_bytes_per_row"]
+        traffic = round(per_row * rows_n / max(1, stage_scopes[dominant]), 1)
+        traffic_note = (f"profiles/r01_traffic.json: {per_row:.0f} B of DRAM traffic per row for this stage "
+                        f"({tj['stages'][dominant]['kernels']} kernels, {tj['rows']}-row capture) x rows / launches")
+    except Exception:
+        pass
     roofline = {"bound": "hbm", "kernel": dk["kernel"], "stage": dominant, "achieved": dk["achieved"], "frac": dk["frac"],
                 "ms": dk["ms"], "launches_per_step": dk["launches_per_step"],
                 "ms_per_launch": round(dk["ms"] / max(1, dk["launches_per_step"]), 4),
