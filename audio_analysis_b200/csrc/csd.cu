@@ -280,7 +280,7 @@ struct TmaCfg {
     static constexpr int kNfft = 2 * M;
     static constexpr int kRawFloats = kNfft + 8;                 // aligned superset of a frame
     static constexpr int kFftElems = M + (M >> kTmaPad);         // padded complex buffer
-    static constexpr size_t kRawBytes = sizeof(float) * 2 * (size_t)kRawFloats;
+    static constexpr size_t kRawBytes = sizeof(float) * (size_t)kRawFloats;   // ONE staging buffer: 72 KB per CTA, three CTAs per SM
     static constexpr size_t kFftBytes = sizeof(float2) * 2 * (size_t)kFftElems;
     static size_t smem_bytes(int n_bins) {
         return kRawBytes + kFftBytes + sizeof(float) * (size_t)kTmaFramesPerCta * (size_t)((n_bins + 3) & ~3);
@@ -295,12 +295,12 @@ __global__ void __launch_bounds__(kCsdThreads) csd_tma_kernel(CsdArgs a) {
     const int rank = (int)cluster.block_rank();
     const int row = blockIdx.x / C;
     extern __shared__ __align__(16) unsigned char dyn_smem[];
-    float* raw = reinterpret_cast<float*>(dyn_smem);                       // [2][kRawFloats]
+    float* raw = reinterpret_cast<float*>(dyn_smem);                       // [kRawFloats]
     float2* fa = reinterpret_cast<float2*>(dyn_smem + Cfg::kRawBytes);   // [kFftElems]
     float2* fb = fa + Cfg::kFftElems;
     float* outs = reinterpret_cast<float*>(dyn_smem + Cfg::kRawBytes + Cfg::kFftBytes);
     const int out_pitch = (a.n_bins + 3) & ~3;
-    __shared__ unsigned long long bars[2];
+    __shared__ unsigned long long bars[1];
     __shared__ float red[kCsdThreads / 32];
     __shared__ float cta_max;
     __shared__ float slice_ref[kTmaFramesPerCta];
@@ -313,35 +313,37 @@ __global__ void __launch_bounds__(kCsdThreads) csd_tma_kernel(CsdArgs a) {
     const int n_mine = (ns > rank) ? (ns - rank + C - 1) / C : 0;   // slices rank, rank + C, ...
 
     auto frame_start = [&](int i) { return start + a.frame_idx[(long long)row * a.max_slices + rank + i * C] * a.hop; };
-    // thread 0 stages frame i into ring slot i & 1 (bulk copy when the aligned superset lies inside the row)
+    // thread 0 stages frame i into the staging buffer (bulk copy when the aligned superset lies inside the row); the
+    // copy of frame i + 1 is issued as soon as frame i has been windowed into the FFT buffer, so it lands during the
+    // transform of frame i (a second staging buffer would cost the third resident CTA per SM)
     auto stage_frame = [&](int i) {
         const int f0 = frame_start(i);
         const int a0 = f0 & ~3;
         const int nvec = (Cfg::kNfft + (f0 - a0) + 3) >> 2;
         if (f0 >= 0 && a0 + 4 * nvec <= len4) {
-            mbar_expect_tx(&bars[i & 1], 16u * (unsigned)nvec);
-            bulk_g2s(raw + (i & 1) * Cfg::kRawFloats, x + a0, 16u * (unsigned)nvec, &bars[i & 1]);
+            mbar_expect_tx(&bars[0], 16u * (unsigned)nvec);
+            bulk_g2s(raw, x + a0, 16u * (unsigned)nvec, &bars[0]);
         }
     };
     if (threadIdx.x == 0) {
         mbar_init(&bars[0], 1);
-        mbar_init(&bars[1], 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         if (n_mine > 0) stage_frame(0);
-        if (n_mine > 1) stage_frame(1);
     }
     __syncthreads();
 
     float run_max = -INFINITY;
+    int bulk_phase = 0;   // completed bulk copies on bars[0]: frames that took the guarded-load path do not use it
     for (int i = 0; i < n_mine; ++i) {
         const int f0 = frame_start(i);
         const int a0 = f0 & ~3;
         const int shift = f0 - a0;
         const int nvec = (Cfg::kNfft + shift + 3) >> 2;
-        float* rb = raw + (i & 1) * Cfg::kRawFloats;
+        float* rb = raw;
         if (f0 >= 0 && a0 + 4 * nvec <= len4) {
-            mbar_wait(&bars[i & 1], (unsigned)((i >> 1) & 1));
+            mbar_wait(&bars[0], (unsigned)(bulk_phase & 1));
+            ++bulk_phase;
         } else {  // frame sticks out of the row (not produced by the host-side frame selection): guarded loads
             for (int q = threadIdx.x; q < nvec; q += kCsdThreads) {
                 const int g = a0 + 4 * q;
@@ -363,10 +365,10 @@ __global__ void __launch_bounds__(kCsdThreads) csd_tma_kernel(CsdArgs a) {
             }
             fa[pad_index<kTmaPad>(m)] = make_float2(x0, x1);
         }
-        __syncthreads();  // ring slot consumed
-        if (threadIdx.x == 0 && i + 2 < n_mine) {
+        __syncthreads();  // staging buffer consumed
+        if (threadIdx.x == 0 && i + 1 < n_mine) {
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic reads before the async overwrite
-            stage_frame(i + 2);
+            stage_frame(i + 1);
         }
         float2* pa = fa;
         float2* pb = fb;
