@@ -7,7 +7,7 @@
 // sample, a level crossing (decay.py:173-199) or fit points (decay.py:224-249) are read again at sample
 // resolution - about a tenth of the signal - instead of streaming it twice as the general kernel (edc.cu) does.
 //
-// One CTA of 8 warps per (row, band) unit.  Semantics are those of edc.cu / edc_body.cuh: float32 squares and
+// One CTA of 4 warps per (row, band) unit (kFitThreads).  Semantics are those of edc.cu / edc_body.cuh: float32 squares and
 // in-tile sums, float64 carries, float32 dB curve and times, first sample <= target, fit mask on float32 times,
 // closed-form least squares in float64 (fit_math.cuh).
 #include "edc_body.cuh"
@@ -25,7 +25,10 @@ using edc::ScanMasks;
 using edc::make_scan_masks;
 using edc::to_db;
 
-constexpr int kFitThreads = 256;
+#ifndef AA_FIT_THREADS
+#define AA_FIT_THREADS 128
+#endif
+constexpr int kFitThreads = AA_FIT_THREADS;
 constexpr int kFitWarps = kFitThreads / 32;
 constexpr int kSub = 128;     // samples per warp step: one float4 per lane
 constexpr int kMaxSub = 8;    // tile length <= 1024 samples
@@ -93,10 +96,11 @@ __device__ __forceinline__ void visit_tile_reverse(const float* __restrict__ y, 
 }
 
 template <int NS>
-// five resident CTAs per SM (48 registers per thread, a few hundred bytes of spills): the kernel is a chain of short
-// phases separated by barriers, and more CTAs in flight hide them - 8.05 -> 6.83 ms per 8192 rows x 26 bands
+// ten resident CTAs of four warps per SM (48 registers per thread, a few hundred bytes of spills): the kernel is a
+// chain of short phases separated by barriers, and more, smaller CTAs in flight hide them - per 8192 rows x 26 bands
+// 8.05 ms (256 threads, 3 CTAs) -> 6.83 (256 x 5) -> 4.29 ms (128 x 10)
 #ifndef AA_FIT_MIN_BLOCKS
-#define AA_FIT_MIN_BLOCKS 5
+#define AA_FIT_MIN_BLOCKS 10
 #endif
 __global__ void __launch_bounds__(kFitThreads, AA_FIT_MIN_BLOCKS) band_fit_kernel(BandFitArgs a) {
     extern __shared__ __align__(16) unsigned char dyn_smem[];

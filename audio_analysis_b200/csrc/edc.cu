@@ -41,7 +41,7 @@ namespace {
 using namespace edc;
 
 template <bool kWriteDb>
-__global__ void __launch_bounds__(kThreads, 2) edc_kernel(EdcArgs a) {
+__global__ void __launch_bounds__(kThreads, 1024 / kThreads) edc_kernel(EdcArgs a) {
     extern __shared__ __align__(16) unsigned char dyn_smem[];
     __shared__ CtaShared sh;
     const int T = (int)cg::this_cluster().num_blocks();
