@@ -372,25 +372,30 @@ bool launch_cols_reg(const C2CPlan* p, const SrcDesc& src, float2* scratch, long
     return false;
 }
 
+#ifndef AA_ROWS_PLAIN_G
+#define AA_ROWS_PLAIN_G 4   /* 96-thread CTAs, 12 per SM: 5.53 -> 5.11 ms per 8192 forward transforms against groups of 8 */
+#endif
 bool launch_rows_reg(const C2CPlan* p, const float2* scratch, const DstDesc& dst, long long units, cudaStream_t stream) {
 #define X(ra1, rb1, g1, ra2, rb2, g2)                                                                         \
     if (p->M1 == ra1 * rb1 && p->M2 == ra2 * rb2) {                                                           \
         using P = RegCfg<ra2, rb2, g2>;                                                                       \
+        /* plain variant (forward transforms, band signals on request): AA_ROWS_PLAIN_G rows per CTA */      \
+        constexpr int gp = ((ra1 * rb1) % AA_ROWS_PLAIN_G == 0) ? AA_ROWS_PLAIN_G : g2;                       \
+        using PP = RegCfg<ra2, rb2, gp>;                                                                      \
         static bool once = false;                                                                             \
         if (!once) {                                                                                          \
-            cudaFuncSetAttribute(fft_rows_reg<P, ra1 * rb1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
-                                 (int)P::kSmemBytes);                                                         \
+            cudaFuncSetAttribute(fft_rows_reg<PP, ra1 * rb1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                                 (int)PP::kSmemBytes);                                                        \
             cudaFuncSetAttribute(fft_rows_reg<P, ra1 * rb1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
                                  (int)P::kSmemBytes);                                                         \
             once = true;                                                                                      \
         }                                                                                                     \
-        const unsigned grid = (unsigned)(units * ((ra1 * rb1) / g2));                                         \
         if (dst.energy)                                                                                       \
-            fft_rows_reg<P, ra1 * rb1, true><<<grid, P::kThreads, P::kSmemBytes, stream>>>(                   \
+            fft_rows_reg<P, ra1 * rb1, true><<<(unsigned)(units * ((ra1 * rb1) / g2)), P::kThreads, P::kSmemBytes, stream>>>( \
                 scratch, (float2*)dst.base, dst.unit_stride, dst.n_valid, dst.conj1, dst.scale1, p->s2.dev.tw, \
                 dst.energy, dst.energy_stride);                                                               \
         else                                                                                                  \
-            fft_rows_reg<P, ra1 * rb1, false><<<grid, P::kThreads, P::kSmemBytes, stream>>>(                  \
+            fft_rows_reg<PP, ra1 * rb1, false><<<(unsigned)(units * ((ra1 * rb1) / gp)), PP::kThreads, PP::kSmemBytes, stream>>>( \
                 scratch, (float2*)dst.base, dst.unit_stride, dst.n_valid, dst.conj1, dst.scale1, p->s2.dev.tw, \
                 nullptr, 0);                                                                                  \
         return true;                                                                                          \
