@@ -20,6 +20,10 @@
 #include "fft_access.cuh"
 #include "fft_radix.cuh"
 
+#ifndef AA_BAND_SRC_SINGLE_RA
+#define AA_BAND_SRC_SINGLE_RA 5
+#endif
+
 namespace aa {
 
 template <int RA_, int RB_, int G_, int TP_>
@@ -158,8 +162,12 @@ struct RegSrcBand {
         // groups), inside a group everything is branch-free so that its loads are in flight together.
         const float2 w0 = twiddle2(twN, base);
         const unsigned bits = bits_k | bits_m;
-        static_for<0, (RA + 3) / 4>([&](auto c_) {
-            constexpr int lo = 4 * decltype(c_)::value, hi = (lo + 4 < RA) ? lo + 4 : RA;
+        // group length: 4 for the long butterflies (wide bands: most inputs are in the support, batching the loads
+        // pays), 1 for radix <= AA_BAND_SRC_SINGLE_RA (the deep-decimation classes hold narrow bands: one or two
+        // inputs of a butterfly are in the support, and a group of four would build three zeros around each)
+        constexpr int kGroup = (RA <= AA_BAND_SRC_SINGLE_RA) ? 1 : 4;
+        static_for<0, (RA + kGroup - 1) / kGroup>([&](auto c_) {
+            constexpr int lo = kGroup * decltype(c_)::value, hi = (lo + kGroup < RA) ? lo + kGroup : RA;
             if ((bits >> lo) & ((1u << (hi - lo)) - 1u)) {
                 static_for<lo, hi>([&](auto r_) {
                     constexpr int r = decltype(r_)::value;
