@@ -18,6 +18,9 @@ constexpr int kTwoLevelShift = 10;
 
 // (M1 = RA1 * RB1, M2 = RA2 * RB2) splits served by the two-stage register-resident kernels of fft.cu
 // (fft_reg.cuh): X(RA1, RB1, G1, RA2, RB2, G2).  host_direct_plan() prefers these splits.
+#ifndef AA_D16_G1
+#define AA_D16_G1 15
+#endif
 #define AA_REG_LIST(X)                                        \
     X(18, 20, 8, 20, 20, 8) /* N = 288000: M = 360 x 400 (400 x 360 with rows in groups of 16 measured 10 % slower) */ \
     X(12, 20, 8, 20, 20, 8) /* N = 192000: M = 240 x 400 */ \
@@ -26,7 +29,7 @@ constexpr int kTwoLevelShift = 10;
     X(10, 12, 8, 20, 20, 8) /* N =  96000 (288000 / 3, 192000 / 2): M = 120 x 400 - short columns: the issue-bound pass does less, the memory-bound rows pass more */ \
     X(10, 12, 8, 10, 20, 8) /* N =  48000 (192000 decimated by 4): M = 120 x 200 */ \
     X(10, 12, 10, 10, 15, 8) /* N =  36000 (288000 decimated by 8): M = 120 x 150 */ \
-    X(5, 8, 15, 15, 15, 8) /* N =  18000 (288000 decimated by 16): M = 40 x 225 (120 x 75 left 40 of 128 threads busy in the rows pass) */ \
+    X(5, 8, AA_D16_G1, 15, 15, 8) /* N =  18000 (288000 decimated by 16): M = 40 x 225 (120 x 75 left 40 of 128 threads busy in the rows pass) */ \
     X(10, 12, 4, 10, 10, 8) /* N =  24000 (192000 decimated by 8): M = 120 x 100 */ \
     X(5, 8, 15, 10, 15, 8) /* N =  12000 (192000 decimated by 16): M = 40 x 150 */ \
     X(8, 10, 8, 20, 20, 8) /* N =  64000 (192000 decimated by 3): M = 80 x 400 */ \
