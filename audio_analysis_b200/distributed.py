@@ -36,6 +36,35 @@ def init_from_env(backend: Optional[str] = None) -> Tuple[int, int, int]:
     return rank, size, local
 
 
+def _parse_cpulist(text: str) -> List[int]:
+    cpus: List[int] = []
+    for part in text.strip().split(","):
+        if not part:
+            continue
+        lo, _, hi = part.partition("-")
+        cpus.extend(range(int(lo), int(hi or lo) + 1))
+    return cpus
+
+
+def bind_host_to_gpu(device) -> Optional[List[int]]:
+    """Pin this process to the CPUs that sit next to `device` (its PCIe root's NUMA node), so that the pinned staging
+    buffers it allocates afterwards are local to the GPU's copy engine.  With one process per GPU on a two-socket box
+    the host-to-device streams otherwise cross the socket interconnect.  Returns the CPU list, or None when the
+    topology cannot be read (then nothing is changed)."""
+    try:
+        props = torch.cuda.get_device_properties(device)
+        bdf = "%04x:%02x:%02x.0" % (props.pci_domain_id, props.pci_bus_id, props.pci_device_id)
+        with open(f"/sys/bus/pci/devices/{bdf}/local_cpulist") as f:
+            cpus = _parse_cpulist(f.read())
+        allowed = sorted(set(cpus) & set(os.sched_getaffinity(0)))
+        if not allowed:
+            return None
+        os.sched_setaffinity(0, allowed)
+        return allowed
+    except (AttributeError, OSError, ValueError):
+        return None
+
+
 def shard_range(n_items: int, rank: int, world_size: int) -> Tuple[int, int]:
     """Contiguous block [begin, end) of item indices owned by `rank`: ceil(n / world) per rank."""
     per = (int(n_items) + world_size - 1) // world_size

@@ -114,6 +114,16 @@ class ClockSampler:
         for line in self.proc.stdout:
             self.lines.append(line.strip())
 
+    def wait_ready(self, timeout_s=8.0):
+        """Block until the first sample has arrived (nvidia-smi takes a second or more to start on an 8-GPU box)."""
+        t0 = time.perf_counter()
+        while self.proc is not None and not self.lines and time.perf_counter() - t0 < timeout_s:
+            time.sleep(0.02)
+
+    def mark(self):
+        """Samples from here on belong to the timed region."""
+        self.first = len(self.lines)
+
     def stop(self):
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
@@ -124,7 +134,13 @@ class ClockSampler:
             self.proc.kill()
         sm, smax, power, reasons = [], [], [], set()
         names = ("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap")
-        for line in self.lines:
+        # samples of the timed region; a region shorter than the 100 ms sampling period falls back to the samples
+        # taken under the same load during the warm-up steps (and says so)
+        window = self.lines[getattr(self, "first", 0):]
+        source = "timed region"
+        if not window:
+            window, source = self.lines, "warm-up + timed region (timed region shorter than the sampling period)"
+        for line in window:
             parts = [p.strip() for p in line.split(",")]
             if len(parts) < 9:
                 continue
@@ -140,7 +156,7 @@ class ClockSampler:
         if not sm:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
         return {"sm_mhz": statistics.median(sm), "sm_max_mhz": max(smax), "power_w_max": max(power),
-                "samples": len(sm), "reasons": sorted(reasons)}
+                "samples": len(sm), "sampled_during": source, "reasons": sorted(reasons)}
 
 
 # ----------------------------------------------------------------------------------------------
@@ -173,6 +189,11 @@ def run_ours(args):
         print(f"note: --gpus {args.gpus} but WORLD_SIZE={world}", file=sys.stderr)
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    # one process per GPU: keep the process (and the pinned staging buffers it allocates) on the GPU's NUMA node.
+    # Not at N = 1, where the CPU baseline below wants every host core.
+    numa_cpus = None
+    if world > 1 and not os.environ.get("AA_BENCH_NO_NUMA"):
+        numa_cpus = distributed.bind_host_to_gpu(dev)
     lib = nat.load()
     rows_n = int(args.rows)
     n = int(args.samples)
@@ -194,15 +215,17 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
+    sampler = ClockSampler(local)
+    sampler.start()
+    sampler.wait_ready()
     for _ in range(max(3, args.warmup)):
         out = step_device()
     barrier()
     launches0 = lib.aa_kernel_launch_count()
-    sampler = ClockSampler(local)
-    sampler.start()
     lib.aa_profile_enable(1)   # CUDA events around every library kernel, on the launching stream
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
+    sampler.mark()
     e0.record()
     for _ in range(args.steps):
         out = step_device()
@@ -389,6 +412,7 @@ def run_ours(args):
                        "band_decimation": {"max": int(lib.aa_bands_get_decimation()), "ms_per_class": class_ms,
                                            "bands_per_factor": {str(d): dec.count(d) for d in sorted(set(dec))}},
                        "l2": "inputs (rows*samples*4 B per GPU) are larger than L2; no flush needed"},
+            "host_binding": (f"{len(numa_cpus)} CPUs local to the GPU" if numa_cpus else None),
             "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
             "roofline": roofline, "roofline_by_kernel": by_kernel, "cpu_baseline": cpu,
             "gather_ms": gather_ms,
@@ -449,7 +473,7 @@ def run_reference(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
     ap.add_argument("--rows", type=int, default=int(os.environ.get("AA_BENCH_ROWS", "8192")),
