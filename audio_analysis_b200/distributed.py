@@ -61,7 +61,7 @@ def bind_host_to_gpu(device) -> Optional[List[int]]:
             return None
         os.sched_setaffinity(0, allowed)
         return allowed
-    except (AttributeError, OSError, ValueError):
+    except (AttributeError, OSError, ValueError, RuntimeError, AssertionError):   # no CUDA, no sysfs entry, old torch
         return None
 
 

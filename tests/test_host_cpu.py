@@ -225,6 +225,19 @@ def _gloo_worker(rank, world, port, q):
     dist.destroy_process_group()
 
 
+def test_host_binding_helpers_without_a_device():
+    """distributed.bind_host_to_gpu: cpulist parsing, and no change of affinity when the topology cannot be read."""
+    import os
+    from audio_analysis_b200 import distributed
+    assert distributed._parse_cpulist("0-3,8,10-11\n") == [0, 1, 2, 3, 8, 10, 11]
+    assert distributed._parse_cpulist("") == []
+    before = os.sched_getaffinity(0)
+    import torch
+    if not torch.cuda.is_available():
+        assert distributed.bind_host_to_gpu("cuda:0") is None   # no device: nothing is read, nothing is changed
+    assert os.sched_getaffinity(0) == before
+
+
 def test_metric_tables_gather_over_gloo_world_size_2():
     """The multi-GPU path's only collective, on CPU with gloo."""
     import torch.multiprocessing as mp
