@@ -18,6 +18,15 @@ constexpr int kTwoLevelShift = 10;
 
 // (M1 = RA1 * RB1, M2 = RA2 * RB2) splits served by the two-stage register-resident kernels of fft.cu
 // (fft_reg.cuh): X(RA1, RB1, G1, RA2, RB2, G2).  host_direct_plan() prefers these splits.
+#ifndef AA_G_D3
+#define AA_G_D3 16   /* columns per CTA of the 120 x 400 split: 16 (7.22 ms for the class) against 8 (7.34) and 10 (7.66) */
+#endif
+#ifndef AA_G_D6
+#define AA_G_D6 8   /* 120 x 200 split: 8 (3.77 ms) against 10 (3.96) and 20 (3.94) */
+#endif
+#ifndef AA_G_D12
+#define AA_G_D12 20   /* 120 x 100 split: 20 (4.45 ms) against 4 (4.94) and 10 (4.51) */
+#endif
 #ifndef AA_D16_G1
 #define AA_D16_G1 15
 #endif
@@ -26,11 +35,11 @@ constexpr int kTwoLevelShift = 10;
     X(12, 20, 8, 20, 20, 8) /* N = 192000: M = 240 x 400 */ \
     X(18, 20, 8, 10, 20, 8) /* N = 144000 (288000 decimated by 2): M = 360 x 200 */ \
     X(10, 12, 10, 15, 20, 8) /* N =  72000 (288000 decimated by 4): M = 120 x 300 */ \
-    X(10, 12, 8, 20, 20, 8) /* N =  96000 (288000 / 3, 192000 / 2): M = 120 x 400 - short columns: the issue-bound pass does less, the memory-bound rows pass more */ \
-    X(10, 12, 8, 10, 20, 8) /* N =  48000 (192000 decimated by 4): M = 120 x 200 */ \
+    X(10, 12, AA_G_D3, 20, 20, 8) /* N =  96000 (288000 / 3, 192000 / 2): M = 120 x 400 - short columns: the issue-bound pass does less, the memory-bound rows pass more */ \
+    X(10, 12, AA_G_D6, 10, 20, 8) /* N =  48000 (192000 decimated by 4): M = 120 x 200 */ \
     X(10, 12, 10, 10, 15, 8) /* N =  36000 (288000 decimated by 8): M = 120 x 150 */ \
     X(5, 8, AA_D16_G1, 15, 15, 8) /* N =  18000 (288000 decimated by 16): M = 40 x 225 (120 x 75 left 40 of 128 threads busy in the rows pass) */ \
-    X(10, 12, 4, 10, 10, 8) /* N =  24000 (192000 decimated by 8): M = 120 x 100 */ \
+    X(10, 12, AA_G_D12, 10, 10, 8) /* N =  24000 (192000 decimated by 8): M = 120 x 100 */ \
     X(5, 8, 15, 10, 15, 8) /* N =  12000 (192000 decimated by 16): M = 40 x 150 */ \
     X(8, 10, 8, 20, 20, 8) /* N =  64000 (192000 decimated by 3): M = 80 x 400 */ \
     X(8, 20, 4, 10, 10, 8) /* N =  32000 (192000 decimated by 6): M = 160 x 100 */ \
