@@ -48,6 +48,7 @@ EXPORTED_SYMBOLS = (
     "aa_bands_classify",
     "aa_bands_workspace_bytes",
     "aa_rt60bands_batch",
+    "aa_rt60bands_batch_ex",
     "aa_csd_batch",
     "aa_stft_db_batch",
     "aa_modal_cloud_batch",
@@ -81,6 +82,32 @@ class Band(C.Structure):
         ("reserved", C.c_int32),
         ("low_edge_hz", C.c_double),
         ("high_edge_hz", C.c_double),
+    ]
+
+
+class BandsOptions(C.Structure):
+    """aa_bands_options: per-call decimation / certification settings of the band stage (zeros = defaults)."""
+
+    _fields_ = [
+        ("max_decimation", C.c_int32),
+        ("refine", C.c_int32),
+        ("cert_safety", C.c_double),
+        ("cert_window", C.c_double),
+        ("cert_tol", C.c_double),
+        ("cert_min_span", C.c_int32),
+        ("reserved", C.c_int32),
+    ]
+
+
+class BandsStats(C.Structure):
+    """aa_bands_stats: (row, band) units each refinement level processed."""
+
+    _fields_ = [
+        ("n_levels", C.c_int32),
+        ("level_limit", C.c_int32 * 4),
+        ("level_units", C.c_int64 * 4),
+        ("n_chunks", C.c_int32),
+        ("rows_per_chunk", C.c_int32),
     ]
 
 
@@ -149,6 +176,10 @@ def _declare(lib: C.CDLL) -> None:
     lib.aa_rt60bands_batch.restype = C.c_int
     lib.aa_rt60bands_batch.argtypes = [vp, vp, i64, i32, vp, C.POINTER(Band), i32, C.c_double,
                                        C.POINTER(DecayParams), vp, vp, vp, sz, vp]
+    lib.aa_rt60bands_batch_ex.restype = C.c_int
+    lib.aa_rt60bands_batch_ex.argtypes = [vp, vp, i64, i32, vp, C.POINTER(Band), i32, C.c_double,
+                                          C.POINTER(DecayParams), vp, vp, vp, sz, vp, C.POINTER(BandsOptions),
+                                          C.POINTER(BandsStats)]
     lib.aa_csd_batch.restype = C.c_int
     lib.aa_csd_batch.argtypes = [vp, i64, vp, i32, i32, vp, vp, vp, i32, C.POINTER(CsdParams), vp, vp]
     lib.aa_stft_db_batch.restype = C.c_int

@@ -68,7 +68,8 @@ int bands_classify(const aa_bands_plan* plan, const aa_band* bands, int nb, doub
                    const aa_decay_params* fits, int* out_decimation);
 int rt60bands_batch(const aa_bands_plan* plan, const float* d_x, long long row_stride, int n_rows,
                     const int* d_start_idx, const aa_band* bands, int nb, double tw_oct, const aa_decay_params* p,
-                    double* d_metrics_out, float* d_band_signal_out, void* d_ws, size_t ws_bytes, cudaStream_t stream);
+                    double* d_metrics_out, float* d_band_signal_out, void* d_ws, size_t ws_bytes, cudaStream_t stream,
+                    const aa_bands_options* opts, aa_bands_stats* stats);
 int deconv_plan_create(int n_fft, aa_deconv_plan** out);
 void deconv_plan_destroy(aa_deconv_plan* p);
 size_t deconv_workspace_bytes(const aa_deconv_plan* p, int rows);
@@ -188,7 +189,17 @@ int aa_rt60bands_batch(const aa_bands_plan* plan, const float* d_x, int64_t row_
                        float* d_band_signal_out, void* d_workspace, size_t workspace_bytes, void* stream) {
     return aa::rt60bands_batch(plan, d_x, row_stride, n_rows, d_start_idx, bands, n_bands, transition_width_octaves, p,
                                d_metrics_out, d_band_signal_out, d_workspace, workspace_bytes,
-                               static_cast<cudaStream_t>(stream));
+                               static_cast<cudaStream_t>(stream), nullptr, nullptr);
+}
+
+int aa_rt60bands_batch_ex(const aa_bands_plan* plan, const float* d_x, int64_t row_stride, int32_t n_rows,
+                          const int32_t* d_start_idx, const aa_band* bands, int32_t n_bands,
+                          double transition_width_octaves, const aa_decay_params* p, double* d_metrics_out,
+                          float* d_band_signal_out, void* d_workspace, size_t workspace_bytes, void* stream,
+                          const aa_bands_options* options, aa_bands_stats* stats_out) {
+    return aa::rt60bands_batch(plan, d_x, row_stride, n_rows, d_start_idx, bands, n_bands, transition_width_octaves, p,
+                               d_metrics_out, d_band_signal_out, d_workspace, workspace_bytes,
+                               static_cast<cudaStream_t>(stream), options, stats_out);
 }
 
 int aa_stft_db_batch(const float* d_x, int64_t row_stride, const int32_t* d_lengths, int32_t uniform_length,

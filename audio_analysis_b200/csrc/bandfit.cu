@@ -46,8 +46,22 @@ struct BandFitArgs {
     int decim, full_n, aligned;
     float kappa;
     int min_fit_points;
-    EdcArgs e;                // start_in / start_div / rt60_out / targets / fit ranges / eps / floor / sr / min_samples
+    // addressing: dense (unit = row * nbc + j) or through a unit list (unit_map[unit] = row * nbc + j); the result of
+    // class band j of a row goes to rt60_out[(row * out_nb + out_band[j]) * AA_MAX_FITS + f]
+    const int* unit_map;
+    int nbc, out_nb;
+    // certification of a decimated unit (launch_band_fit's BandFitCert): see certify_unit below
+    BandFitCert cert;
+    EdcArgs e;                // start_in / rt60_out / targets / fit ranges / eps / floor / sr / min_samples
 };
+
+// append (row, band) to the unit list of the level that will redo it: entries are row * nbc' + j' in the addressing
+// of the class that owns the band on that level
+__device__ __forceinline__ void flag_unit(const BandFitCert& c, int row, int cj) {
+    const int l = c.next_list[cj];
+    const int pos = atomicAdd(c.counts + l, 1);
+    c.lists[c.next_off[cj] + pos] = row * (int)c.next_nbc[cj] + (int)c.next_j[cj];
+}
 
 // energy of sample c (0..3) of the lane's four from the in-lane suffix sums
 __device__ __forceinline__ float lane_sample_energy(const TileScan& sc, int c) {
@@ -56,6 +70,10 @@ __device__ __forceinline__ float lane_sample_energy(const TileScan& sc, int c) {
 }
 
 struct FitShared {
+    int cert_idx[AA_MAX_FITS * 4];
+    float fit_wa[AA_MAX_FITS], fit_wb[AA_MAX_FITS];   // weights of the first / last sample of a fit (decimated grids)
+    double fit_slope_u[AA_MAX_FITS], fit_b0[AA_MAX_FITS];
+    int fit_n_full[AA_MAX_FITS];
     double warp_tot[kFitWarps];
     double e0, inv_e0;
     int cross_ok[kMaxTargets], cross_idx[kMaxTargets];
@@ -106,6 +124,9 @@ __global__ void __launch_bounds__(kFitThreads, AA_FIT_MIN_BLOCKS) band_fit_kerne
     extern __shared__ __align__(16) unsigned char dyn_smem[];
     __shared__ FitShared sh;
     const int unit = blockIdx.x;
+    const int um = a.unit_map ? __ldg(a.unit_map + unit) : unit;
+    const int row = um / a.nbc, cj = um - row * a.nbc;
+    double* __restrict__ rt60_out = a.e.rt60_out + ((long long)row * a.out_nb + a.cert.out_band[cj]) * AA_MAX_FITS;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const ScanMasks masks = make_scan_masks();
     const int NT = a.n_tiles, TL = a.tile_len;
@@ -114,7 +135,8 @@ __global__ void __launch_bounds__(kFitThreads, AA_FIT_MIN_BLOCKS) band_fit_kerne
     const float* __restrict__ y = a.y + (long long)unit * a.y_stride;
     const float* __restrict__ part = a.part + (long long)unit * a.part_stride;
     const EdcArgs& p = a.e;
-    int n = a.n, start = min(max(p.start_in[unit / p.start_div], 0), a.aligned ? a.full_n : a.n);
+    int n = a.n, start = min(max(p.start_in[row], 0), a.aligned ? a.full_n : a.n);
+    const int full_len = a.full_n - start;   // analysed samples at full rate (aligned grids)
     if (a.aligned) {   // the (decimated) grid starts at the analysis start and stops before the signal wraps around
         n = min(a.n, (a.full_n - start + a.decim - 1) / a.decim);
         start = 0;
@@ -123,8 +145,9 @@ __global__ void __launch_bounds__(kFitThreads, AA_FIT_MIN_BLOCKS) band_fit_kerne
     const int n_an = n - start;
     const float srf = (float)p.sr;
 
-    if (n_an < p.min_samples) {  // rt60bands.py:395-397: every metric None
-        if (threadIdx.x < AA_MAX_FITS) p.rt60_out[(long long)unit * AA_MAX_FITS + threadIdx.x] = nan("");
+    // rt60bands.py:395-397: fewer than 8 samples -> every metric None (aligned grids test the full-rate count)
+    if (a.aligned ? (full_len < p.min_samples) : (n_an < p.min_samples)) {
+        if (threadIdx.x < AA_MAX_FITS) rt60_out[threadIdx.x] = nan("");
         return;
     }
 
@@ -168,7 +191,15 @@ __global__ void __launch_bounds__(kFitThreads, AA_FIT_MIN_BLOCKS) band_fit_kerne
         for (int w = warp + 1; w < kFitWarps; ++w) higher += sh.warp_tot[w];
         double after = __shfl_down_sync(kFullMask, inc, 1);
         if (lane == 31) after = 0.0;
-        double running = higher + after;
+        // far end of a decimated grid: the last sample J stands for the r = full_len - decim J samples that are left,
+        // and the trapezoid rule gives it half a step: S += (r - (decim + 1) / 2) / decim * y_J^2
+        double s_end = 0.0;
+        if (a.decim > 1 && n > 0) {
+            const float yl = __ldg(y + (n - 1));
+            const double r = (double)(full_len - a.decim * (n - 1));
+            s_end = (r - 0.5 * (double)(a.decim + 1)) / (double)a.decim * (double)__fmul_rn(yl, yl);
+        }
+        double running = higher + after + s_end;
         for (int q = per - 1; q >= 0; --q) {
             const int k = t0 + q;
             if (k < NT) {
@@ -197,76 +228,81 @@ __global__ void __launch_bounds__(kFitThreads, AA_FIT_MIN_BLOCKS) band_fit_kerne
     const double inv_e0 = sh.inv_e0;
     const int n_targets = 2 + 2 * p.n_fits;
 
-    // ---- crossings (decay.py:173-199): warp w resolves target w
-    for (int tg = warp; tg < n_targets; tg += kFitWarps) {
-        const double tau = p.target[tg];
-        const float tauf = (float)tau;
-        int found = 0, idx = 0;
-        float y0 = 0.f, y1 = 0.f;
+    // ---- crossings (decay.py:173-199): first sample <= target, by one warp (all lanes return the same values)
+    auto resolve = [&](float tauf, int& found, int& idx, float& y0, float& y1) {
+        found = 0;
+        idx = 0;
+        y0 = y1 = 0.f;
         if (tauf >= 0.0f) {
             found = 1;  // the curve starts at exactly 0 dB (decay.py:186-187)
             idx = start;
-        } else {
-            int hit = -1;
-            for (int kb = ks; kb < NT && hit < 0; kb += 32) {
-                const int k = kb + lane;
-                bool ok = false;
-                if (k < NT) {
-                    const float b_next = to_db(carry[k], p.eps, inv_e0, p.floor_db);
-                    float b_first = 0.0f;
-                    if (k > ks) b_first = to_db(carry[k] + (double)tsum[k], p.eps, inv_e0, p.floor_db);
-                    ok = (b_first > tauf) && (b_next <= tauf);
-                }
-                const unsigned m = __ballot_sync(kFullMask, ok);
-                if (m) hit = kb + (__ffs(m) - 1);
-            }
-            if (hit >= 0) {
-                const int k = hit;
-                // steps are visited last to first; the curve is monotone, so the last step that reports a
-                // sample <= target holds the first such sample
-                visit_tile_reverse<NS>(y, k, TL, n, carry[k], lane, masks, [&](int j, const TileScan& sc, double after) {
-                    int first_c = 4;
-                    float dbv = 0.f;
-                    double ev = 0.0;
-#pragma unroll
-                    for (int c = 3; c >= 0; --c) {
-                        const int off = j * kSub + 4 * lane + c;
-                        const int i = k * TL + off;
-                        const double eu = after + (double)__fadd_rn(sc.excl, sc.s[c]);
-                        const float d = to_db(eu - kappa * (double)lane_sample_energy(sc, c), p.eps, inv_e0, p.floor_db);
-                        if (off < TL && i >= start && i < n && d <= tauf) {
-                            first_c = c;
-                            dbv = d;
-                            ev = eu;
-                        }
-                    }
-                    const unsigned m = __ballot_sync(kFullMask, first_c < 4);
-                    if (m) {
-                        const int fl = __ffs(m) - 1;
-                        float py0 = 0.f;
-                        int pidx = 0;
-                        if (lane == fl) {
-                            pidx = k * TL + j * kSub + 4 * lane + first_c;
-                            // value one sample earlier: E[i-1] = E[i] + y[i-1]^2 (i > start because b_first > tau)
-                            const float yp = __ldg(y + pidx - 1);
-                            py0 = to_db(ev + (1.0 - kappa) * (double)__fmul_rn(yp, yp), p.eps, inv_e0, p.floor_db);
-                        }
-                        found = 1;
-                        idx = __shfl_sync(kFullMask, pidx, fl);
-                        y1 = __shfl_sync(kFullMask, dbv, fl);
-                        y0 = __shfl_sync(kFullMask, py0, fl);
-                    }
-                });
-                if (!found && k + 1 < NT && (k + 1) * TL < n) {
-                    // every sample of the tile is above the target: the crossing is the first sample of tile k+1
-                    found = 1;
-                    idx = (k + 1) * TL;
-                    y1 = to_db(carry[k], p.eps, inv_e0, p.floor_db);
-                    const float yp = __ldg(y + idx - 1);
-                    y0 = to_db(carry[k] + (1.0 - kappa) * (double)__fmul_rn(yp, yp), p.eps, inv_e0, p.floor_db);
-                }
-            }
+            return;
         }
+        int hit = -1;
+        for (int kb = ks; kb < NT && hit < 0; kb += 32) {
+            const int k = kb + lane;
+            bool ok = false;
+            if (k < NT) {
+                const float b_next = to_db(carry[k], p.eps, inv_e0, p.floor_db);
+                float b_first = 0.0f;
+                if (k > ks) b_first = to_db(carry[k] + (double)tsum[k], p.eps, inv_e0, p.floor_db);
+                ok = (b_first > tauf) && (b_next <= tauf);
+            }
+            const unsigned m = __ballot_sync(kFullMask, ok);
+            if (m) hit = kb + (__ffs(m) - 1);
+        }
+        if (hit < 0) return;
+        const int k = hit;
+        // steps are visited last to first; the curve is monotone, so the last step that reports a
+        // sample <= target holds the first such sample
+        visit_tile_reverse<NS>(y, k, TL, n, carry[k], lane, masks, [&](int j, const TileScan& sc, double after) {
+            int first_c = 4;
+            float dbv = 0.f;
+            double ev = 0.0;
+#pragma unroll
+            for (int c = 3; c >= 0; --c) {
+                const int off = j * kSub + 4 * lane + c;
+                const int i = k * TL + off;
+                const double eu = after + (double)__fadd_rn(sc.excl, sc.s[c]);
+                const float d = to_db(eu - kappa * (double)lane_sample_energy(sc, c), p.eps, inv_e0, p.floor_db);
+                if (off < TL && i >= start && i < n && d <= tauf) {
+                    first_c = c;
+                    dbv = d;
+                    ev = eu;
+                }
+            }
+            const unsigned m = __ballot_sync(kFullMask, first_c < 4);
+            if (m) {
+                const int fl = __ffs(m) - 1;
+                float py0 = 0.f;
+                int pidx = 0;
+                if (lane == fl) {
+                    pidx = k * TL + j * kSub + 4 * lane + first_c;
+                    // value one sample earlier: E[i-1] = E[i] + y[i-1]^2 (i > start because b_first > tau)
+                    const float yp = __ldg(y + pidx - 1);
+                    py0 = to_db(ev + (1.0 - kappa) * (double)__fmul_rn(yp, yp), p.eps, inv_e0, p.floor_db);
+                }
+                found = 1;
+                idx = __shfl_sync(kFullMask, pidx, fl);
+                y1 = __shfl_sync(kFullMask, dbv, fl);
+                y0 = __shfl_sync(kFullMask, py0, fl);
+            }
+        });
+        if (!found && k + 1 < NT && (k + 1) * TL < n) {
+            // every sample of the tile is above the target: the crossing is the first sample of tile k+1
+            found = 1;
+            idx = (k + 1) * TL;
+            y1 = to_db(carry[k], p.eps, inv_e0, p.floor_db);
+            const float yp = __ldg(y + idx - 1);
+            y0 = to_db(carry[k] + (1.0 - kappa) * (double)__fmul_rn(yp, yp), p.eps, inv_e0, p.floor_db);
+        }
+    };
+    // warp w resolves target w; targets 0 / 1 (0 dB, -10 dB) only serve early10, which band tables do not carry
+    for (int tg = 2 + warp; tg < n_targets; tg += kFitWarps) {
+        const double tau = p.target[tg];
+        int found, idx;
+        float y0, y1;
+        resolve((float)tau, found, idx, y0, y1);
         if (lane == 0) {
             sh.cross_ok[tg] = found;
             sh.cross_idx[tg] = idx;
@@ -277,24 +313,81 @@ __global__ void __launch_bounds__(kFitThreads, AA_FIT_MIN_BLOCKS) band_fit_kerne
     if (threadIdx.x < p.n_fits) {
         const int f = threadIdx.x;
         const int ts_i = 2 + 2 * f, te_i = 3 + 2 * f;
-        int first = 0, last = -1;
-        const int valid = fit_index_range(sh.cross_ok[ts_i], sh.cross_ok[te_i], sh.cross_t[ts_i], sh.cross_t[te_i],
-                                          sh.cross_idx[ts_i] - start, sh.cross_idx[te_i] - start, srf, &first, &last,
-                                          a.min_fit_points);
+        int first = 0, last = -1, valid;
+        float wa = 1.0f, wb = 1.0f;
+        if (a.decim > 1) {
+            // The reference fits the full-rate samples i0..i1 between the crossing times (decay.py:224-228).  On the
+            // decimated grid sample j stands for the D full-rate samples around it, so the fit takes every j whose
+            // cell overlaps [i0, i1] and weights the first and the last by the covered fraction of their cell: which
+            // end samples the grid happens to include then moves the slope ~50 x less (a band's curve is bumpy, and
+            // its end points can sit several dB off the fitted line).
+            const double D = (double)a.decim, sr_full = (double)p.sr * D;
+            const double ts = sh.cross_t[ts_i], te = sh.cross_t[te_i];
+            valid = sh.cross_ok[ts_i] && sh.cross_ok[te_i] && te > ts;
+            const double i0 = ceil(ts * sr_full - 1e-6), i1 = floor(te * sr_full + 1e-6);
+            valid = valid && (i1 - i0 + 1.0 >= 8.0);
+            const double lo_r = i0 - 0.5, hi_r = i1 + 0.5;
+            int ja = (int)floor((lo_r - 0.5 * D) / D) + 1, jb = (int)ceil((hi_r + 0.5 * D) / D) - 1;
+            ja = max(ja, 0);
+            jb = min(jb, n - 1);
+            valid = valid && jb >= ja;
+            if (valid) {
+                wa = (float)((fmin(D * ja + 0.5 * D, hi_r) - fmax(D * ja - 0.5 * D, lo_r)) / D);
+                wb = (jb > ja) ? (float)((fmin(D * jb + 0.5 * D, hi_r) - fmax(D * jb - 0.5 * D, lo_r)) / D) : wa;
+            }
+            first = ja;
+            last = jb;
+            sh.fit_n_full[f] = (int)(i1 - i0 + 1.0);
+        } else {
+            valid = fit_index_range(sh.cross_ok[ts_i], sh.cross_ok[te_i], sh.cross_t[ts_i], sh.cross_t[te_i],
+                                    sh.cross_idx[ts_i] - start, sh.cross_idx[te_i] - start, srf, &first, &last,
+                                    a.min_fit_points);
+            sh.fit_n_full[f] = last - first + 1;
+        }
         sh.fit_valid[f] = valid;
         sh.fit_first[f] = start + first;
         sh.fit_last[f] = start + last;
+        sh.fit_wa[f] = wa;
+        sh.fit_wb[f] = wb;
         sh.fit_ts[f] = sh.cross_t[ts_i];
         sh.fit_te[f] = sh.cross_t[te_i];
     }
     __syncthreads();
+
+    // ---- certification of a decimated unit, part 1.  The sub-sampled Schroeder sum differs from the reference's by
+    // at most delta dB near a fit end point: the 2 f ripple of y^2 folds to another frequency on the decimated grid
+    // (the host's per-band error model times a safety factor, scaled by the unit's own decay rate), and the far end of
+    // the grid is known to about one cell of energy.  The reference's crossing then lies between the first decimated
+    // samples <= target + delta and <= target - delta: resolve those four extra targets per fit.
+    if (a.cert.on) {
+        const float m_b = a.cert.m[cj];
+        const float yl = __ldg(y + (n - 1));
+        const double end_cell = (double)__fmul_rn(yl, yl) * inv_e0;   // one far-end cell relative to E0
+        for (int ct = warp; ct < 4 * p.n_fits; ct += kFitWarps) {
+            const int f = ct >> 2, e = (ct >> 1) & 1, minus = ct & 1;
+            const int ts_i = 2 + 2 * f, te_i = 3 + 2 * f;
+            int cidx = -1;
+            const int span = sh.cross_idx[te_i] - sh.cross_idx[ts_i];
+            if (sh.fit_valid[f] && span > 0) {
+                const double tau0 = p.target[e ? te_i : ts_i];
+                const double delta = (double)m_b * (p.target[ts_i] - p.target[te_i]) / (double)span +
+                                     4.342944819 * end_cell * exp10(-0.1 * tau0);
+                const double tau = tau0 + (minus ? -delta : delta);
+                int found, idx;
+                float y0, y1;
+                resolve((float)tau, found, idx, y0, y1);
+                if (found) cidx = idx;
+            }
+            if (lane == 0) sh.cert_idx[ct] = cidx;
+        }
+    }
 
     // ---- regression sums over the fit ranges (decay.py:224-249)
     double acc[AA_MAX_FITS * 3];
 #pragma unroll
     for (int q = 0; q < AA_MAX_FITS * 3; ++q) acc[q] = 0.0;
     int ffirst[AA_MAX_FITS], flast[AA_MAX_FITS];
-    float ymid_f[AA_MAX_FITS];
+    float ymid_f[AA_MAX_FITS], fwa[AA_MAX_FITS], fwb[AA_MAX_FITS];
     int lo = 0x7fffffff, hi = -1;
 #pragma unroll
     for (int f = 0; f < AA_MAX_FITS; ++f) {
@@ -302,6 +395,8 @@ __global__ void __launch_bounds__(kFitThreads, AA_FIT_MIN_BLOCKS) band_fit_kerne
         ffirst[f] = on ? sh.fit_first[f] : 0x7fffffff;
         flast[f] = on ? sh.fit_last[f] : -1;
         ymid_f[f] = (float)(0.5 * (p.fit_hi[f] + p.fit_lo[f]));
+        fwa[f] = on ? sh.fit_wa[f] : 1.0f;
+        fwb[f] = on ? sh.fit_wb[f] : 1.0f;
         if (on) {
             lo = min(lo, ffirst[f]);
             hi = max(hi, flast[f]);
@@ -337,9 +432,11 @@ __global__ void __launch_bounds__(kFitThreads, AA_FIT_MIN_BLOCKS) band_fit_kerne
                         for (int c = 0; c < 4; ++c) {
                             const int i = i0 + c;
                             const float yc = (c < in_tile && i >= ffirst[f] && i <= flast[f]) ? db[c] - ymid_f[f] : 0.0f;
-                            s0 += yc;
-                            s1 = fmaf((float)c, yc, s1);
-                            s2 = fmaf(yc, yc, s2);
+                            // end weights (1 at full rate: the products below are then exact)
+                            const float yw = yc * ((i == ffirst[f]) ? fwa[f] : (i == flast[f]) ? fwb[f] : 1.0f);
+                            s0 += yw;
+                            s1 = fmaf((float)c, yw, s1);
+                            s2 = fmaf(yw, yc, s2);
                         }
                         const double ub = (double)(i0 - ffirst[f]);
                         acc[f * 3 + 0] += (double)s0;
@@ -366,11 +463,61 @@ __global__ void __launch_bounds__(kFitThreads, AA_FIT_MIN_BLOCKS) band_fit_kerne
                 s1 += sh.warp_acc[w][f * 3 + 1];
                 s2 += sh.warp_acc[w][f * 3 + 2];
             }
-            double res[AA_FIT_COLS];
-            rt60 = fit_finalize(s0, s1, s2, sh.fit_first[f] - start, sh.fit_last[f] - start, (double)ymid_f[f], p.sr, sh.fit_ts[f],
-                                sh.fit_te[f], res);
+            if (a.decim > 1) {
+                // weighted least squares over u = 0..m (u = j - first): only the end weights differ from 1
+                const double m = (double)(sh.fit_last[f] - sh.fit_first[f]);
+                const double wa = (double)sh.fit_wa[f], wb = (m > 0.0) ? (double)sh.fit_wb[f] : 0.0;
+                const double inner = fmax(m - 1.0, 0.0);                       // u = 1..m-1
+                const double W = wa + wb + inner;
+                const double U1 = wb * m + 0.5 * (m - 1.0) * m * (m > 0.0 ? 1.0 : 0.0);
+                const double U2 = wb * m * m + (m > 0.0 ? (m - 1.0) * m * (2.0 * m - 1.0) / 6.0 : 0.0);
+                const double den = W * U2 - U1 * U1;
+                if (den > 0.0) {
+                    const double slope_u = (W * s1 - U1 * s0) / den;          // dB per decimated sample
+                    sh.fit_slope_u[f] = slope_u;
+                    sh.fit_b0[f] = (s0 - slope_u * U1) / W + (double)ymid_f[f];  // line value at u = 0
+                    const double slope = slope_u * (double)p.sr;               // dB per second (decay.py:241-249)
+                    if (slope < 0.0) rt60 = -60.0 / slope;
+                }
+                if (rt60 != rt60) sh.fit_valid[f] = 0;
+            } else {
+                double res[AA_FIT_COLS];
+                rt60 = fit_finalize(s0, s1, s2, sh.fit_first[f] - start, sh.fit_last[f] - start, (double)ymid_f[f], p.sr,
+                                    sh.fit_ts[f], sh.fit_te[f], res);
+            }
         }
-        p.rt60_out[(long long)unit * AA_MAX_FITS + f] = rt60;
+        rt60_out[f] = rt60;
+    }
+    // ---- certification, part 2: with the crossing windows [lo, hi] (decimated samples) and the fitted line, moving an
+    // end point of the fit by `win` full-rate samples changes the slope by about 6 (win / n) (r / range), r = distance
+    // of the curve from the line at that end.  The unit is certified when both ends together stay under cert.tol;
+    // otherwise it goes on the list of the next, finer level (bands.cu), whose last level is the full-rate path.
+    if (a.cert.on) {
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            bool ok = true;
+            for (int f = 0; f < p.n_fits && ok; ++f) {
+                const int ts_i = 2 + 2 * f, te_i = 3 + 2 * f;
+                const int span = sh.cross_idx[te_i] - sh.cross_idx[ts_i];
+                ok = sh.fit_valid[f] && (float)span >= (float)a.cert.min_span[cj] * a.cert.fit_scale[f];
+                if (!ok) break;
+                const double range = p.target[ts_i] - p.target[te_i];
+                const double n_full = (double)sh.fit_n_full[f];
+                double moved = 0.0;
+                for (int e = 0; e < 2 && ok; ++e) {
+                    const int lo = sh.cert_idx[4 * f + 2 * e], hi = sh.cert_idx[4 * f + 2 * e + 1];
+                    ok = lo >= 0 && hi >= 0 && hi - lo <= max(1, (int)(a.cert.w * (float)span));
+                    const double tc = (e ? sh.fit_te[f] : sh.fit_ts[f]) * (double)p.sr - (double)(sh.fit_first[f] - start);
+                    const double line = sh.fit_b0[f] + sh.fit_slope_u[f] * tc;
+                    const double r = fmax(fabs(p.target[e ? te_i : ts_i] - line), 0.5) + fabs(sh.fit_slope_u[f]) * (double)(hi - lo + 1);
+                    // a start target at 0 dB is the first sample whatever the curve (decay.py:186-187)
+                    const double win = (p.target[e ? te_i : ts_i] >= 0.0) ? 0.0 : ((double)(hi - lo) + 0.25) * (double)a.decim;
+                    moved += 6.0 * (win / n_full) * (r / range);
+                }
+                ok = ok && moved <= (double)a.cert.tol;
+            }
+            if (!ok) flag_unit(a.cert, row, cj);
+        }
     }
 }
 
@@ -378,8 +525,8 @@ __global__ void __launch_bounds__(kFitThreads, AA_FIT_MIN_BLOCKS) band_fit_kerne
 
 int launch_band_fit(const float* d_y, long long y_stride, const float* d_part, long long part_stride, int n_groups,
                     int n_tiles, int tile_len, int n, long long n_units, const aa_decay_params* p,
-                    const int* d_start_idx, int start_div, int min_samples, double* d_rt60_out, cudaStream_t stream,
-                    int decim, int full_n, int aligned) {
+                    const int* d_start_idx, int nbc, int out_nb, const int* d_unit_map, const BandFitCert* cert,
+                    int min_samples, double* d_rt60_out, cudaStream_t stream, int decim, int full_n, int aligned) {
     AA_REQUIRE(d_y && d_part && p && d_start_idx && d_rt60_out, AA_ERR_INVALID_ARGUMENT, "null argument");
     AA_REQUIRE(tile_len % 4 == 0 && tile_len >= 4 && tile_len <= kSub * kMaxSub, AA_ERR_UNSUPPORTED,
                "tile length must be a multiple of 4 and at most 1024");
@@ -398,9 +545,20 @@ int launch_band_fit(const float* d_y, long long y_stride, const float* d_part, l
     a.n_tiles = n_tiles;
     a.tile_len = tile_len;
     a.n = n;
+    AA_REQUIRE(nbc >= 1 && nbc <= AA_MAX_BANDS && out_nb >= 1, AA_ERR_INVALID_ARGUMENT, "band counts out of range");
     a.e.start_in = d_start_idx;
-    a.e.start_div = start_div > 0 ? start_div : 1;
+    a.e.start_div = nbc;
     a.e.rt60_out = d_rt60_out;
+    a.unit_map = d_unit_map;
+    a.nbc = nbc;
+    a.out_nb = out_nb;
+    if (cert) {
+        a.cert = *cert;
+    } else {
+        AA_REQUIRE(nbc == out_nb, AA_ERR_INVALID_ARGUMENT, "a class needs its band map");
+        for (int j = 0; j < nbc; ++j) a.cert.out_band[j] = (short)j;
+    }
+    AA_REQUIRE(!a.cert.on || (a.cert.counts && a.cert.lists), AA_ERR_INVALID_ARGUMENT, "certification without unit lists");
     a.e.min_samples = min_samples;
     a.decim = decim > 1 ? decim : 1;
     a.full_n = full_n;
@@ -410,7 +568,6 @@ int launch_band_fit(const float* d_y, long long y_stride, const float* d_part, l
     if (decim > 1) {
         AA_REQUIRE(p->sample_rate_hz % decim == 0, AA_ERR_INVALID_ARGUMENT, "sample rate not divisible by the decimation");
         a.e.sr = p->sample_rate_hz / decim;
-        a.e.min_samples = (min_samples + decim - 1) / decim;
     }
     const size_t smem = (size_t)n_tiles * (sizeof(double) + sizeof(float));
     AA_REQUIRE(smem <= 48 * 1024, AA_ERR_UNSUPPORTED, "too many tiles");

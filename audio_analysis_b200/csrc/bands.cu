@@ -14,6 +14,7 @@
 #include <string.h>
 
 #include <algorithm>
+#include <atomic>
 #include <vector>
 
 #include "fft.cuh"
@@ -37,6 +38,8 @@ struct aa_bands_plan {
     };
     static constexpr int kDecims = 8;
     Decim dec[kDecims];   // D = kDecimList[i]
+    // pinned (device-visible) host words the refinement levels report their unit-list lengths through
+    int* h_counts = nullptr;
 };
 
 namespace aa {
@@ -47,16 +50,29 @@ constexpr int kDecimList[aa_bands_plan::kDecims] = {2, 3, 4, 6, 8, 12, 16, 24};
 constexpr int kMaxBandDecimation = 24;
 // largest mask value a bin may have and still be left out when a band's support pokes past its Nyquist zone
 constexpr float kZoneDropMask = 0.02f;
-static int g_band_decimation = -1;
+// process default of aa_bands_options::max_decimation (per-call options override it)
+static std::atomic<int> g_band_decimation{-1};
 static int clamp_band_decimation(int v) { return v < 1 ? 1 : (v > kMaxBandDecimation ? kMaxBandDecimation : v); }
 int band_decimation_limit() {
-    if (g_band_decimation < 0) {
+    int v = g_band_decimation.load(std::memory_order_relaxed);
+    if (v < 0) {
         const char* env = getenv("AA_BANDS_DECIMATION");
-        g_band_decimation = clamp_band_decimation(env ? atoi(env) : kDefaultBandDecimation);
+        v = clamp_band_decimation(env ? atoi(env) : kDefaultBandDecimation);
+        g_band_decimation.store(v, std::memory_order_relaxed);
     }
-    return g_band_decimation;
+    return v;
 }
-void set_band_decimation_limit(int max_d) { g_band_decimation = clamp_band_decimation(max_d); }
+void set_band_decimation_limit(int max_d) { g_band_decimation.store(clamp_band_decimation(max_d), std::memory_order_relaxed); }
+
+// Certification defaults (aa_bands_options; bandfit.cu: band_fit_kernel).  Calibrated on a numpy model of the decimated
+// estimator over 160 k (row, band) units and confirmed on the device over 4096 rows x 26 bands per length
+// (tools/decimation_tail.py, profiles/r02_decimation_tail.txt): no metric further than 1.5e-3 from the full-rate path
+// (tolerance 5e-3), 8 % of the units redone at D <= 4 and 0.1 % at full rate.
+constexpr double kCertSafety = 9.0;     // crossing window half-width = safety x modelled quadrature error
+constexpr double kCertWindow = 0.015;   // a crossing window may cover at most this fraction of the fit span
+constexpr double kCertTol = 3.0e-3;     // modelled relative slope change allowed from both crossing windows together
+constexpr int kCertMinSpan = 240;       // decimated samples between the end points of a certified 30 dB fit, at least
+constexpr int kRefineLimit = 4;         // decimation limit of the middle level
 
 namespace {
 
@@ -121,20 +137,13 @@ __global__ void band_table_kernel(BandTableArg tab, BandDev* __restrict__ out, i
     if ((int)threadIdx.x < n) out[threadIdx.x] = tab.b[threadIdx.x];
 }
 
-// class table [rows][nbc][AA_MAX_FITS] -> caller's table [rows][nb][AA_MAX_FITS] at the class's band positions
 struct BandMapArg {
-    int map[AA_MAX_BANDS];
+    int map[AA_MAX_BANDS];   // class band -> caller band
 };
-__global__ void scatter_metrics_kernel(const double* __restrict__ src, double* __restrict__ dst, long long rows, int nbc,
-                                       int nb, BandMapArg m) {
-    const long long total = rows * nbc * AA_MAX_FITS;
-    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-        const int f = (int)(i % AA_MAX_FITS);
-        const long long u = i / AA_MAX_FITS;
-        const long long row = u / nbc;
-        const int j = (int)(u - row * nbc);
-        dst[(row * nb + m.map[j]) * AA_MAX_FITS + f] = src[i];
-    }
+
+// unit-list lengths -> pinned host memory (a kernel store, not the copy engine: see band_table_kernel)
+__global__ void publish_counts_kernel(const int* __restrict__ counts, int* __restrict__ host_counts, int n) {
+    if ((int)threadIdx.x < n) host_counts[threadIdx.x] = counts[threadIdx.x];
 }
 
 // Host mirror of _make_lowpass_mask / _make_highpass_mask / _make_bandpass_mask edge handling
@@ -227,9 +236,11 @@ int upload_bands(const aa_band* bands, int nb, double tw_oct, double nyq, double
 }
 
 struct Layout {
-    size_t off_bands, off_mask, off_X, off_y, off_scratch, off_part, off_tmp_metrics, off_db0, off_db1, off_unit_start,
-        total;
+    size_t off_bands, off_mask, off_X, off_y, off_scratch, off_part, off_counts, off_lists, off_db0, off_db1,
+        off_unit_start, total;
 };
+constexpr int kMaxLevels = 3;
+constexpr int kMaxLists = (kMaxLevels - 1) * (aa_bands_plan::kDecims + 1);
 
 // Largest per-row footprint over the decimation classes of a call (elements per row): the buffers are shared by
 // the classes, which run one after the other, so decimated calls fit several times more rows per chunk.
@@ -244,10 +255,12 @@ Layout make_layout(const aa_bands_plan* p, long long rows, int nb, bool smoothin
     size_t o = 0;
     l.off_bands = o;  // the call's band table, then one re-ordered copy per decimation class
     o += align_up(sizeof(BandDev) * AA_MAX_BANDS * 2);
+    l.off_counts = o;  // lengths of the refinement levels' unit lists
+    o += align_up(sizeof(int) * kMaxLists);
     l.off_mask = o;  // mask tables: at most one value per rfft bin per band (offsets up to here do not depend on rows)
     o += align_up(sizeof(float) * (size_t)nb * (size_t)(p->n / 2 + 1));
-    l.off_tmp_metrics = o;  // per-class RT60 tables before they are scattered into the caller's band order
-    o += align_up(sizeof(double) * (size_t)units * AA_MAX_FITS);
+    l.off_lists = o;  // unit lists of the refinement levels: one entry per (row, band) unit and level at most
+    o += align_up(sizeof(int) * (size_t)units * (kMaxLevels - 1));
     l.off_X = o;
     o += align_up(sizeof(float2) * (size_t)rows * (size_t)p->x_stride);
     l.off_y = o;  // also the forward transform's packed output Z (rows * M float2 <= units * y_stride floats)
@@ -318,29 +331,33 @@ bool place_in_zone(const BandDev& b, int Mc, double freq_scale, BandDev* out) {
     return true;
 }
 
-// Largest decimation the requested fits tolerate (tools/decimation_error.py against the oracle, tools/decimation_tail.py
-// over 4096 rows x 26 bands against the full-rate device path).  The sub-sampled Schroeder sum is off by a fraction
-// ~ D / (decay time in samples) of the local energy; a fit whose end points sit on the 2 f staircase of the curve can
-// then pick a neighbouring step.  Metrics outside the 0.5 % / 1 ms tolerance per 106,496:
-//   T30 (30 dB):  1 at D <= 4,  1 at D <= 8,  2 at D <= 16,  11 at D <= 24     -> D <= 16
-//   T20 (20 dB):  0 at D <= 4,  2 at D <= 8, 18 at D <= 16,  79 at D <= 24     -> D <= 4
-//   EDT (10 dB from 0 dB): worst 7e-4 at D <= 4, 6e-3 at D <= 16 (12 rows)     -> D <= 4
+// Decimation limits of the levels a metrics-only call runs (first = coarsest, applied to every unit; a unit whose
+// fits are not certified there is redone on the next level; the last level is the full-rate path when refinement is on).
+// Long late fits (T30) start at max_decimation (default 16); a call with a fit shorter than 28 dB or starting above
+// -2.5 dB (T20, EDT: few decimated points per fit) starts at 4.
 int fit_decimation_limit(const aa_decay_params* p) {
     int lim = 16;
     if (!p) return lim;
     for (int f = 0; f < p->n_fits && f < AA_MAX_FITS; ++f) {
         const double hi = p->fit_hi_db[f], lo = fmax(p->fit_lo_db[f], p->fit_lower_limit_db);
-        if (hi > -2.5 || hi - lo < 28.0) lim = 4;
+        if (hi > -2.5 || hi - lo < 28.0) lim = kRefineLimit;
     }
     return lim;
 }
 
-void classify_bands(const aa_bands_plan* plan, const std::vector<BandDev>& hb, int sample_rate_hz, double freq_scale,
-                    bool metrics_only, const aa_decay_params* fits, std::vector<BandClass>* classes) {
-    int tile_c = 0, n_tiles = 0, n_groups = 0;
-    // the setter / AA_BANDS_DECIMATION can lower the limit, or raise it to 24 for T30-only calls
+void level_limits(const aa_decay_params* fits, int max_decimation, bool refine, std::vector<int>* limits) {
     const int fit_lim = fit_decimation_limit(fits);
-    const int max_d = (fit_lim >= 16) ? band_decimation_limit() : std::min(band_decimation_limit(), fit_lim);
+    const int top = (fit_lim >= 16) ? max_decimation : std::min(max_decimation, fit_lim);
+    limits->clear();
+    limits->push_back(top);
+    if (!refine || top <= 1) return;
+    if (top > kRefineLimit) limits->push_back(kRefineLimit);
+    limits->push_back(1);
+}
+
+void classify_bands(const aa_bands_plan* plan, const std::vector<BandDev>& hb, int sample_rate_hz, double freq_scale,
+                    bool metrics_only, int max_d, std::vector<BandClass>* classes) {
+    int tile_c = 0, n_tiles = 0, n_groups = 0;
     const bool can = (plan->n % 2) == 0 && metrics_only && c2c_energy_layout(plan->c2c, &tile_c, &n_tiles, &n_groups);
     BandClass by_d[aa_bands_plan::kDecims + 1];   // [0] full rate, [1 + c] plan->dec[c]
     for (size_t i = 0; i < hb.size(); ++i) {
@@ -366,6 +383,35 @@ void classify_bands(const aa_bands_plan* plan, const std::vector<BandDev>& hb, i
         if (!c.bands.empty()) classes->push_back(c);
 }
 
+// Modelled error of the decimated Schroeder sum of a band, in decimated samples of a straight decay: the 2 f part of
+// y^2 (frequency theta = 4 pi f / sr per sample) has the running sum 1 / (1 - e^{-i theta}) at full rate and
+// D / (1 - e^{-i D theta}) on the grid; after the trapezoid end term the two differ by (i / 2) (cot(theta / 2) -
+// D cot(D theta / 2)) times the component, i.e. by that many samples' worth of local energy.  0.7 / D x the largest
+// value over the pass band matches the measured rms error (numpy model) within 30 % for every band / D.
+double band_quadrature_error(const aa_band& b, int D, double sr) {
+    if (D <= 1) return 0.0;
+    const double nyq = 0.5 * sr;
+    double lo = (b.kind == AA_BAND_LOWPASS) ? 1.0 : b.low_edge_hz, hi = (b.kind == AA_BAND_HIGHPASS) ? nyq : b.high_edge_hz;
+    lo = fmin(fmax(lo, 1.0), nyq - 1.0);
+    hi = fmin(fmax(hi, lo), nyq - 1.0);
+    double worst = 0.0;
+    for (int i = 0; i < 64; ++i) {
+        const double f = lo + (hi - lo) * (double)i / 63.0;
+        const double th = 4.0 * 3.14159265358979323846 * f / sr;
+        const double v = 0.5 * fabs(1.0 / tan(0.5 * th) - (double)D / tan(0.5 * (double)D * th));
+        if (v > worst || v != v) worst = (v != v) ? 1e9 : v;
+    }
+    return fmin(0.7 * worst / (double)D, 1e6);
+}
+
+// One level of a call: the decimation classes at its limit, and for every caller band where it sits.
+struct Level {
+    int limit = 1;
+    std::vector<BandClass> classes;
+    int class_of[AA_MAX_BANDS], j_of[AA_MAX_BANDS], d_of[AA_MAX_BANDS];
+    int list_of_class[aa_bands_plan::kDecims + 1];   // unit list of a class (levels >= 1), -1 = none
+};
+
 }  // namespace
 
 int bands_plan_create(int n, aa_bands_plan** out) {
@@ -387,6 +433,10 @@ int bands_plan_create(int n, aa_bands_plan** out) {
         return rc;
     }
     p->kind = even ? (p->c2c->bluestein ? 1 : 0) : 2;
+    if (cudaMallocHost(reinterpret_cast<void**>(&p->h_counts), sizeof(int) * kMaxLists) != cudaSuccess) {
+        cudaGetLastError();
+        p->h_counts = nullptr;   // refinement is refused without it (rt60bands_batch)
+    }
     {
         int tc, nt, ng;
         if (p->kind == 0 && band_decimation_parent(n) && c2c_energy_layout(p->c2c, &tc, &nt, &ng)) {
@@ -417,6 +467,7 @@ int bands_plan_kind(const aa_bands_plan* p) { return p ? p->kind : AA_ERR_INVALI
 void bands_plan_destroy(aa_bands_plan* p) {
     if (!p) return;
     if (p->c2c) c2c_plan_destroy(p->c2c);
+    if (p->h_counts) cudaFreeHost(p->h_counts);
     free_two_level(&p->twN);
     for (auto& d : p->dec) {
         if (d.c2c) c2c_plan_destroy(d.c2c);
@@ -439,7 +490,9 @@ int bands_classify(const aa_bands_plan* plan, const aa_band* bands, int nb, doub
         if (rc != AA_OK) return rc;
     }
     std::vector<BandClass> classes;
-    classify_bands(plan, hb, sample_rate_hz, freq_scale, true, fits, &classes);
+    std::vector<int> limits;
+    level_limits(fits, band_decimation_limit(), false, &limits);
+    classify_bands(plan, hb, sample_rate_hz, freq_scale, true, limits[0], &classes);
     for (const BandClass& c : classes)
         for (size_t j = 0; j < c.bands.size(); ++j) out_decimation[c.map.map[j]] = c.D;
     return AA_OK;
@@ -453,7 +506,8 @@ size_t bands_workspace_bytes(const aa_bands_plan* p, int rows, int nb) {
 int rt60bands_batch(const aa_bands_plan* plan, const float* d_x, long long row_stride, int n_rows,
                     const int* d_start_idx, const aa_band* bands, int nb, double tw_oct, const aa_decay_params* p,
                     double* d_metrics_out, float* d_band_signal_out, void* d_ws, size_t ws_bytes,
-                    cudaStream_t stream) {
+                    cudaStream_t stream, const aa_bands_options* opts, aa_bands_stats* stats) {
+    if (stats) memset(stats, 0, sizeof(*stats));
     AA_REQUIRE(plan && d_x && d_start_idx && bands && p && d_metrics_out && d_ws, AA_ERR_INVALID_ARGUMENT,
                "null argument");
     AA_REQUIRE(nb >= 1 && nb <= AA_MAX_BANDS, AA_ERR_INVALID_ARGUMENT, "band count out of range");
@@ -482,22 +536,56 @@ int rt60bands_batch(const aa_bands_plan* plan, const float* d_x, long long row_s
                               stream, &hb);
         if (rc != AA_OK) return rc;
     }
-    // decimation classes of this call (classify_bands above)
-    std::vector<BandClass> classes;
-    classify_bands(plan, hb, p->sample_rate_hz, freq_scale, !smoothing && d_band_signal_out == nullptr, p, &classes);
+    // levels of this call: decimation classes per limit (classify_bands above), coarsest first
+    const int opt_max_d = (opts && opts->max_decimation > 0) ? clamp_band_decimation(opts->max_decimation) : band_decimation_limit();
+    const bool refine = !(opts && opts->refine < 0);
+    const double cert_k = (opts && opts->cert_safety > 0.0) ? opts->cert_safety : kCertSafety;
+    const double cert_w = (opts && opts->cert_window > 0.0) ? opts->cert_window : kCertWindow;
+    const int cert_min_span = (opts && opts->cert_min_span > 0) ? opts->cert_min_span : kCertMinSpan;
+    const double cert_tol = (opts && opts->cert_tol > 0.0) ? opts->cert_tol : kCertTol;
+    const bool metrics_only = !smoothing && d_band_signal_out == nullptr;
+    std::vector<int> limits;
+    level_limits(p, opt_max_d, refine, &limits);
+    std::vector<Level> levels;
+    int n_lists = 0;
+    for (size_t li = 0; li < limits.size(); ++li) {
+        Level lv;
+        lv.limit = limits[li];
+        classify_bands(plan, hb, p->sample_rate_hz, freq_scale, metrics_only, lv.limit, &lv.classes);
+        for (size_t c = 0; c < lv.classes.size(); ++c) {
+            lv.list_of_class[c] = (li > 0) ? n_lists++ : -1;
+            for (size_t j = 0; j < lv.classes[c].bands.size(); ++j) {
+                const int b = lv.classes[c].map.map[j];
+                lv.class_of[b] = (int)c;
+                lv.j_of[b] = (int)j;
+                lv.d_of[b] = lv.classes[c].D;
+            }
+        }
+        levels.push_back(lv);
+        if (li == 0 && lv.classes.size() == 1 && lv.classes[0].D == 1) break;   // nothing is decimated: one level
+    }
+    AA_REQUIRE(n_lists <= kMaxLists, AA_ERR_UNSUPPORTED, "too many refinement lists");
+    const std::vector<BandClass>& classes = levels[0].classes;
     const bool one_class = classes.size() == 1 && classes[0].D == 1;
+    AA_REQUIRE(one_class || levels.size() == 1 || plan->h_counts != nullptr, AA_ERR_CUDA,
+               "pinned host memory for the refinement counters is missing");
+    if (stats) {
+        stats->n_levels = (int)levels.size();
+        for (size_t li = 0; li < levels.size() && li < 4; ++li) stats->level_limit[li] = levels[li].limit;
+    }
     // rows per chunk that fit the workspace; the classes share the signal / scratch / partial buffers
     ClassFootprint fp;
     if (!one_class) {
-        for (const BandClass& bc : classes) {
-            const C2CPlan* c2c = bc.sub ? bc.sub->c2c : plan->c2c;
-            int tile_c = 0, n_tiles = 0, n_groups = 0;
-            c2c_energy_layout(c2c, &tile_c, &n_tiles, &n_groups);
-            const size_t nbc = bc.bands.size();
-            fp.y_floats = std::max(fp.y_floats, nbc * (size_t)(bc.sub ? bc.sub->y_stride : plan->y_stride));
-            fp.scratch_c = std::max(fp.scratch_c, nbc * (size_t)(bc.sub ? bc.sub->M : M));
-            fp.part_floats = std::max(fp.part_floats, nbc * (size_t)n_tiles * (size_t)n_groups);
-        }
+        for (size_t li = 0; li < levels.size(); ++li)
+            for (const BandClass& bc : levels[li].classes) {
+                const C2CPlan* c2c = bc.sub ? bc.sub->c2c : plan->c2c;
+                int tile_c = 0, n_tiles = 0, n_groups = 0;
+                c2c_energy_layout(c2c, &tile_c, &n_tiles, &n_groups);
+                const size_t nbc = (li == 0) ? bc.bands.size() : 1;   // later levels run unit lists in batches that fit
+                fp.y_floats = std::max(fp.y_floats, nbc * (size_t)(bc.sub ? bc.sub->y_stride : plan->y_stride));
+                fp.scratch_c = std::max(fp.scratch_c, nbc * (size_t)(bc.sub ? bc.sub->M : M));
+                fp.part_floats = std::max(fp.part_floats, nbc * (size_t)n_tiles * (size_t)n_groups);
+            }
     }
     const ClassFootprint* fpp = one_class ? nullptr : &fp;
     long long rc_rows = 0;
@@ -511,12 +599,17 @@ int rt60bands_batch(const aa_bands_plan* plan, const float* d_x, long long row_s
     }
     AA_REQUIRE(rc_rows >= 1, AA_ERR_WORKSPACE, "workspace too small for one row (see aa_bands_workspace_bytes)");
     const Layout lay = make_layout(plan, rc_rows, nb, smoothing, fpp);
+    if (stats) {
+        stats->rows_per_chunk = (int)rc_rows;
+        stats->n_chunks = (int)((n_rows + rc_rows - 1) / rc_rows);
+    }
     float2* d_X = reinterpret_cast<float2*>(ws + lay.off_X);
     float* d_y = reinterpret_cast<float*>(ws + lay.off_y);
     float2* d_Z = reinterpret_cast<float2*>(ws + lay.off_y);
     float2* d_scr = reinterpret_cast<float2*>(ws + lay.off_scratch);
     BandDev* d_class_bands = d_bands + AA_MAX_BANDS;
-    double* d_tmp_metrics = reinterpret_cast<double*>(ws + lay.off_tmp_metrics);
+    int* d_counts = reinterpret_cast<int*>(ws + lay.off_counts);
+    int* d_lists = reinterpret_cast<int*>(ws + lay.off_lists);
 
     for (long long r0 = 0; r0 < n_rows; r0 += rc_rows) {
         const long long rows = (n_rows - r0 < rc_rows) ? (n_rows - r0) : rc_rows;
@@ -548,60 +641,114 @@ int rt60bands_batch(const aa_bands_plan* plan, const float* d_x, long long row_s
             if (rc != AA_OK) return rc;
         }
         if (!one_class) {
-            // ---- 2 + 3 per decimation class: masked inverse on the class's grid, tile energies, band_fit, scatter
-            for (const BandClass& bc : classes) {
-                const int nbc = (int)bc.bands.size();
-                const long long units_c = rows * nbc;
-                const int D = bc.D;
-                const C2CPlan* c2c = bc.sub ? bc.sub->c2c : plan->c2c;
-                const int n_c = bc.sub ? bc.sub->n : N;
-                const int M_c = bc.sub ? bc.sub->M : M;
-                const int ystride_c = bc.sub ? bc.sub->y_stride : plan->y_stride;
-                // nested stage timing per class (aa_profile_ms("band_class_d<D>")): the kernels inside keep their own scopes
-                static char class_names[kMaxBandDecimation + 1][24];
-                if (!class_names[1][0])
-                    for (int d = 0; d <= kMaxBandDecimation; ++d) snprintf(class_names[d], sizeof(class_names[d]), "band_class_d%d", d);
-                ProfScope class_prof(class_names[D <= kMaxBandDecimation ? D : 0], stream);
-                rc = store_band_table(bc.bands.data(), nbc, d_class_bands, stream);
-                if (rc != AA_OK) return rc;
-                SrcDesc s{};
-                s.mode = SRC_BAND_PACKED;
-                s.base = d_X;
-                s.unit_stride = plan->x_stride;
-                s.n_valid = M_c;
-                s.conj = 1;
-                s.n_bands = nbc;
-                s.bands = d_class_bands;
-                s.bands_have_tables = 1;
-                s.freq_scale = freq_scale;
-                s.N = n_c;
-                s.M = M_c;
-                s.twN = bc.sub ? bc.sub->twN.dev : plan->twN.dev;
-                // the spectra of this path are stored time-advanced (untangle_kernel): y[j] = band signal at start + D j
-                int tile_c = 0, n_tiles = 0, n_groups = 0;
-                AA_REQUIRE(c2c_energy_layout(c2c, &tile_c, &n_tiles, &n_groups), AA_ERR_UNSUPPORTED,
-                           "decimated plan without tile energies");
-                float* d_part = reinterpret_cast<float*>(ws + lay.off_part);
-                DstDesc d = make_dst_complex(reinterpret_cast<float2*>(d_y), ystride_c / 2, M_c, 1,
-                                             1.0f / ((float)M_c * (float)D));
-                d.energy = d_part;
-                d.energy_stride = (long long)n_tiles * n_groups;
-                rc = c2c_exec(c2c, s, d, units_c, d_scr, stream);
-                if (rc != AA_OK) return rc;
-                {
-                    ProfScope prof("band_fit", stream);
-                    rc = launch_band_fit(d_y, ystride_c, d_part, (long long)n_tiles * n_groups, n_groups, n_tiles,
-                                         2 * tile_c, n_c, units_c, &pk, d_start_idx + r0, nbc, 8, d_tmp_metrics, stream, D, N,
-                                         1);
-                    if (rc != AA_OK) return rc;
+            // ---- 2 + 3 per level and decimation class: masked inverse on the class's grid, tile energies, band_fit.
+            // Level 0 runs every unit; a unit whose fits band_fit does not certify is appended to the list of the class
+            // that owns its band on the next finer level, and the host reads the list lengths between levels.
+            // a list holds at most one entry per (row, band of its class): lists of a level share rows x nb entries
+            long long list_off[kMaxLists + 1];
+            list_off[0] = 0;
+            for (size_t lj = 1; lj < levels.size(); ++lj)
+                for (size_t cj = 0; cj < levels[lj].classes.size(); ++cj) {
+                    const int id = levels[lj].list_of_class[cj];
+                    list_off[id + 1] = list_off[id] + rows * (long long)levels[lj].classes[cj].bands.size();
                 }
-                const long long total = units_c * AA_MAX_FITS;
-                int gx = (int)((total + 255) / 256);
-                if (gx > 1024) gx = 1024;
-                scatter_metrics_kernel<<<gx, 256, 0, stream>>>(d_tmp_metrics, d_metrics_out + r0 * nb * AA_MAX_FITS, rows, nbc,
-                                                              nb, bc.map);
-                rc = launch_check("scatter_metrics_kernel");
-                if (rc != AA_OK) return rc;
+            if (levels.size() > 1) AA_CUDA_TRY(cudaMemsetAsync(d_counts, 0, sizeof(int) * kMaxLists, stream));
+            for (size_t li = 0; li < levels.size(); ++li) {
+                const Level& lv = levels[li];
+                if (li > 0) {   // list lengths written by the previous levels
+                    publish_counts_kernel<<<1, kMaxLists, 0, stream>>>(d_counts, plan->h_counts, n_lists);
+                    rc = launch_check("publish_counts_kernel");
+                    if (rc != AA_OK) return rc;
+                    AA_CUDA_TRY(cudaStreamSynchronize(stream));
+                }
+                for (size_t ci = 0; ci < lv.classes.size(); ++ci) {
+                    const BandClass& bc = lv.classes[ci];
+                    const int nbc = (int)bc.bands.size();
+                    const int list_id = lv.list_of_class[ci];
+                    const long long todo = (li == 0) ? rows * nbc : (long long)plan->h_counts[list_id];
+                    if (todo <= 0) continue;
+                    if (stats && li < 4) stats->level_units[li] += todo;
+                    const int D = bc.D;
+                    const C2CPlan* c2c = bc.sub ? bc.sub->c2c : plan->c2c;
+                    const int n_c = bc.sub ? bc.sub->n : N;
+                    const int M_c = bc.sub ? bc.sub->M : M;
+                    const int ystride_c = bc.sub ? bc.sub->y_stride : plan->y_stride;
+                    // nested stage timing per class (aa_profile_ms("band_class_d<D>")): the kernels inside keep their own scopes
+                    static char class_names[kMaxBandDecimation + 1][24];
+                    if (!class_names[1][0])
+                        for (int d = 0; d <= kMaxBandDecimation; ++d) snprintf(class_names[d], sizeof(class_names[d]), "band_class_d%d", d);
+                    ProfScope class_prof(li == 0 ? class_names[D <= kMaxBandDecimation ? D : 0] : "band_refine", stream);
+                    rc = store_band_table(bc.bands.data(), nbc, d_class_bands, stream);
+                    if (rc != AA_OK) return rc;
+                    int tile_c = 0, n_tiles = 0, n_groups = 0;
+                    AA_REQUIRE(c2c_energy_layout(c2c, &tile_c, &n_tiles, &n_groups), AA_ERR_UNSUPPORTED,
+                               "decimated plan without tile energies");
+                    // where the class's results go, and where its uncertified units go
+                    BandFitCert cert{};
+                    cert.on = (D > 1 && li + 1 < levels.size()) ? 1 : 0;
+                    cert.w = (float)cert_w;
+                    cert.tol = (float)cert_tol;
+                    for (int f = 0; f < AA_MAX_FITS; ++f) {   // shorter fits need more points for the same slope error
+                        const double range = (f < pk.n_fits) ? pk.fit_hi_db[f] - fmax(pk.fit_lo_db[f], pk.fit_lower_limit_db) : 30.0;
+                        cert.fit_scale[f] = (float)fmax(1.0, 30.0 / fmax(range, 1.0));
+                    }
+                    cert.counts = d_counts;
+                    cert.lists = d_lists;
+                    for (int j = 0; j < nbc; ++j) {
+                        const int b = bc.map.map[j];
+                        cert.out_band[j] = (short)b;
+                        cert.m[j] = (float)(cert_k * band_quadrature_error(bands[b], D, sr));
+                        cert.min_span[j] = cert_min_span;
+                        if (cert.on) {
+                            size_t ln = li + 1;   // next level on which the band is sampled more finely
+                            while (ln + 1 < levels.size() && levels[ln].d_of[b] >= D) ++ln;
+                            const Level& nx = levels[ln];
+                            cert.next_list[j] = (short)nx.list_of_class[nx.class_of[b]];
+                            cert.next_off[j] = list_off[nx.list_of_class[nx.class_of[b]]];
+                            cert.next_j[j] = (short)nx.j_of[b];
+                            cert.next_nbc[j] = (short)nx.classes[(size_t)nx.class_of[b]].bands.size();
+                        }
+                    }
+                    // unit lists run in batches that fit the buffers sized for level 0
+                    long long batch = todo;
+                    if (li > 0) {
+                        const long long by_y = (long long)((size_t)rows * fp.y_floats / (size_t)ystride_c);
+                        const long long by_s = (long long)((size_t)rows * fp.scratch_c / (size_t)M_c);
+                        const long long by_p = (long long)((size_t)rows * fp.part_floats / ((size_t)n_tiles * (size_t)n_groups));
+                        batch = std::max(1LL, std::min(by_y, std::min(by_s, by_p)));
+                    }
+                    for (long long u0 = 0; u0 < todo; u0 += batch) {
+                        const long long units_c = std::min(batch, todo - u0);
+                        const int* d_map = (li == 0) ? nullptr : d_lists + list_off[list_id] + u0;
+                        SrcDesc s{};
+                        s.mode = SRC_BAND_PACKED;
+                        s.base = d_X;
+                        s.unit_stride = plan->x_stride;
+                        s.n_valid = M_c;
+                        s.conj = 1;
+                        s.n_bands = nbc;
+                        s.unit_map = d_map;
+                        s.bands = d_class_bands;
+                        s.bands_have_tables = 1;
+                        s.freq_scale = freq_scale;
+                        s.N = n_c;
+                        s.M = M_c;
+                        s.twN = bc.sub ? bc.sub->twN.dev : plan->twN.dev;
+                        // the spectra of this path are stored time-advanced (untangle_kernel): y[j] = band signal at start + D j
+                        float* d_part = reinterpret_cast<float*>(ws + lay.off_part);
+                        DstDesc d = make_dst_complex(reinterpret_cast<float2*>(d_y), ystride_c / 2, M_c, 1,
+                                                     1.0f / ((float)M_c * (float)D));
+                        d.energy = d_part;
+                        d.energy_stride = (long long)n_tiles * n_groups;
+                        rc = c2c_exec(c2c, s, d, units_c, d_scr, stream);
+                        if (rc != AA_OK) return rc;
+                        ProfScope prof("band_fit", stream);
+                        rc = launch_band_fit(d_y, ystride_c, d_part, (long long)n_tiles * n_groups, n_groups, n_tiles,
+                                             2 * tile_c, n_c, units_c, &pk, d_start_idx + r0, nbc, nb, d_map, &cert, 8,
+                                             d_metrics_out + r0 * nb * AA_MAX_FITS, stream, D, N, 1);
+                        if (rc != AA_OK) return rc;
+                    }
+                }
             }
             continue;
         }
@@ -651,7 +798,7 @@ int rt60bands_batch(const aa_bands_plan* plan, const float* d_x, long long row_s
             // revisit only the tiles with the start sample, a crossing or fit points
             ProfScope prof("band_fit", stream);
             rc = launch_band_fit(d_y, plan->y_stride, d_part, (long long)n_tiles * n_groups, n_groups, n_tiles,
-                                 2 * tile_c, N, units, &pk, d_start_idx + r0, nb, 8,
+                                 2 * tile_c, N, units, &pk, d_start_idx + r0, nb, nb, nullptr, nullptr, 8,
                                  d_metrics_out + r0 * nb * AA_MAX_FITS, stream);
             if (rc != AA_OK) return rc;
         } else if (!smoothing) {

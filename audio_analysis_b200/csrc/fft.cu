@@ -150,8 +150,9 @@ __device__ __forceinline__ float2 fetch(const SrcDesc& s, long long unit, int id
         }
         return v;
     } else if (kSrc == SRC_BAND_PACKED) {
-        const long long row = unit / s.n_bands;
-        const BandDev& b = s.bands[unit - row * s.n_bands];
+        const long long um = s.unit_map ? (long long)__ldg(s.unit_map + unit) : unit;
+        const long long row = um / s.n_bands;
+        const BandDev& b = s.bands[um - row * s.n_bands];
         const int mk = s.M - idx;
         const bool in_k = (idx >= b.k_first && idx <= b.k_last), in_m = (mk >= b.k_first && mk <= b.k_last);
         if (!in_k && !in_m) return make_float2(0.f, 0.f);
@@ -289,10 +290,11 @@ __global__ void __launch_bounds__(P::kThreads, cols_min_blocks(P::kThreads, kSrc
     const int unit = blockIdx.x / groups;
     const int col0 = (blockIdx.x - unit * groups) * P::G;
     if (kSrc == SRC_BAND_PACKED) {
-        const int row = unit / src.n_bands;
+        const int um = src.unit_map ? __ldg(src.unit_map + unit) : unit;
+        const int row = um / src.n_bands;
         RegSrcBand s;
         s.X = (const float2*)src.base + (size_t)row * src.unit_stride;
-        s.b = src.bands[unit - row * src.n_bands];
+        s.b = src.bands[um - row * src.n_bands];
         s.freq_scale = src.freq_scale;
         s.M = src.M;
         s.twN = src.twN;

@@ -82,8 +82,10 @@ struct SrcDesc {
     int n_valid;            // logical elements (complex for 0/3/4/5, real samples for 1/2) that exist
     int conj;               // conjugate the produced value
     int clip;               // SRC_REAL_PACKED: clip samples to [-1, 1] (deconvolve.py:137)
-    // band modes: unit = row * n_bands + band
+    // band modes: unit = row * n_bands + band, or unit_map[unit] = row * n_bands + band when a unit list is given
+    // (bands.cu: the full-rate redo of the decimated units whose fits are not certified)
     int n_bands;
+    const int* unit_map;
     const BandDev* bands;
     int bands_have_tables;  // every bands[i].mask points at a table (required by the register-pass kernels)
     double freq_scale;      // rfftfreq: f_k = float(k * freq_scale)
@@ -164,8 +166,9 @@ AA_HD float2 src_inner(const SrcDesc& s, long long unit, int idx) {
             return make_float2(a, b);
         }
         case SRC_BAND_PACKED: {
-            long long row = unit / s.n_bands;
-            const BandDev& b = s.bands[unit - row * s.n_bands];
+            const long long um = s.unit_map ? (long long)s.unit_map[unit] : unit;
+            long long row = um / s.n_bands;
+            const BandDev& b = s.bands[um - row * s.n_bands];
             const float2* X = (const float2*)s.base + row * s.unit_stride;
             float2 yk = band_Y(s, X, b, idx);
             float2 ym = band_Y(s, X, b, s.M - idx);
@@ -173,8 +176,9 @@ AA_HD float2 src_inner(const SrcDesc& s, long long unit, int idx) {
             return pack_half_spectrum(yk, ym, twiddle2(s.twN, idx));
         }
         case SRC_BAND_FULL: {
-            long long row = unit / s.n_bands;
-            const BandDev& b = s.bands[unit - row * s.n_bands];
+            const long long um = s.unit_map ? (long long)s.unit_map[unit] : unit;
+            long long row = um / s.n_bands;
+            const BandDev& b = s.bands[um - row * s.n_bands];
             const float2* X = (const float2*)s.base + row * s.unit_stride;
             int half = s.N / 2;
             if (idx <= half) return band_Y(s, X, b, idx);

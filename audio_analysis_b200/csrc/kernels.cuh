@@ -40,10 +40,38 @@ int launch_box_smooth(const float* d_in, float* d_out, long long stride, const i
 namespace aa {
 
 // band EDC / fits from the energy partials written by the register-pass rows kernel (bandfit.cu)
+//
+// BandFitCert: addressing of a class's results and, for a decimated level, the certification of its fits.
+//   out_band[j]  : position of class band j in the caller's table (always used)
+//   on           : decide per unit whether the decimated fits may be kept (band_fit_kernel: "certification");
+//                  a unit that is not certified is appended to list next_list[j] (which starts at lists + next_off[j]
+//                  and whose length is counts[next_list[j]]) as row * next_nbc[j] + next_j[j]
+//   m[j]         : half-width of the crossing window in decimated samples of a straight decay (safety factor x the
+//                  host's quadrature-error model of band j at this decimation, bands.cu: band_quadrature_error)
+//   w            : a crossing window may span at most w x (decimated samples between the fit's end points)
+//   min_span[j]  : decimated samples a certified 30 dB fit of band j needs between its end points (the steps of a low
+//                  band's curve make the fit sensitive to which end samples the grid includes);
+//                  fit f needs min_span[j] x fit_scale[f] (shorter fits need more)
+struct BandFitCert {
+    int on;
+    float w;
+    float tol;   // largest modelled relative slope change a certified fit may suffer from its crossing windows
+    float fit_scale[AA_MAX_FITS];
+    int min_span[AA_MAX_BANDS];
+    float m[AA_MAX_BANDS];
+    short out_band[AA_MAX_BANDS];
+    short next_list[AA_MAX_BANDS], next_j[AA_MAX_BANDS], next_nbc[AA_MAX_BANDS];
+    long long next_off[AA_MAX_BANDS];
+    int* counts;
+    int* lists;
+};
+
+// unit = row * nbc + j (dense) or d_unit_map[unit] = row * nbc + j; cert == NULL: nbc == out_nb, identity band map
 int launch_band_fit(const float* d_y, long long y_stride, const float* d_part, long long part_stride, int n_groups,
                     int n_tiles, int tile_len, int n, long long n_units, const aa_decay_params* p,
-                    const int* d_start_idx, int start_div, int min_samples, double* d_rt60_out, cudaStream_t stream,
-                    int decim = 1, int full_n = 0, int aligned = 0);
+                    const int* d_start_idx, int nbc, int out_nb, const int* d_unit_map, const BandFitCert* cert,
+                    int min_samples, double* d_rt60_out, cudaStream_t stream, int decim = 1, int full_n = 0,
+                    int aligned = 0);
 
 }  // namespace aa
 

@@ -342,9 +342,27 @@ def bands_classify(n: int, dev: torch.device, bands: Sequence[Tuple[int, Optiona
     return [int(v) for v in out]
 
 
+# units per refinement level of the most recent rt60bands call on this process: {"limits": [...], "units": [...]}
+last_bands_stats: Dict[str, object] = {"limits": [], "units": [], "chunks": 0}
+
+
+def bands_options(max_decimation: int = 0, refine: Optional[bool] = None, cert_safety: float = 0.0,
+                  cert_window: float = 0.0, cert_min_span: int = 0, cert_tol: float = 0.0) -> nat.BandsOptions:
+    """Per-call options of the band stage (aa_bands_options).  max_decimation 1 = every band at full rate (the
+    reference's estimator), 0 = process default; refine False keeps every first-level result uncertified."""
+    o = nat.BandsOptions()
+    o.max_decimation = int(max_decimation)
+    o.refine = 0 if refine is None else (1 if refine else -1)
+    o.cert_safety = float(cert_safety)
+    o.cert_window = float(cert_window)
+    o.cert_min_span = int(cert_min_span)
+    o.cert_tol = float(cert_tol)
+    return o
+
+
 def rt60bands(rows: Rows, start_idx: torch.Tensor, bands: Sequence[Tuple[int, Optional[float], Optional[float]]],
               transition_width_octaves: float, params: nat.DecayParams, want_band_signals: bool = False,
-              workspace_bytes: Optional[int] = None):
+              workspace_bytes: Optional[int] = None, options: Optional[nat.BandsOptions] = None):
     """RT60 table [B, n_bands, 3] (float64, NaN = None; columns follow params' fit order)."""
     if not rows.uniform:
         raise ValueError("rt60bands needs rows of equal length (group channels by length)")
@@ -357,14 +375,20 @@ def rt60bands(rows: Rows, start_idx: torch.Tensor, bands: Sequence[Tuple[int, Op
     if budget < one:
         budget = one
     allrows = int(lib.aa_bands_workspace_bytes(plan.handle, b, nb))
-    ws = workspace(min(budget, allrows), dev)
+    ws_bytes = min(budget, allrows)
+    ws = workspace(ws_bytes, dev)
     metrics = torch.empty((b, nb, nat.AA_MAX_FITS), dtype=torch.float64, device=dev)
     sig = torch.empty((b, nb, rows.n), dtype=torch.float32, device=dev) if want_band_signals else None
     barr = band_array(bands)
+    stats = nat.BandsStats()
     with torch.cuda.device(dev):
-        nat.check(lib.aa_rt60bands_batch(
+        nat.check(lib.aa_rt60bands_batch_ex(
             plan.handle, _ptr(rows.x), rows.stride, b, _ptr(start_idx), barr, nb, float(transition_width_octaves),
-            C.byref(params), _ptr(metrics), _ptr(sig), _ptr(ws), ws.numel(), _stream_ptr()))
+            C.byref(params), _ptr(metrics), _ptr(sig), _ptr(ws), ws_bytes, _stream_ptr(),
+            C.byref(options) if options is not None else None, C.byref(stats)))
+    last_bands_stats["limits"] = [int(stats.level_limit[i]) for i in range(int(stats.n_levels))]
+    last_bands_stats["units"] = [int(stats.level_units[i]) for i in range(int(stats.n_levels))]
+    last_bands_stats["chunks"] = int(stats.n_chunks)
     return metrics, sig
 
 

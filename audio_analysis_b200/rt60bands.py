@@ -179,8 +179,10 @@ def decimation_classes(bands: Sequence[BandDefinition], n: int, sample_rate_hz: 
 
 
 def run_rt60_bands(rows: engine.Rows, sample_rate_hz: int, settings: Rt60BandsAnalysisSettings,
-                   start_idx=None, bands: Optional[Sequence[BandDefinition]] = None, want_band_signals: bool = False):
-    """Device-level call: returns (metrics tensor [B, nb, 3], bands, plan, start_idx, band signals or None)."""
+                   start_idx=None, bands: Optional[Sequence[BandDefinition]] = None, want_band_signals: bool = False,
+                   options=None, workspace_bytes: Optional[int] = None):
+    """Device-level call: returns (metrics tensor [B, nb, 3], bands, plan, start_idx, band signals or None).
+    `options`: engine.bands_options(...) - decimation / certification of the band stage (None = defaults)."""
     if rows.n < 8:  # reference rt60bands.py:346-347
         raise ValueError("Not enough samples for rt60bands analysis.")
     bands = list(bands) if bands is not None else _build_band_definitions(settings, sample_rate_hz)
@@ -200,7 +202,8 @@ def run_rt60_bands(rows: engine.Rows, sample_rate_hz: int, settings: Rt60BandsAn
         if ign > 0:
             start_idx = torch.clamp(start_idx + min(ign, rows.n), max=rows.n).to(torch.int32)
     metrics, sig = engine.rt60bands(rows, start_idx, band_triples(bands), float(settings.transition_width_octaves),
-                                    params, want_band_signals=want_band_signals)
+                                    params, want_band_signals=want_band_signals, workspace_bytes=workspace_bytes,
+                                    options=options)
     return metrics, bands, plan, start_idx, sig
 
 

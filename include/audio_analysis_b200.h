@@ -181,17 +181,40 @@ void aa_bands_plan_destroy(aa_bands_plan* plan);
 /* 0 = direct mixed radix, 1 = Bluestein on n/2, 2 = Bluestein on n (odd n) */
 int aa_bands_plan_kind(const aa_bands_plan* plan);
 /*
- * Band decimation (rows of 288,000 / 192,000 samples, metrics only): the samples y[start + D j] of a band signal are
- * the length n / D inverse transform of the band's spectrum folded into [0, n / 2D].  A band whose mask support lies
- * inside one Nyquist zone [m n/2D, (m+1) n/2D] of the decimated rate folds without overlap, so those samples ARE
- * samples of the reference's band signal (rt60bands.py:170-175); its Schroeder integral (decay.py:150-158) is taken
- * on that grid with a trapezoid end correction.  D in {2, 3, 4, 6, 8, 12, 16, 24}, D <= max_decimation (1 = off);
- * default 16, or the environment variable AA_BANDS_DECIMATION.  The limit also depends on the fits a call asks for:
- * T30-only calls use up to max_decimation; a call with a fit shorter than 28 dB or starting above -2.5 dB (T20, EDT)
- * keeps D <= 4.  Measured against the full-rate path over 106,496 band metrics: <= 2 outside the 0.5 % / 1 ms
- * tolerance, 99.99 % within 2.7e-3 (T30, D <= 16) and 1.0e-3 (T20, D <= 4); tools/decimation_tail.py.
- * aa_bands_classify reports the factor chosen for each band (host only, no device work).
+ * Band decimation with certified refinement (rows of 288,000 / 192,000 samples, metrics only).
+ * The samples y[start + D j] of a band signal are the length n / D inverse transform of the band's spectrum folded
+ * into [0, n / 2D].  A band whose mask support lies inside one Nyquist zone [m n/2D, (m+1) n/2D] of the decimated rate
+ * folds without overlap, so those samples ARE samples of the reference's band signal (rt60bands.py:170-175); its
+ * Schroeder integral (decay.py:150-158) is taken on that grid with trapezoid end terms.  That sum is an estimate of the
+ * reference's full-rate sum, so every (row, band) unit is CERTIFIED before its fits are kept: the reference's level
+ * crossings (decay.py:173-199) lie in a window around the decimated ones (modelled quadrature error x cert_safety),
+ * and moving a fit's end points across those windows must change its slope by less than cert_tol (estimated from the
+ * distance of the curve from the fitted line at the end points; window <= cert_window x span, >= cert_min_span
+ * decimated points per 30 dB fit).  The line fit itself (decay.py:224-249) weights the first and last decimated
+ * sample by the part of their cell inside the reference's sample range.  Units that fail are redone on the next level: D <= max_decimation (default 16, or the environment
+ * variable AA_BANDS_DECIMATION) -> D <= 4 -> full rate, whose results are the reference's estimator itself.
+ * A call with a fit shorter than 28 dB or starting above -2.5 dB (T20, EDT) starts at D <= 4.
+ * D in {2, 3, 4, 6, 8, 12, 16, 24}; max_decimation 1 = everything at full rate.
+ * aa_bands_classify reports the first-level factor of each band (host only, no device work).
+ * With refinement the call synchronises `stream` with the host once per level and chunk of rows (it reads the
+ * lengths of the unit lists); one plan must not be used by two host threads at the same time.
  */
+typedef struct aa_bands_options {
+    int32_t max_decimation;  /* 0 = process default (aa_bands_set_decimation) */
+    int32_t refine;          /* 0 = default (on), 1 = on, -1 = off: keep every first-level result (round-1 behaviour) */
+    double cert_safety;      /* 0 = default 9 */
+    double cert_window;      /* 0 = default 0.015 */
+    double cert_tol;         /* 0 = default 3e-3 */
+    int32_t cert_min_span;   /* 0 = default 240 */
+    int32_t reserved;
+} aa_bands_options;
+typedef struct aa_bands_stats {
+    int32_t n_levels;
+    int32_t level_limit[4];  /* decimation limit of each level (last = 1 when refinement is on) */
+    int64_t level_units[4];  /* (row, band) units processed on each level */
+    int32_t n_chunks;        /* chunks of rows the workspace forced */
+    int32_t rows_per_chunk;
+} aa_bands_stats;
 int aa_bands_get_decimation(void);
 void aa_bands_set_decimation(int max_decimation);
 int aa_bands_classify(const aa_bands_plan* plan, const aa_band* bands, int32_t n_bands, double transition_width_octaves,
@@ -298,6 +321,16 @@ int aa_deconvolve_batch(const aa_deconv_plan* plan, const float* d_sweep, int32_
                         int32_t remove_dc, double target_peak, int32_t norm_group, int32_t n_out,
                         float* d_ir_out, int64_t ir_stride, void* d_workspace, size_t workspace_bytes,
                         void* stream);
+
+/*
+ * aa_rt60bands_batch_ex - aa_rt60bands_batch with per-call options (NULL = defaults) and, optionally, the number of
+ * units each refinement level processed (HOST struct, filled when the call returns).
+ */
+int aa_rt60bands_batch_ex(const aa_bands_plan* plan, const float* d_x, int64_t row_stride, int32_t n_rows,
+                          const int32_t* d_start_idx, const aa_band* bands, int32_t n_bands,
+                          double transition_width_octaves, const aa_decay_params* p, double* d_metrics_out,
+                          float* d_band_signal_out, void* d_workspace, size_t workspace_bytes, void* stream,
+                          const aa_bands_options* options, aa_bands_stats* stats_out);
 
 #ifdef __cplusplus
 }
