@@ -72,25 +72,84 @@ def shard_range(n_items: int, rank: int, world_size: int) -> Tuple[int, int]:
     return begin, min(int(n_items), begin + per)
 
 
+class TableGatherer:
+    """The path's one collective, made cheap: the per-row tables of a rank are packed into ONE pre-allocated byte
+    buffer (a fixed-size record per row) and travel in ONE `dist.gather` to rank `dst`, whose receive buffer is
+    allocated once.  Build it during warm-up (the first NCCL call on a communicator sets up the peer channels and
+    costs hundreds of milliseconds), then call `gather` every step.
+
+    `like`: {name: tensor} giving dtype and trailing shape of every table; `rows_per_rank`: the common (padded) shard
+    size.  Tables are packed in sorted-name order.
+    """
+
+    def __init__(self, like: Dict[str, torch.Tensor], rows_per_rank: int, dst: int = 0):
+        self.rank, self.size = world()
+        self.dst = int(dst)
+        self.per = int(rows_per_rank)
+        self.names = sorted(like)
+        self.meta = {}
+        off = 0
+        for name in self.names:
+            t = like[name]
+            tail = tuple(int(v) for v in t.shape[1:])
+            width = t.element_size()
+            for v in tail:
+                width *= v
+            off = (off + 7) // 8 * 8          # keep every field 8-byte aligned inside the record
+            self.meta[name] = (off, width, t.dtype, tail)
+            off += width
+        self.record = (off + 15) // 16 * 16
+        dev = like[self.names[0]].device
+        self.send = torch.zeros((self.per, self.record), dtype=torch.uint8, device=dev)
+        self.recv = None
+        if self.rank == self.dst and self.size > 1:
+            self.recv = torch.empty((self.size * self.per, self.record), dtype=torch.uint8, device=dev)
+            self.parts = list(self.recv.view(self.size, self.per, self.record).unbind(0))
+
+    def pack(self, tables: Dict[str, torch.Tensor]) -> torch.Tensor:
+        for name in self.names:
+            off, width, dtype, tail = self.meta[name]
+            t = tables[name]
+            rows = int(t.shape[0])
+            if rows > self.per or t.dtype != dtype or tuple(int(v) for v in t.shape[1:]) != tail:
+                raise ValueError(f"table {name!r} does not match the gatherer's layout")
+            self.send[:rows, off:off + width].copy_(t.contiguous().view(rows, -1).view(torch.uint8))
+        return self.send
+
+    def unpack(self, buf: torch.Tensor, n_items: int) -> Dict[str, torch.Tensor]:
+        out = {}
+        for name in self.names:
+            off, width, dtype, tail = self.meta[name]
+            out[name] = buf[:n_items, off:off + width].contiguous().view(dtype).view((n_items,) + tail)
+        return out
+
+    def gather(self, tables: Dict[str, torch.Tensor], n_items: Optional[int] = None,
+               unpack: bool = True) -> Optional[Dict[str, torch.Tensor]]:
+        """One collective.  Returns the gathered tables on `dst` (None elsewhere, or when `unpack` is False: the
+        packed records then sit in `self.recv`)."""
+        send = self.pack(tables)
+        if self.size == 1:
+            n = int(tables[self.names[0]].shape[0]) if n_items is None else int(n_items)
+            return self.unpack(send, n) if unpack else None
+        if self.rank == self.dst:
+            dist.gather(send, self.parts, dst=self.dst)
+            if not unpack:
+                return None
+            n = self.size * self.per if n_items is None else int(n_items)
+            return self.unpack(self.recv, n)
+        dist.gather(send, None, dst=self.dst)
+        return None
+
+
 def gather_tables(tables: Dict[str, torch.Tensor], n_items: int, dst: int = 0) -> Optional[Dict[str, torch.Tensor]]:
     """Gather per-row tables (first dimension = this rank's rows, in shard order) to rank `dst`.
 
-    Returns {name: tensor with n_items rows} on `dst`, None elsewhere.  Shards may have different
-    sizes (the last one is short); rows are padded to the common shard size for the collective.
+    Returns {name: tensor with n_items rows} on `dst`, None elsewhere.  Shards may have different sizes (the last
+    one is short); rows are padded to the common shard size and packed into one record per row, so the exchange is
+    a single collective (TableGatherer; build one and reuse it when gathering every step).
     """
     rank, size = world()
     if size == 1:
         return {k: v[:n_items] for k, v in tables.items()}
     per = (int(n_items) + size - 1) // size
-    out: Dict[str, torch.Tensor] = {}
-    for name in sorted(tables):
-        t = tables[name]
-        pad = torch.zeros((per,) + tuple(t.shape[1:]), dtype=t.dtype, device=t.device)
-        pad[: t.shape[0]] = t
-        if rank == dst:
-            parts: List[torch.Tensor] = [torch.empty_like(pad) for _ in range(size)]
-            dist.gather(pad, parts, dst=dst)
-            out[name] = torch.cat(parts, dim=0)[:n_items]
-        else:
-            dist.gather(pad, None, dst=dst)
-    return out if rank == dst else None
+    return TableGatherer(tables, per, dst).gather(tables, n_items)

@@ -33,7 +33,7 @@ def run_hot_path(rows: engine.Rows, sample_rate_hz: int,
                  bands_settings: Optional[Rt60BandsAnalysisSettings] = None,
                  waterfall_settings: Optional[WaterfallAnalysisSettings] = None,
                  want_edc: bool = True, do_bands: bool = True, do_csd: bool = True,
-                 validate: bool = False, edc_out=None) -> HotPathOut:
+                 validate: bool = False, edc_out=None, bands_options=None) -> HotPathOut:
     ds = decay_settings or DecayAnalysisSettings()
     dec = run_decay(rows, sample_rate_hz, ds, want_edc=want_edc, edc_out=edc_out)
     metrics = bands = plan = None
@@ -42,7 +42,8 @@ def run_hot_path(rows: engine.Rows, sample_rate_hz: int,
         bd = bs.decay_settings
         same_zero = (bool(bd.trim_to_peak) == bool(ds.trim_to_peak)
                      and float(bd.ignore_leading_seconds) == float(ds.ignore_leading_seconds))
-        metrics, bands, plan, _, _ = run_rt60_bands(rows, sample_rate_hz, bs, start_idx=dec.start if same_zero else None)
+        metrics, bands, plan, _, _ = run_rt60_bands(rows, sample_rate_hz, bs, start_idx=dec.start if same_zero else None,
+                                                    options=bands_options)
     csd = csd_plan = None
     if do_csd:
         ws = waterfall_settings or WaterfallAnalysisSettings()
@@ -78,7 +79,7 @@ def run_hot_path_host(x_host, sample_rate_hz: int,
                       bands_settings: Optional[Rt60BandsAnalysisSettings] = None,
                       waterfall_settings: Optional[WaterfallAnalysisSettings] = None,
                       chunk_rows: int = 256, want_edc: bool = True, do_bands: bool = True, do_csd: bool = True,
-                      device=None, reuse: Optional[HostPathOut] = None) -> HostPathOut:
+                      device=None, reuse: Optional[HostPathOut] = None, bands_options=None) -> HostPathOut:
     """The hot path for a HOST batch [B, N] (numpy array or torch CPU tensor, ideally pinned): float32 samples, or
     int16 mono PCM as it sits in the reference's WAV inputs (decoded on the device with io.py:46-64's rule,
     sample / 32768; half the bytes over PCIe).
@@ -156,7 +157,7 @@ def run_hot_path_host(x_host, sample_rate_hz: int,
         smoothing = int(ds.edc_smoothing_window_samples or 0) > 1
         out = run_hot_path(rows, sample_rate_hz, ds, bands_settings, waterfall_settings, want_edc=want_edc,
                            do_bands=do_bands, do_csd=do_csd, validate=False,
-                           edc_out=edc_all[r0:r1] if (want_edc and not smoothing) else None)
+                           edc_out=edc_all[r0:r1] if (want_edc and not smoothing) else None, bands_options=bands_options)
         if want_edc and smoothing:
             edc_all[r0:r1].copy_(out.decay.edc_db)
         ev = torch.cuda.Event()

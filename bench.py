@@ -7,8 +7,9 @@
 Metric: IR-seconds analysed per second for third-octave RT60 + broadband EDC + CSD waterfall.
 Workload: config 5 of BASELINE.json (6 s @ 48 kHz mono IRs, 288,000 samples), sharded by IR:
 each GPU analyses `--rows` IRs per step (default 8192 = the 8-GPU shard of the 65,536-IR config),
-so N GPUs analyse N * rows IRs per step (weak scaling, no data-path collective; one NCCL gather of
-the metric tables per step).
+so N GPUs analyse N * rows IRs per step (weak scaling, no data-path collective; one packed NCCL gather
+of the metric tables per step, inside the timed step).  The full 65,536-IR config at N = 1 is a rate metric
+over the same rows: it is not run as one batch.
 
 One step = decay (EDC curve + EDT/T20/T30 fits + early-decay time) + rt60bands (third-octave, T30) +
 waterfall (18 slices x 1705 bins) over the whole batch.  `value` is timed with the inputs resident in
@@ -207,8 +208,16 @@ def run_ours(args):
     rows = engine.make_rows(x_dev)
     torch.cuda.synchronize()
 
-    def step_device():
-        return run_hot_path(rows, SR, ds, bs, ws, want_edc=True)
+    def step_device(bands_options=None):
+        return run_hot_path(rows, SR, ds, bs, ws, want_edc=True, bands_options=bands_options)
+
+    # the one collective (N > 1): the metric tables of every rank, packed into one record per row, one dist.gather per
+    # step INSIDE the timed step.  The gatherer is built and first used during warm-up: the first NCCL call on the
+    # communicator sets up the peer channels (hundreds of ms, reported as gather_first_call_ms).
+    gatherer = None
+
+    def tables_of(o):
+        return {"band_rt60": o.band_metrics, "fits": o.decay.fits, "early10": o.decay.early10, "start": o.decay.start}
 
     def barrier():
         if world > 1:
@@ -220,19 +229,40 @@ def run_ours(args):
     sampler.wait_ready()
     for _ in range(max(3, args.warmup)):
         out = step_device()
+    gather_first_ms = None
+    if world > 1:
+        barrier()
+        g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        g0.record()
+        gatherer = distributed.TableGatherer(tables_of(out), rows_n)
+        gatherer.gather(tables_of(out), unpack=False)
+        g1.record()
+        barrier()
+        gather_first_ms = g0.elapsed_time(g1)
+        for _ in range(2):
+            gatherer.gather(tables_of(out), unpack=False)
     barrier()
     launches0 = lib.aa_kernel_launch_count()
     lib.aa_profile_enable(1)   # CUDA events around every library kernel, on the launching stream
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     sampler.mark()
+    gather_events = []
     e0.record()
     for _ in range(args.steps):
         out = step_device()
+        if gatherer is not None:
+            ga, gb = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            ga.record()
+            gatherer.gather(tables_of(out), unpack=False)
+            gb.record()
+            gather_events.append((ga, gb))
     e1.record()
     barrier()
     clocks = sampler.stop()
     ms_total = e0.elapsed_time(e1)
+    band_levels = dict(engine.last_bands_stats)
+    gather_ms = (sum(a.elapsed_time(b) for a, b in gather_events) / len(gather_events)) if gather_events else None
     lib.aa_profile_collect()
     stage_names = ["edc", "fft_cols", "fft_rows", "untangle", "fft_cols_band", "fft_rows_band", "band_fit", "band_edc", "csd"]
     stage_ms = {k: lib.aa_profile_ms(k.encode()) / args.steps for k in stage_names}
@@ -240,6 +270,7 @@ def run_ours(args):
     # band stage per decimation class (nested scopes around the class's kernels)
     class_ms = {f"D{d}": round(lib.aa_profile_ms(f"band_class_d{d}".encode()) / args.steps, 4) for d in (1, 2, 3, 4, 6, 8, 12, 16, 24)}
     class_ms = {k: v for k, v in class_ms.items() if v > 0.0}
+    lib_refine_ms = lib.aa_profile_ms(b"band_refine") / args.steps
     lib.aa_profile_enable(0)
     launches = (lib.aa_kernel_launch_count() - launches0) // max(1, args.steps)
     t = torch.tensor([ms_total], dtype=torch.float64, device=dev)
@@ -296,10 +327,12 @@ def run_ours(args):
     traffic = None
     traffic_note = None
     try:
-        tj = json.loads((Path(__file__).resolve().parent / "profiles" / "r01_traffic.json").read_text())
+        prof = Path(__file__).resolve().parent / "profiles"
+        tpath = prof / "r02_traffic.json" if (prof / "r02_traffic.json").exists() else prof / "r01_traffic.json"
+        tj = json.loads(tpath.read_text())
         per_row = tj["stages"][dominant]["dram_bytes_per_row"]
         traffic = round(per_row * rows_n / max(1, stage_scopes[dominant]), 1)
-        traffic_note = (f"profiles/r01_traffic.json: {per_row:.0f} B of DRAM traffic per row for this stage "
+        traffic_note = (f"profiles/{tpath.name}: {per_row:.0f} B of DRAM traffic per row for this stage "
                         f"({tj['stages'][dominant]['kernels']} kernels, {tj['rows']}-row capture) x rows / launches")
     except Exception:
         pass
@@ -318,6 +351,26 @@ def run_ours(args):
                                     "kernel": "whole band stage against SURVEY 8d's 4 B/sample (read x once)",
                                     "share_of_step": round(ms_bands / ms_step, 4)}
 
+    # ---- the same step with every band at full rate (the reference's estimator, no decimation) and with the first
+    # decimation level kept uncertified (round-1 behaviour): the price of the default's parity guarantee, side by side
+    def timed_variant(opt, steps=3):
+        step_device(opt)
+        barrier()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(steps):
+            step_device(opt)
+        b.record()
+        barrier()
+        t = torch.tensor([a.elapsed_time(b)], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item()) / steps
+        return {"value": round(ir_seconds_per_step / (ms / 1e3), 1), "unit": UNIT, "ms_per_step": round(ms, 3)}
+
+    variants = {"full_rate_bands": timed_variant(engine.bands_options(max_decimation=1)),
+                "uncertified_first_level": timed_variant(engine.bands_options(refine=False))}
+
     # ---- end to end through the public batch API: pinned host input -> chunked H2D overlapped with the kernels ->
     # tables and CSD slices D2H (run_hot_path_host)
     from audio_analysis_b200.pipeline import run_hot_path_host
@@ -335,7 +388,7 @@ def run_ours(args):
         res = step_e2e(res)     # warm: pinned result buffers exist and are reused from here on
         barrier()
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        steps_e2e = max(1, min(args.steps, 3))
+        steps_e2e = max(3, min(args.steps, 10))
         a.record()
         for _ in range(steps_e2e):
             res = step_e2e(res)
@@ -373,21 +426,20 @@ def run_ours(args):
         except Exception as exc:
             e2e["pcm16_input"] = {"value": None, "error": str(exc)[:200]}
         del x_host, res
+        # headline e2e = the reference's wire format (16-bit PCM taps, include/analysis/recorder.hpp:55-90); the
+        # float32 line stays beside it
+        pcm = e2e.get("pcm16_input") or {}
+        if pcm.get("value"):
+            f32 = {k: e2e[k] for k in ("value", "unit", "ms_per_step", "h2d_bytes_per_step", "d2h_bytes_per_step")}
+            e2e.update({"value": pcm["value"], "ms_per_step": pcm["ms_per_step"],
+                        "h2d_bytes_per_step": pcm["h2d_bytes_per_step"], "d2h_bytes_per_step": pcm["d2h_bytes_per_step"],
+                        "input": "int16 PCM in pinned host memory, decoded on the device (sample / 32768, io.py:46-64)",
+                        "float32_input": f32, "steps": steps_e2e})
+            del e2e["pcm16_input"]
+        else:
+            e2e["input"] = "float32 in pinned host memory"
     except Exception as exc:  # pinned allocation can fail on small hosts
         e2e = {"value": None, "unit": UNIT, "error": str(exc)[:200]}
-
-    # ---- the one collective: gather the metric tables to rank 0 (timed, not part of `value`)
-    gather_ms = None
-    if world > 1:
-        tables = {"band_rt60": out.band_metrics, "fits": out.decay.fits, "early10": out.decay.early10,
-                  "start": out.decay.start}
-        barrier()
-        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        a.record()
-        distributed.gather_tables(tables, world * rows_n)
-        b.record()
-        barrier()
-        gather_ms = a.elapsed_time(b)
 
     # ---- CPU baseline: the oracle port on the host cores, bounded sample (rank 0, single GPU run only)
     cpu = None
@@ -409,13 +461,24 @@ def run_ours(args):
             "config": {"workload": f"config5 shard: {rows_n} x {n / SR:.0f} s @48 kHz mono IRs per GPU "
                                    f"(third-octave RT60 + broadband EDC/EDT/T20/T30 + CSD 18x{n_bins})",
                        "rows_per_gpu": rows_n, "samples_per_row": n, "bands": 26,
-                       "band_decimation": {"max": int(lib.aa_bands_get_decimation()), "ms_per_class": class_ms,
-                                           "bands_per_factor": {str(d): dec.count(d) for d in sorted(set(dec))}},
+                       "band_decimation": {
+                           "max": int(lib.aa_bands_get_decimation()), "ms_per_class": class_ms,
+                           "bands_per_factor": {str(d): dec.count(d) for d in sorted(set(dec))},
+                           "levels": band_levels.get("limits"), "units_per_level": band_levels.get("units"),
+                           "redo_fraction": round(sum(band_levels.get("units", [0])[1:]) / max(1, units), 5),
+                           "refine_ms": round(lib_refine_ms, 4),
+                           "note": "every (row, band) fit of the first level is certified or redone at D <= 4, then at "
+                                   "full rate (DESIGN.md 4.3); tests: 0 of 213k metrics outside 0.5 % / 1 ms"},
+                       "e2e_returns": "metric tables + CSD slices (EDC curves stay in HBM, fetched on demand)",
+                       "gather": ("one packed dist.gather of the metric tables per step, inside the timed step"
+                                  if world > 1 else None),
                        "l2": "inputs (rows*samples*4 B per GPU) are larger than L2; no flush needed"},
             "host_binding": (f"{len(numa_cpus)} CPUs local to the GPU" if numa_cpus else None),
             "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
             "roofline": roofline, "roofline_by_kernel": by_kernel, "cpu_baseline": cpu,
-            "gather_ms": gather_ms,
+            "variants": variants,
+            "gather_ms": (round(gather_ms, 4) if gather_ms is not None else None),
+            "gather_first_call_ms": (round(gather_first_ms, 2) if gather_first_ms is not None else None),
         }
         print(json.dumps(line))
     if world > 1:
