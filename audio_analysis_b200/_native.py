@@ -50,6 +50,7 @@ EXPORTED_SYMBOLS = (
     "aa_rt60bands_batch",
     "aa_rt60bands_batch_ex",
     "aa_csd_batch",
+    "aa_csd_smooth_batch",
     "aa_stft_db_batch",
     "aa_modal_cloud_batch",
     "aa_pcm16_to_float_batch",
@@ -182,6 +183,8 @@ def _declare(lib: C.CDLL) -> None:
                                           C.POINTER(BandsStats)]
     lib.aa_csd_batch.restype = C.c_int
     lib.aa_csd_batch.argtypes = [vp, i64, vp, i32, i32, vp, vp, vp, i32, C.POINTER(CsdParams), vp, vp]
+    lib.aa_csd_smooth_batch.restype = C.c_int
+    lib.aa_csd_smooth_batch.argtypes = [vp, i32, vp, i32, i32, i32, i32, vp, vp, i32, vp, vp, i32, i32, C.c_double, vp]
     lib.aa_stft_db_batch.restype = C.c_int
     lib.aa_stft_db_batch.argtypes = [vp, i64, vp, i32, i32, vp, vp, i32, i32, i32, C.c_double, i32, vp, vp]
     lib.aa_modal_cloud_batch.restype = C.c_int

@@ -25,6 +25,12 @@ class BundleRunSettings:
 
 
 def run_bundle_report(bundle_root: str | Path, settings: Optional[BundleRunSettings] = None) -> Path:
+    """Reference bundle.py:35-74.  All taps go through `report.run_reports_batch`: their PCM16 payloads are staged
+    once in pinned memory and decoded on the device, and every channel shares the kernel launches.  Under
+    `torch.distributed` (one process per GPU) the taps are sharded over the ranks in contiguous blocks
+    (`distributed.shard_range`); every rank writes the reports of its taps, rank 0 writes the index."""
+    from . import distributed
+
     settings = settings or BundleRunSettings()
     root = Path(bundle_root)
     meta = json.loads((root / "meta.json").read_text())
@@ -32,20 +38,28 @@ def run_bundle_report(bundle_root: str | Path, settings: Optional[BundleRunSetti
     reports_root = root / settings.reports_subdir
     reports_root.mkdir(parents=True, exist_ok=True)
 
-    wavs = [root / "taps" / f"{tap}.wav" for tap in taps]
-    bases = [reports_root / tap / tap for tap in taps]
+    rank, size = distributed.world()
+    lo, hi = distributed.shard_range(len(taps), rank, size)
+    mine = taps[lo:hi]
+    wavs = [root / "taps" / f"{tap}.wav" for tap in mine]
+    bases = [reports_root / tap / tap for tap in mine]
     for b in bases:
         b.parent.mkdir(parents=True, exist_ok=True)
     run_reports_batch(wavs, bases, settings.report_settings)
+    if size > 1:
+        import torch.distributed as dist
 
-    lines = [
-        "# IR Bundle Report\n",
-        f"**Bundle:** `{root}`\n",
-        f"**Sample rate:** {meta.get('sample_rate_hz')}\n",
-        f"**Length (samples):** {meta.get('length_samples')}\n",
-        "\n## Taps\n",
-    ]
-    lines += [f"- [{tap}]({settings.reports_subdir}/{tap}/{tap}_report.md)" for tap in taps]
+        dist.barrier()
+
     index = reports_root / "bundle_report.md"
-    index.write_text("\n".join(lines) + "\n")
+    if rank == 0:
+        lines = [
+            "# IR Bundle Report\n",
+            f"**Bundle:** `{root}`\n",
+            f"**Sample rate:** {meta.get('sample_rate_hz')}\n",
+            f"**Length (samples):** {meta.get('length_samples')}\n",
+            "\n## Taps\n",
+        ]
+        lines += [f"- [{tap}]({settings.reports_subdir}/{tap}/{tap}_report.md)" for tap in taps]
+        index.write_text("\n".join(lines) + "\n")
     return index

@@ -1,17 +1,20 @@
-"""Command line for the accelerated path: `decay`, `rt60bands`, `waterfall`, `bundle`, `spectrogram`, `modalcloud`.
+"""Command line for the accelerated path: `decay`, `rt60bands`, `waterfall`, `bundle`, `deconvolve`, `spectrogram`,
+`modalcloud`.
 
     python -m analyse.cli decay --input ir.wav --no_show
     python -m analyse.cli rt60bands --input ir.wav --mono --band_mode third --no_show
     python -m analyse.cli waterfall --input ir.wav --no_show
     python -m analyse.cli bundle --input analysis_runs/20250101_120000
+    python -m analyse.cli deconvolve --recorded_wav_file_path capture.wav --sweep_wav_file_path sweep.wav
     python -m analyse.cli spectrogram --input ir.wav --no_show
     python -m analyse.cli modalcloud --input ir.wav --no_show
 
 Argument names, defaults and quirks follow the reference's `analyse/cli.py`
-(decay :461-531, rt60bands :536-636, waterfall :1010-1100, bundle :377-388, spectrogram :842-917, modalcloud :1105-1145), including
+(decay :461-531, rt60bands :536-636, waterfall :1010-1100, bundle :377-388, deconvolve :392-455 / :1219-1246,
+spectrogram :842-917, modalcloud :1105-1145), including
 `decay --compute_edt` defaulting to true, `rt60bands --trim_to_peak` being impossible to
 switch off, and the tri-state `rt60bands --legend_values`.  Each command prints the same
-summary text as the reference.  The reference's other eight subcommands are outside this
+summary text as the reference.  The reference's other seven subcommands are outside this
 build and are rejected by argparse.
 """
 
@@ -22,6 +25,7 @@ from pathlib import Path
 from typing import Optional, Sequence
 
 from .bundle import BundleRunSettings, run_bundle_report
+from .deconvolve import DeconvolveSettings, default_output_ir_path, deconvolve_from_wav_files
 from .decay import DecayAnalysisSettings, DecayPlotSettings, plot_decay_from_wav_file, summarise_decay_results_text
 from .modalcloud import (ModalCloudAnalysisSettings, ModalCloudPlotSettings, plot_modal_cloud_from_wav_file,
                          summarise_modal_cloud_results_text)
@@ -52,6 +56,24 @@ def build_parser() -> argparse.ArgumentParser:
     bundle.add_argument("--input", dest="bundle_root", type=str, required=True, help="Bundle root folder")
     bundle.add_argument("--reports-subdir", dest="reports_subdir", type=str, default="reports",
                         help="Subfolder under bundle root to write outputs (default: reports)")
+
+    dc = sub.add_parser("deconvolve", help="Deconvolve recorded sweep output into an impulse response WAV.")
+    dc.add_argument("--recorded_wav_file_path", type=str, required=True,
+                    help="Recorded output WAV (mono or stereo, 48 kHz expected).")
+    dc.add_argument("--sweep_wav_file_path", type=str, required=True,
+                    help="Original sweep WAV that was played (mono or stereo, 48 kHz expected).")
+    dc.add_argument("--output_ir_wav_file_path", type=str, default=None,
+                    help="Output IR WAV path. If omitted, writes next to recorded file as: <recorded_stem>_ir.wav")
+    dc.add_argument("--regularization_relative", type=float, default=1e-10,
+                    help="Regularization as fraction of max(|X|^2). Default: 1e-10.")
+    dc.add_argument("--normalise_peak", action=BoolOpt, default=True,
+                    help="If true, peak-normalise the output IR. Default: true.")
+    dc.add_argument("--target_peak", type=float, default=0.95,
+                    help="Target peak value if normalise_peak is enabled. Default: 0.95.")
+    dc.add_argument("--remove_dc", action=BoolOpt, default=True,
+                    help="If true, remove DC offset from the output IR. Default: true.")
+    dc.add_argument("--output_length_mode", type=str, choices=["recorded", "full_fft"], default="recorded",
+                    help="Length of output IR. Default: recorded.")
 
     decay = sub.add_parser("decay", help="Schroeder EDC + T20/T30/RT60 decay estimation")
     _io_arguments(decay, "a PNG: <basename>_decay.png")
@@ -318,6 +340,26 @@ def run_modalcloud_command(a: argparse.Namespace) -> str:
     return summarise_modal_cloud_results_text(results)
 
 
+def run_deconvolve_command(a: argparse.Namespace) -> str:
+    """Reference cli.py:1219-1246: same settings mapping and the same confirmation lines."""
+    out = str(Path(a.output_ir_wav_file_path)) if a.output_ir_wav_file_path is not None \
+        else str(default_output_ir_path(a.recorded_wav_file_path))
+    settings = DeconvolveSettings(
+        regularization_relative=float(a.regularization_relative),
+        normalise_peak=bool(a.normalise_peak),
+        target_peak=float(a.target_peak),
+        remove_dc=bool(a.remove_dc),
+        output_length_mode=str(a.output_length_mode),
+    )
+    result = deconvolve_from_wav_files(str(a.recorded_wav_file_path), str(a.sweep_wav_file_path), settings, out)
+    return "\n".join([
+        f"Wrote IR WAV: {out}",
+        f"  sample_rate_hz={result.sample_rate_hz}",
+        f"  channels={result.samples.shape[1]}",
+        f"  length_seconds={result.samples.shape[0] / float(result.sample_rate_hz):.3f}",
+    ])
+
+
 def run_bundle_command(a: argparse.Namespace) -> str:
     index = run_bundle_report(str(a.bundle_root), settings=BundleRunSettings(reports_subdir=str(a.reports_subdir)))
     return f"Wrote bundle report index: {index}"
@@ -328,6 +370,7 @@ COMMANDS = {
     "rt60bands": run_rt60bands_command,
     "waterfall": run_waterfall_command,
     "bundle": run_bundle_command,
+    "deconvolve": run_deconvolve_command,
     "spectrogram": run_spectrogram_command,
     "modalcloud": run_modalcloud_command,
 }

@@ -202,6 +202,16 @@ int aa_rt60bands_batch_ex(const aa_bands_plan* plan, const float* d_x, int64_t r
                                static_cast<cudaStream_t>(stream), options, stats_out);
 }
 
+int aa_csd_smooth_batch(float* d_slices, int32_t n_rows, const int32_t* d_n_slices, int32_t max_slices, int32_t n_bins,
+                        int32_t first_bin_inside, int32_t n_bins_inside, const double* d_freq_inside,
+                        const double* d_grid_hz, int32_t n_grid, const int32_t* d_grid_segment,
+                        const int32_t* d_bin_segment, int32_t smoothing_log_bins, int32_t db_reference,
+                        double dynamic_range_db, void* stream) {
+    return aa::launch_csd_smooth(d_slices, n_rows, d_n_slices, max_slices, n_bins, first_bin_inside, n_bins_inside,
+                                 d_freq_inside, d_grid_hz, n_grid, d_grid_segment, d_bin_segment, smoothing_log_bins,
+                                 db_reference == AA_DBREF_SLICE_MAX, dynamic_range_db, static_cast<cudaStream_t>(stream));
+}
+
 int aa_stft_db_batch(const float* d_x, int64_t row_stride, const int32_t* d_lengths, int32_t uniform_length,
                      int32_t n_rows, const int32_t* d_start_idx, const int32_t* d_span, int32_t n_fft, int32_t hop_length,
                      int32_t use_hann_window, double floor_db, int32_t frames_max, float* d_out, void* stream) {

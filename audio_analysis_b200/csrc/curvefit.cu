@@ -157,8 +157,8 @@ __global__ void __launch_bounds__(kCfThreads) curve_fits_kernel(CurveArgs a) {
 // out[i] = max(floor, (1/w) * sum_{m = i - w/2}^{i + (w-1)/2} in[m]), zero outside the curve
 __global__ void box_smooth_kernel(const float* __restrict__ in, float* __restrict__ out, long long stride,
                                   const int* __restrict__ lengths, int uniform_len, const int* __restrict__ offsets,
-                                  int w, float floor_db) {
-    const int row = blockIdx.y;
+                                  int w, float floor_db, int row0) {
+    const int row = row0 + blockIdx.y;
     const int off = offsets ? offsets[row] : 0;
     const int n = (lengths ? lengths[row] : uniform_len) - off;
     const float* __restrict__ c = in + (long long)row * stride + off;
@@ -217,10 +217,15 @@ int launch_box_smooth(const float* d_in, float* d_out, long long stride, const i
     int gx = (uniform_len + 255) / 256;
     if (gx > 2048) gx = 2048;
     if (gx < 1) gx = 1;
-    box_smooth_kernel<<<dim3((unsigned)gx, (unsigned)n_rows), 256, 0, stream>>>(d_in, d_out, stride, d_lengths,
-                                                                                uniform_len, d_offsets, window,
-                                                                                (float)floor_db);
-    return launch_check("box_smooth_kernel");
+    // gridDim.y holds at most 65,535 rows: band units (rows x bands) go past that
+    for (int r0 = 0; r0 < n_rows; r0 += 65535) {
+        const int cnt = (n_rows - r0 < 65535) ? (n_rows - r0) : 65535;
+        box_smooth_kernel<<<dim3((unsigned)gx, (unsigned)cnt), 256, 0, stream>>>(d_in, d_out, stride, d_lengths, uniform_len,
+                                                                               d_offsets, window, (float)floor_db, r0);
+        int rc = launch_check("box_smooth_kernel");
+        if (rc != AA_OK) return rc;
+    }
+    return AA_OK;
 }
 
 }  // namespace aa

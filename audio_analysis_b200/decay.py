@@ -150,17 +150,28 @@ def analyse_decay_batch(
         settings = DecayAnalysisSettings()
     rows = channels if isinstance(channels, engine.Rows) else engine.make_rows(channels, device)
     out = run_decay(rows, sample_rate_hz, settings, want_edc=return_curves)
+    names = list(channel_names) if channel_names is not None else [f"ch{i}" for i in range(rows.n_rows)]
+    return decay_results(out, rows, names, settings, sample_rate_hz, return_curves)
+
+
+def decay_results(out: engine.DecayOut, rows: engine.Rows, names: Sequence[str], settings: DecayAnalysisSettings,
+                  sample_rate_hz: int, return_curves: bool = True,
+                  strict: bool = True) -> List[Optional[ChannelDecayAnalysis]]:
+    """Result records from the device tables.  strict=False: a row the reference would raise on (fewer than 4 samples
+    after trimming, decay.py:146) yields None instead of an exception (batched reports isolate such files)."""
     plan = fit_plan(settings)
     status = out.status.cpu().numpy()
-    if np.any(status == nat.AA_ROW_TOO_SHORT):
+    if strict and np.any(status == nat.AA_ROW_TOO_SHORT):
         raise ValueError(_TOO_SHORT)
     start = out.start.cpu().numpy()
     fits = out.fits.cpu().numpy()
     early = out.early10.cpu().numpy()
     curves = out.edc_db.cpu().numpy() if (return_curves and out.edc_db is not None) else None
-    names = list(channel_names) if channel_names is not None else [f"ch{i}" for i in range(rows.n_rows)]
-    results: List[ChannelDecayAnalysis] = []
+    results: List[Optional[ChannelDecayAnalysis]] = []
     for b in range(rows.n_rows):
+        if status[b] == nat.AA_ROW_TOO_SHORT:
+            results.append(None)
+            continue
         s, n = int(start[b]), int(rows.host_lengths[b])
         if curves is not None:
             edc = np.array(curves[b, s:n], dtype=np.float32)

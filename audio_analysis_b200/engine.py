@@ -287,6 +287,12 @@ _workspaces: Dict[int, torch.Tensor] = {}
 DEFAULT_WORKSPACE_BYTES = 12 << 30   # of 180 GB; 6 -> 12 GB is worth 1.2 % of the resident step, 48 GB another 0.2 %
 
 
+def slice_rows(rows: Rows, r0: int, r1: int) -> Rows:
+    """Rows [r0, r1) of a batch as a batch of their own (views, no copy)."""
+    lengths = None if rows.lengths is None else rows.lengths[r0:r1].contiguous()
+    return Rows(x=rows.x[r0:r1], lengths=lengths, n=rows.n, host_lengths=rows.host_lengths[r0:r1])
+
+
 def bands_plan(n: int, dev: torch.device) -> _BandsPlan:
     key = (dev.index if dev.index is not None else torch.cuda.current_device(), int(n))
     plan = _bands_plans.get(key)
@@ -398,15 +404,20 @@ def rt60bands(rows: Rows, start_idx: torch.Tensor, bands: Sequence[Tuple[int, Op
 
 
 def csd_params(n_fft: int, hop_length: int, use_hann_window: bool, bin_lo: int, n_bins: int, db_reference: str,
-               floor_db: float, dynamic_range_db: float) -> nat.CsdParams:
+               floor_db: float, dynamic_range_db: float, raw_db: bool = False) -> nat.CsdParams:
+    """`db_reference`: the user's setting - "slice_max", anything else means the global maximum like the reference
+    (waterfall.py:328-336).  `raw_db`: internal - no reference level and no clip (spectrogram-style output, and the
+    input of the smoothing kernel)."""
     p = nat.CsdParams()
     p.n_fft = int(n_fft)
     p.hop_length = int(hop_length)
     p.use_hann_window = 1 if use_hann_window else 0
     p.bin_lo = int(bin_lo)
     p.n_bins = int(n_bins)
-    ref = str(db_reference).lower()
-    p.db_reference = {"slice_max": nat.AA_DBREF_SLICE_MAX, "none": nat.AA_DBREF_NONE}.get(ref, nat.AA_DBREF_GLOBAL_MAX)
+    if raw_db:
+        p.db_reference = nat.AA_DBREF_NONE
+    else:
+        p.db_reference = nat.AA_DBREF_SLICE_MAX if str(db_reference).lower() == "slice_max" else nat.AA_DBREF_GLOBAL_MAX
     p.floor_db = float(floor_db)
     p.dynamic_range_db = float(max(10.0, dynamic_range_db))  # analyse/waterfall.py:338
     return p
@@ -425,6 +436,25 @@ def csd(rows: Rows, start_idx: torch.Tensor, frame_idx: torch.Tensor, n_slices: 
                                    _ptr(frame_idx), _ptr(n_slices), max_slices, C.byref(params), _ptr(out),
                                    _stream_ptr()))
     return out
+
+
+def csd_smooth(slices: torch.Tensor, n_slices: torch.Tensor, k0: int, f_in: np.ndarray, grid: np.ndarray,
+               grid_seg: np.ndarray, bin_seg: np.ndarray, window: int, db_reference: str,
+               dynamic_range_db: float) -> torch.Tensor:
+    """In place: raw dB slices [B, S_max, F] -> log-frequency smoothed, referenced and clipped (aa_csd_smooth_batch)."""
+    lib = nat.load()
+    dev = slices.device
+    b, s_max, f = (int(v) for v in slices.shape)
+    tf = torch.from_numpy(np.ascontiguousarray(f_in, dtype=np.float64)).to(dev)
+    tg = torch.from_numpy(np.ascontiguousarray(grid, dtype=np.float64)).to(dev)
+    tgs = torch.from_numpy(np.ascontiguousarray(grid_seg, dtype=np.int32)).to(dev)
+    tbs = torch.from_numpy(np.ascontiguousarray(bin_seg, dtype=np.int32)).to(dev)
+    ref = nat.AA_DBREF_SLICE_MAX if str(db_reference).lower() == "slice_max" else nat.AA_DBREF_GLOBAL_MAX
+    with torch.cuda.device(dev):
+        nat.check(lib.aa_csd_smooth_batch(_ptr(slices), b, _ptr(n_slices), s_max, f, int(k0), int(f_in.size), _ptr(tf),
+                                          _ptr(tg), int(grid.size), _ptr(tgs), _ptr(tbs), int(window), ref,
+                                          float(max(10.0, dynamic_range_db)), _stream_ptr()))
+    return slices
 
 
 # --------------------------------------------------------------------------------------

@@ -140,9 +140,10 @@ def _header(path: Path, audio_shape: Tuple[int, int], sample_rate: int, expected
 class _FileJob:
     path: Path
     basename: Path
-    audio: LoadedAudio
+    shape: Tuple[int, int]     # (samples, channels) of the file
+    sample_rate_hz: int
     names: List[str]           # analysed channel names
-    first_row: int = 0         # index of this file's first channel in the batch
+    first_row: int = 0         # index of this file's first channel in its group's batch
 
 
 def _per_channel_block(parts, have_plots, results, figure_fn, title, stem, alt, base, mono, summary) -> None:
@@ -170,8 +171,8 @@ def _render(job: _FileJob, settings: ReportSettings, decay_s, bands_s, water_s,
     have_plots = pyplot() is not None
     job.basename.parent.mkdir(parents=True, exist_ok=True)
     # header counts channels the way the reference does: mono files are shown upmixed to stereo (report.py:193-199)
-    shape = (int(job.audio.samples.shape[0]), max(2, int(job.audio.samples.shape[1])))
-    parts = [_header(job.path, shape, job.audio.sample_rate_hz, settings.expected_sample_rate_hz)]
+    shape = (int(job.shape[0]), max(2, int(job.shape[1])))
+    parts = [_header(job.path, shape, job.sample_rate_hz, settings.expected_sample_rate_hz)]
     base = job.basename
     if decay_r is not None:
         if have_plots:
@@ -226,49 +227,145 @@ def _render(job: _FileJob, settings: ReportSettings, decay_s, bands_s, water_s,
     return ReportResults(job.path, job.basename, md_path, text)
 
 
+# rows per launch of the dense-STFT blocks (spectrogram n_fft 4096: 2.3 MB per second of audio and row, modal cloud
+# n_fft 8192 the same again): bounds the [rows, frames, bins] tables to a few GB whatever the bundle size
+DENSE_BLOCK_ROWS = 64
+
+
+def _channel_names(channels: int, mono_downmix: bool) -> List[str]:
+    if channels == 1 or mono_downmix:
+        return ["mono"]
+    return ["left", "right"]
+
+
+def _analyse_group(rows: engine.Rows, sr: int, names: List[str], settings: ReportSettings, decay_s, bands_s, water_s,
+                   spec_s, modal_s):
+    """Every enabled block for one batch of equal-rate channels.  Returns per-block lists with one entry per row; an
+    entry is None (or a ValueError for the dense blocks) where the reference would have raised for that channel."""
+    from .decay import decay_results
+    from .pipeline import run_hot_path
+    from .rt60bands import metrics_to_results
+    from .waterfall import waterfall_results
+
+    out = {"decay": None, "bands": None, "water": None, "spec": None, "modal": None}
+    smoothing = int(decay_s.edc_smoothing_window_samples or 0) > 1
+    do_bands = bool(settings.run_rt60_bands) and rows.uniform
+    hot = run_hot_path(rows, sr, decay_s, bands_s, water_s, want_edc=bool(settings.run_decay),
+                       do_bands=do_bands, do_csd=bool(settings.run_waterfall), validate=False)
+    if settings.run_decay:
+        out["decay"] = decay_results(hot.decay, rows, names, decay_s, sr, return_curves=True, strict=False)
+    if settings.run_rt60_bands:
+        if do_bands:
+            out["bands"] = metrics_to_results(hot.band_metrics.cpu().numpy(), hot.bands, hot.band_fit_plan, names, sr)
+        else:   # ragged group: the band stage plans one FFT per length
+            out["bands"] = analyse_rt60_bands_batch(rows, sr, names, bands_s)
+    if settings.run_waterfall:
+        out["water"] = waterfall_results(hot.csd, hot.csd_plan, names, sr, strict=False)
+    del hot
+    peaks = None
+    for key, enabled, fn, s in (("spec", settings.run_spectrogram, analyse_spectrogram_batch, spec_s),
+                                ("modal", settings.run_modal_cloud, analyse_modal_cloud_batch, modal_s)):
+        if not enabled:
+            continue
+        res: List[Any] = []
+        for r0 in range(0, rows.n_rows, DENSE_BLOCK_ROWS):
+            r1 = min(rows.n_rows, r0 + DENSE_BLOCK_ROWS)
+            part = engine.slice_rows(rows, r0, r1)
+            try:
+                res += fn(part, sr, names[r0:r1], s)
+            except ValueError:
+                # isolate the channel(s) the reference would have raised on
+                for r in range(r0, r1):
+                    try:
+                        res += fn(engine.slice_rows(rows, r, r + 1), sr, names[r:r + 1], s)
+                    except ValueError as exc:
+                        res.append(exc)
+        out[key] = res
+    return out
+
+
 def run_reports_batch(
     input_wav_file_paths: Sequence[str | Path],
     output_basenames: Sequence[str | Path],
     settings: Optional[ReportSettings] = None,
     loaded: Optional[Sequence[LoadedAudio]] = None,
 ) -> List[ReportResults]:
-    """Reports for many WAV files with every channel analysed in shared launches."""
+    """Reports for many WAV files with every channel analysed in shared launches.
+
+    PCM16 files of one common shape (a bundle's taps, recorder.hpp:55-90) are read once into a pinned int16 staging
+    buffer and decoded on the device (wire.py); anything else goes through io.load_wav_file and is grouped by sample
+    rate.  One peak search per channel serves decay, rt60bands and waterfall (pipeline.run_hot_path).  Files are
+    rendered in order; the first file with a channel the reference would have raised on raises that ValueError after
+    the reports of the files before it have been written (the reference's loop stops at the same point,
+    bundle.py:56-67)."""
+    from . import wire
+
     settings = settings or ReportSettings()
     decay_s, bands_s, water_s = resolved_settings(settings)
-    jobs: List[_FileJob] = []
-    channels: List[np.ndarray] = []
-    names: List[str] = []
-    for i, (path, base) in enumerate(zip(input_wav_file_paths, output_basenames)):
-        audio = loaded[i] if loaded is not None else load_wav_file(
-            path, expected_sample_rate_hz=settings.expected_sample_rate_hz,
-            expected_channel_mode="mono_or_stereo", allow_mono_and_upmix_to_stereo=False)
-        chans = get_analysis_channels(audio, settings.common_use_mono_downmix_for_stereo)
-        job = _FileJob(Path(path), Path(base), audio, [n for n, _ in chans], first_row=len(channels))
-        jobs.append(job)
-        for n, c in chans:
-            channels.append(c)
-            names.append(n)
-    if not jobs:
-        return []
-    sr = jobs[0].audio.sample_rate_hz
-    same_len = len({c.size for c in channels}) == 1
-    rows = engine.make_rows(np.stack(channels, axis=0) if same_len else channels)
-    decay_r = analyse_decay_batch(rows, sr, names, decay_s) if settings.run_decay else None
-    bands_r = analyse_rt60_bands_batch(rows, sr, names, bands_s) if settings.run_rt60_bands else None
-    water_r = analyse_waterfall_batch(rows, sr, names, water_s) if settings.run_waterfall else None
     spec_s = _apply_common_overrides(settings.spectrogram_analysis_settings or SpectrogramAnalysisSettings(), settings)
     modal_s = _apply_common_overrides(settings.modal_cloud_analysis_settings or ModalCloudAnalysisSettings(), settings)
-    spec_r = analyse_spectrogram_batch(rows, sr, names, spec_s) if settings.run_spectrogram else None
-    modal_r = analyse_modal_cloud_batch(rows, sr, names, modal_s) if settings.run_modal_cloud else None
-    out = []
-    for job in jobs:
-        sl = slice(job.first_row, job.first_row + len(job.names))
-        out.append(_render(job, settings, decay_s, bands_s, water_s,
-                           None if decay_r is None else decay_r[sl],
-                           None if bands_r is None else bands_r[sl],
-                           None if water_r is None else water_r[sl],
-                           spec_s, None if spec_r is None else spec_r[sl],
-                           modal_s, None if modal_r is None else modal_r[sl]))
+    paths = [Path(p) for p in input_wav_file_paths]
+    bases = [Path(b) for b in output_basenames]
+    if not paths:
+        return []
+    mono = bool(settings.common_use_mono_downmix_for_stereo)
+    groups: List[Tuple[List[_FileJob], engine.Rows, int, List[str]]] = []
+    staged = wire.stage_pcm16(paths) if loaded is None else None
+    if staged is not None and staged.channels in (1, 2):
+        if staged.sample_rate_hz != settings.expected_sample_rate_hz:   # io.py:161-165
+            raise ValueError(f"Expected sample rate {settings.expected_sample_rate_hz} Hz, "
+                             f"but got {staged.sample_rate_hz} Hz for file {paths[0]}")
+        import torch
+
+        dev = engine._device(None)
+        pcm_dev = staged.pcm.to(dev, non_blocking=True)
+        rows = engine.pcm16_to_rows(pcm_dev, staged.frames, staged.channels, mono)
+        per = _channel_names(staged.channels, mono)
+        jobs = [_FileJob(p, b, (staged.frames, staged.channels), staged.sample_rate_hz, list(per), i * len(per))
+                for i, (p, b) in enumerate(zip(paths, bases))]
+        groups.append((jobs, rows, staged.sample_rate_hz, [n for _ in jobs for n in per]))
+    else:
+        by_rate: Dict[int, Tuple[List[_FileJob], List[np.ndarray], List[str]]] = {}
+        for i, (p, b) in enumerate(zip(paths, bases)):
+            audio = loaded[i] if loaded is not None else load_wav_file(
+                p, expected_sample_rate_hz=settings.expected_sample_rate_hz,
+                expected_channel_mode="mono_or_stereo", allow_mono_and_upmix_to_stereo=False)
+            chans = get_analysis_channels(audio, mono)
+            jobs, channels, names = by_rate.setdefault(int(audio.sample_rate_hz), ([], [], []))
+            jobs.append(_FileJob(p, b, tuple(int(v) for v in audio.samples.shape), int(audio.sample_rate_hz),
+                                 [n for n, _ in chans], first_row=len(channels)))
+            for n, c in chans:
+                channels.append(c)
+                names.append(n)
+        for sr, (jobs, channels, names) in by_rate.items():
+            same_len = len({c.size for c in channels}) == 1
+            groups.append((jobs, engine.make_rows(np.stack(channels, axis=0) if same_len else channels), sr, names))
+    rendered: Dict[Path, ReportResults] = {}
+    failed: Dict[Path, Exception] = {}
+    for jobs, rows, sr, names in groups:
+        res = _analyse_group(rows, sr, names, settings, decay_s, bands_s, water_s, spec_s, modal_s)
+        for job in jobs:
+            sl = slice(job.first_row, job.first_row + len(job.names))
+            blocks = {k: (None if v is None else v[sl]) for k, v in res.items()}
+            err = None
+            for key, msg in (("decay", "Not enough samples after trimming/ignoring to compute EDC."),
+                             ("water", "Not enough samples for STFT after trimming/ignoring (need at least n_fft).")):
+                if blocks[key] is not None and any(r is None for r in blocks[key]):
+                    err = err or ValueError(msg)
+            for key in ("spec", "modal"):
+                if blocks[key] is not None:
+                    err = err or next((r for r in blocks[key] if isinstance(r, Exception)), None)
+            if err is not None:
+                failed[job.path] = err
+                continue
+            rendered[job.path] = (job, blocks)
+    out: List[ReportResults] = []
+    for p in paths:   # the reference's order: write until the first file that fails
+        if p in failed:
+            raise failed[p]
+        job, blocks = rendered[p]
+        out.append(_render(job, settings, decay_s, bands_s, water_s, blocks["decay"], blocks["bands"], blocks["water"],
+                           spec_s, blocks["spec"], modal_s, blocks["modal"]))
     return out
 
 

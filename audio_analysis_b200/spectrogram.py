@@ -113,7 +113,8 @@ def _stft_via_slices(rows: engine.Rows, start, span, settings: SpectrogramAnalys
     out = torch.zeros((b, t_max, f), dtype=torch.float32, device=dev)
     n_frames = torch.where(span >= n_fft, 1 + torch.div(span - n_fft, hop, rounding_mode="floor"),
                            torch.zeros_like(span))
-    params = engine.csd_params(n_fft, hop, settings.use_hann_window, 0, f, "none", settings.floor_db, 1.0)
+    params = engine.csd_params(n_fft, hop, settings.use_hann_window, 0, f, "global_max", settings.floor_db, 1.0,
+                               raw_db=True)
     for j0 in range(0, t_max, nat.AA_MAX_SLICES):
         cnt = min(nat.AA_MAX_SLICES, t_max - j0)
         frames = (torch.arange(cnt, dtype=torch.int32, device=dev) + j0).unsqueeze(0).expand(b, cnt).contiguous()

@@ -142,44 +142,31 @@ def analysed_span(length: int, peak: int, settings: WaterfallAnalysisSettings, s
 # --------------------------------------------------------------------------------------
 
 
-def _moving_average_1d(values: np.ndarray, window: int) -> np.ndarray:
-    if window <= 1:
-        return values.astype(np.float32, copy=False)
-    taps = np.full(int(window), 1.0 / float(int(window)), dtype=np.float64)
-    return np.convolve(values.astype(np.float64), taps, mode="same").astype(np.float32)
-
-
-def _smooth_mag_db_log_frequency(frequency_hz: np.ndarray, magnitude_db: np.ndarray, f_min_hz: float, f_max_hz: float,
-                                 smoothing_log_bins: int, log_bins_per_octave: int) -> np.ndarray:
-    if smoothing_log_bins <= 1:
-        return magnitude_db.astype(np.float32, copy=False)
+def smoothing_tables(frequency_hz: np.ndarray, settings: WaterfallAnalysisSettings):
+    """Host side of the log-frequency smoothing (reference waterfall.py:159-176): which kept bins lie inside
+    [f_min, f_max], the uniform log2(f) grid, and for every grid point / bin the interval of the other axis that
+    np.interp would pick.  Returns None when no bin is inside (the slices then stay unsmoothed, :164-165), else
+    (k0, f_in float64, grid float64, grid_seg int32, bin_seg int32).  The arithmetic on the curves is the kernel's."""
     f = frequency_hz.astype(np.float64, copy=False)
-    m = magnitude_db.astype(np.float64, copy=False)
-    lo = float(max(1.0, f_min_hz))
-    hi = float(max(lo, f_max_hz))
-    inside = (f >= lo) & (f <= hi)
-    if not np.any(inside):
-        return magnitude_db.astype(np.float32, copy=False)
-    f_in, m_in = f[inside], m[inside]
+    lo = float(max(1.0, settings.f_min_hz))
+    hi = float(max(lo, settings.f_max_hz))
+    inside = np.flatnonzero((f >= lo) & (f <= hi))
+    if inside.size == 0:
+        return None
+    k0 = int(inside[0])
+    f_in = f[k0:k0 + inside.size]
     a, b = float(np.log2(f_in[0])), float(np.log2(f_in[-1]))
-    per_octave = int(max(16, log_bins_per_octave))
+    per_octave = int(max(16, settings.log_bins_per_octave))
     count = int(max(8, np.ceil((b - a) * per_octave))) + 1
     grid = 2.0 ** np.linspace(a, b, count, dtype=np.float64)
-    on_grid = np.interp(grid, f_in, m_in)
-    on_grid = _moving_average_1d(on_grid.astype(np.float32), int(smoothing_log_bins)).astype(np.float64)
-    result = magnitude_db.astype(np.float32, copy=True)
-    result[inside] = np.interp(f_in, grid, on_grid).astype(np.float32)
-    return result
 
+    def segments(x, xp):
+        seg = (np.searchsorted(xp, x, side="right") - 1).astype(np.int32)
+        seg[x < xp[0]] = -1
+        seg[x >= xp[-1]] = -2
+        return seg
 
-def _normalise_slices(raw_db: np.ndarray, settings: WaterfallAnalysisSettings) -> np.ndarray:
-    """Reference level and clip on the host (only used after the optional smoothing), waterfall.py:328-339."""
-    if str(settings.db_reference).lower() == "slice_max":
-        rel = raw_db - np.max(raw_db, axis=1, keepdims=True)
-    else:
-        rel = raw_db - float(np.max(raw_db))
-    dyn = float(max(10.0, settings.dynamic_range_db))
-    return np.clip(rel, -dyn, 0.0).astype(np.float32)
+    return k0, f_in, grid, segments(grid, f_in), segments(f_in, grid)
 
 
 # --------------------------------------------------------------------------------------
@@ -195,7 +182,8 @@ class WaterfallPlan:
     """
 
     def __init__(self, start, length, frames, n_slices, bin_lo: int, freq: np.ndarray, hop_length: int,
-                 sample_rate_hz: int):
+                 sample_rate_hz: int, n_fft: int = 0):
+        self.n_fft = int(n_fft)
         self._dev = {"start": start, "length": length, "frames": frames, "n_slices": n_slices}
         self._host: Dict[str, np.ndarray] = {}
         self.bin_lo = int(bin_lo)
@@ -315,14 +303,16 @@ def run_waterfall(rows: engine.Rows, sample_rate_hz: int, settings: WaterfallAna
     table_d, counts_d = _device_slice_table(table, counts, dev)
     frames_d = table_d[n_frames].contiguous()
     nslices_d = counts_d[n_frames].contiguous()
-    smoothing = int(settings.smoothing_log_bins or 0) > 1
-    params = engine.csd_params(n_fft, hop, settings.use_hann_window, bin_lo, int(freq.size),
-                               "none" if smoothing else settings.db_reference, settings.floor_db,
-                               settings.dynamic_range_db)
+    tables = smoothing_tables(freq, settings) if int(settings.smoothing_log_bins or 0) > 1 else None
+    params = engine.csd_params(n_fft, hop, settings.use_hann_window, bin_lo, int(freq.size), settings.db_reference,
+                               settings.floor_db, settings.dynamic_range_db, raw_db=tables is not None)
     start = start.contiguous()
     slices = engine.csd(rows, start, frames_d, nslices_d, params)
+    if tables is not None:   # reference waterfall.py:312-339 on the device: smooth, then reference level and clip
+        engine.csd_smooth(slices, nslices_d, *tables, int(settings.smoothing_log_bins), settings.db_reference,
+                          settings.dynamic_range_db)
     plan = WaterfallPlan(start=start, length=remaining, frames=frames_d, n_slices=nslices_d, bin_lo=bin_lo, freq=freq,
-                         hop_length=hop, sample_rate_hz=int(sample_rate_hz))
+                         hop_length=hop, sample_rate_hz=int(sample_rate_hz), n_fft=n_fft)
     if validate:
         if np.any(plan.length < n_fft):
             raise ValueError(_TOO_SHORT)
@@ -338,21 +328,23 @@ def analyse_waterfall_batch(channels, sample_rate_hz: int, channel_names: Option
     rows = channels if isinstance(channels, engine.Rows) else engine.make_rows(channels, device)
     names = list(channel_names) if channel_names is not None else [f"ch{i}" for i in range(rows.n_rows)]
     slices, plan = run_waterfall(rows, sample_rate_hz, settings, peaks)
+    return waterfall_results(slices, plan, names, sample_rate_hz)
+
+
+def waterfall_results(slices, plan: WaterfallPlan, names: Sequence[str], sample_rate_hz: int,
+                      strict: bool = True) -> List[Optional[ChannelWaterfallResult]]:
+    """Result records from the device table.  strict=False: a row the reference would raise on (too short, fewer than
+    two slices) yields None instead of an exception (batched reports isolate such files)."""
     table = slices.cpu().numpy()
-    smoothing = int(settings.smoothing_log_bins or 0) > 1
-    nyquist = float(np.fft.rfftfreq(int(settings.n_fft), d=1.0 / float(sample_rate_hz)).astype(np.float32)[-1])
-    f_lo = float(np.clip(settings.f_min_hz, 1.0, nyquist))
-    f_hi = float(np.clip(settings.f_max_hz, f_lo, nyquist))
-    results = []
-    for b in range(rows.n_rows):
+    results: List[Optional[ChannelWaterfallResult]] = []
+    for b in range(table.shape[0]):
         s = int(plan.n_slices[b])
+        if s < 2 or int(plan.length[b]) < plan.n_fft:
+            if strict:
+                raise ValueError(_TOO_SHORT if int(plan.length[b]) < plan.n_fft else _TOO_FEW_SLICES)
+            results.append(None)
+            continue
         rel = np.array(table[b, :s, :], dtype=np.float32)
-        if smoothing:
-            rel = np.stack([
-                _smooth_mag_db_log_frequency(plan.freq, row, f_lo, f_hi, int(settings.smoothing_log_bins),
-                                             int(settings.log_bins_per_octave)) for row in rel
-            ], axis=0).astype(np.float32)
-            rel = _normalise_slices(rel, settings)
         results.append(ChannelWaterfallResult(
             channel_name=str(names[b]),
             sample_rate_hz=int(sample_rate_hz),

@@ -441,6 +441,21 @@ def run_ours(args):
     except Exception as exc:  # pinned allocation can fail on small hosts
         e2e = {"value": None, "unit": UNIT, "error": str(exc)[:200]}
 
+    # ---- the other GPU configurations of BASELINE.json, a few steps each (parity for these shapes is in tests/)
+    other = {}
+    if not args.no_other_configs:
+        del x_dev, rows, out
+        torch.cuda.empty_cache()
+        try:
+            other["config3_bundle"] = bench_config3(world, rank, dev, barrier)
+        except Exception as exc:
+            other["config3_bundle"] = {"error": str(exc)[:300]}
+        try:
+            other["config4_deconvolve_chain"] = bench_config4(world, rank, dev, barrier)
+        except Exception as exc:
+            other["config4_deconvolve_chain"] = {"error": str(exc)[:300]}
+        x_dev = synth_batch_torch(min(rows_n, 256), n, SR, first_index=rank * rows_n, device=dev)   # for the CPU sample
+
     # ---- CPU baseline: the oracle port on the host cores, bounded sample (rank 0, single GPU run only)
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -476,7 +491,7 @@ def run_ours(args):
             "host_binding": (f"{len(numa_cpus)} CPUs local to the GPU" if numa_cpus else None),
             "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
             "roofline": roofline, "roofline_by_kernel": by_kernel, "cpu_baseline": cpu,
-            "variants": variants,
+            "variants": variants, "other_configs": other,
             "gather_ms": (round(gather_ms, 4) if gather_ms is not None else None),
             "gather_first_call_ms": (round(gather_first_ms, 2) if gather_first_ms is not None else None),
         }
@@ -484,6 +499,145 @@ def run_ours(args):
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
+
+
+
+def _max_ms(ms, world, dev):
+    import torch
+    import torch.distributed as dist
+
+    t = torch.tensor([ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t.item())
+
+
+def bench_config3(world, rank, dev, barrier, n_taps=256, seconds=4.0, steps=3):
+    """BASELINE.json config 3: a bundle of 256 synthetic stereo 4 s taps in the recorder's wire format (16-bit PCM WAV,
+    include/analysis/recorder.hpp:55-90) through `run_bundle_report` with decay + third-octave rt60bands: file reads
+    (page cache), pinned staging, H2D, device decode, kernels, result records and the Markdown reports - wall clock of
+    the call the user makes.  Under torchrun the taps are sharded over the ranks."""
+    import json as _json
+    import shutil
+    import tempfile
+
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+
+    from audio_analysis_b200 import engine, wire
+    from audio_analysis_b200.bundle import BundleRunSettings, run_bundle_report
+    from audio_analysis_b200.decay import DecayAnalysisSettings
+    from audio_analysis_b200.pipeline import run_hot_path
+    from audio_analysis_b200.report import ReportSettings
+    from audio_analysis_b200.rt60bands import Rt60BandsAnalysisSettings
+    from audio_analysis_b200.synth import synth_batch_torch
+
+    frames = int(seconds * SR)
+    base = "/dev/shm" if os.path.isdir("/dev/shm") and os.access("/dev/shm", os.W_OK) else None
+    root = Path(os.environ.get("AA_BENCH_BUNDLE_DIR") or os.path.join(base or tempfile.gettempdir(), "aa_bench_bundle"))
+    names = [f"tap_{i:03d}" for i in range(n_taps)]
+    if rank == 0:
+        shutil.rmtree(root, ignore_errors=True)
+        (root / "taps").mkdir(parents=True)
+        for i0 in range(0, n_taps, 64):
+            x = synth_batch_torch(2 * min(64, n_taps - i0), frames, SR, first_index=100000 + 2 * i0, device=dev)
+            pcm = (x * 32767.0).round().clamp_(-32768, 32767).to(torch.int16).cpu().numpy()
+            for k in range(pcm.shape[0] // 2):
+                wire.write_pcm16_wav(root / "taps" / f"{names[i0 + k]}.wav", np.stack([pcm[2 * k], pcm[2 * k + 1]], axis=1), SR)
+        (root / "meta.json").write_text(_json.dumps({"sample_rate_hz": SR, "length_samples": frames, "taps": names}))
+    barrier()
+    rs = ReportSettings(rt60_bands_settings=Rt60BandsAnalysisSettings(band_mode="third"), run_spectrogram=False,
+                        run_waterfall=False, run_modal_cloud=False)
+    settings = BundleRunSettings(report_settings=rs)
+    run_bundle_report(root, settings)                      # warm: plans, pinned pools, page cache
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        run_bundle_report(root, settings)
+    torch.cuda.synchronize()
+    wall_ms = _max_ms((time.perf_counter() - t0) * 1e3 / steps, world, dev)
+    # the kernels alone on the same taps (already decoded, resident)
+    lo, hi = (rank * n_taps) // world, ((rank + 1) * n_taps) // world
+    st = wire.stage_pcm16([root / "taps" / f"{t}.wav" for t in names[lo:hi]])
+    rows = engine.pcm16_to_rows(st.pcm.to(dev), st.frames, st.channels, False)
+    ds = DecayAnalysisSettings()
+    bs = Rt60BandsAnalysisSettings(band_mode="third")
+    run_hot_path(rows, SR, ds, bs, None, want_edc=True, do_csd=False)
+    barrier()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for _ in range(steps):
+        run_hot_path(rows, SR, ds, bs, None, want_edc=True, do_csd=False)
+    b.record()
+    barrier()
+    dev_ms = _max_ms(a.elapsed_time(b) / steps, world, dev)
+    if world > 1:
+        dist.barrier()
+    if rank == 0:
+        shutil.rmtree(root, ignore_errors=True)
+    ir_s = n_taps * 2 * seconds
+    return {"workload": f"bundle of {n_taps} stereo {seconds:.0f} s @48 kHz PCM16 taps ({n_taps * 2} channels x {frames} samples): "
+                        "decay (T20/T30, EDC curves) + third-octave rt60bands per channel, reports written",
+            "value": round(ir_s / (wall_ms / 1e3), 1), "unit": UNIT, "ms_per_bundle": round(wall_ms, 2),
+            "timed": "run_bundle_report wall clock (WAV payloads -> pinned int16 -> device decode -> kernels -> "
+                     "result records incl. EDC curves -> Markdown), max over ranks",
+            "resident_kernels": {"value": round(ir_s / (dev_ms / 1e3), 1), "unit": UNIT, "ms": round(dev_ms, 3)},
+            "file_seconds_per_s": round(n_taps * seconds / (wall_ms / 1e3), 1), "steps": steps}
+
+
+def bench_config4(world, rank, dev, barrier, n_captures=64, steps=3):
+    """BASELINE.json config 4: 64 synthetic captures of the 10 s log sweep of test_tones/sweep.wav's shape (13 s at
+    48 kHz = 624,000 samples: 1 s silence + sweep + 2 s tail) -> deconvolution at n_fft = 2^20 (deconvolve.py:124-193)
+    -> third-octave rt60bands + CSD waterfall on the 624,000-sample impulse responses; captures resident in HBM,
+    sharded over the ranks."""
+    import numpy as np
+    import torch
+
+    from audio_analysis_b200 import deconvolve as dv, engine
+    from audio_analysis_b200.decay import DecayAnalysisSettings
+    from audio_analysis_b200.pipeline import run_hot_path
+    from audio_analysis_b200.rt60bands import Rt60BandsAnalysisSettings
+    from audio_analysis_b200.synth import synth_batch_torch
+    from audio_analysis_b200.waterfall import WaterfallAnalysisSettings
+
+    n = 624000
+    t = np.arange(10 * SR) / SR
+    k = np.log(20000.0 / 20.0) / 10.0
+    sweep = np.zeros(n, dtype=np.float32)
+    sweep[SR:SR + t.size] = (0.5 * np.sin(2.0 * np.pi * 20.0 * (np.exp(k * t) - 1.0) / k)).astype(np.float32)
+    lo, hi = (rank * n_captures) // world, ((rank + 1) * n_captures) // world
+    mine = max(1, hi - lo)
+    # captures = sweep convolved with synthetic rooms (circular convolution at 2^20 on the device; the 2 s of silence
+    # after the sweep hold the tails)
+    rooms = synth_batch_torch(mine, 96000, SR, first_index=200000 + lo, device=dev)
+    nfft = 1 << 20
+    S = torch.fft.rfft(torch.from_numpy(sweep).to(dev), n=nfft)
+    cap = torch.fft.irfft(torch.fft.rfft(rooms, n=nfft) * S, n=nfft)[:, :n].contiguous()
+    cap = (0.9 * cap / cap.abs().amax(dim=1, keepdim=True)).contiguous()
+    rows = engine.make_rows(cap)
+    ds, bs, ws = DecayAnalysisSettings(), Rt60BandsAnalysisSettings(band_mode="third"), WaterfallAnalysisSettings()
+    sweep_t = torch.from_numpy(sweep)
+
+    def step():
+        irs, _ = dv.deconvolve_batch(rows, sweep_t, dv.DeconvolveSettings(), channels_per_file=1)
+        return run_hot_path(irs, SR, ds, bs, ws, want_edc=False)
+
+    step()
+    barrier()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for _ in range(steps):
+        out = step()
+    b.record()
+    barrier()
+    ms = _max_ms(a.elapsed_time(b) / steps, world, dev)
+    ir_s = n_captures * n / SR
+    return {"workload": f"{n_captures} captures x 13 s (624,000 samples) of a 10 s log sweep -> deconvolve (n_fft 2^20) -> "
+                        "third-octave rt60bands (Bluestein-free 13-smooth length) + CSD 18 x 1705, resident in HBM",
+            "value": round(ir_s / (ms / 1e3), 1), "unit": UNIT, "ms_per_step": round(ms, 3), "scaling": "strong",
+            "captures_per_gpu": mine, "steps": steps,
+            "band_levels": dict(engine.last_bands_stats)}
 
 
 # ----------------------------------------------------------------------------------------------
@@ -543,6 +697,8 @@ def main():
                     help="IRs per GPU per step (default 8192: config 5 sharded over 8 GPUs)")
     ap.add_argument("--samples", type=int, default=N_SAMPLES)
     ap.add_argument("--no-cpu-baseline", dest="no_cpu_baseline", action="store_true")
+    ap.add_argument("--no-other-configs", dest="no_other_configs", action="store_true",
+                    help="skip the config-3 (bundle) and config-4 (deconvolve chain) lines")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

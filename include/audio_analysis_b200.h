@@ -260,6 +260,23 @@ int aa_csd_batch(const float* d_x, int64_t row_stride, const int32_t* d_lengths,
                  void* stream);
 
 /*
+ * aa_csd_smooth_batch - the optional log-frequency smoothing of the waterfall slices, then reference level and clip.
+ * Replaces _smooth_mag_db_log_frequency / _moving_average_1d (analyse/waterfall.py:132-185) and the tail of
+ * _build_rel_db_slices (:312-339) when smoothing_log_bins > 1.
+ *  d_slices[n_rows][max_slices][n_bins] : RAW dB slices from aa_csd_batch(AA_DBREF_NONE) in, relative dB out
+ *  bins [first_bin_inside, + n_bins_inside) lie inside [f_min, f_max] (waterfall.py:162); d_freq_inside holds their
+ *  frequencies, d_grid_hz the uniform log2(f) grid (:171-176) - both float64, built by the host with the
+ *  reference's expressions - and d_grid_segment[g] / d_bin_segment[k] the interval of the other axis each point
+ *  falls in (np.interp's search; -1 = left of the first point, -2 = right of the last).
+ *  db_reference: AA_DBREF_GLOBAL_MAX or AA_DBREF_SLICE_MAX (:328-336); the clip is [-dynamic_range_db, 0] (:338-339).
+ */
+int aa_csd_smooth_batch(float* d_slices, int32_t n_rows, const int32_t* d_n_slices, int32_t max_slices, int32_t n_bins,
+                        int32_t first_bin_inside, int32_t n_bins_inside, const double* d_freq_inside,
+                        const double* d_grid_hz, int32_t n_grid, const int32_t* d_grid_segment,
+                        const int32_t* d_bin_segment, int32_t smoothing_log_bins, int32_t db_reference,
+                        double dynamic_range_db, void* stream);
+
+/*
  * aa_stft_db_batch - dense STFT magnitude in dB: every frame of the analysed segment of every row
  * (replaces _compute_stft_magnitude_db of analyse/spectrogram.py:107-160).
  *  d_start_idx[n_rows] : first analysed sample (peak + ignore), d_span[n_rows]: analysed samples from there

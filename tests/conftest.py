@@ -36,6 +36,23 @@ def load_golden(name: str) -> dict:
     return d
 
 
+def load_verb_case() -> dict:
+    """BASELINE.json configs 1-2 at their real shape (tests/golden/make_golden_verb.py): the fixture holds the
+    reference's outputs, the 1,151,844 x 2 int16 input is regenerated from its seeds and checked against the stored
+    checksum.  Returns the fixture plus x [N, 2] float32 (analyse/io.py:59) and mono = 0.5 (L + R) (io.py:90)."""
+    if str(GOLDEN_DIR) not in sys.path:
+        sys.path.insert(0, str(GOLDEN_DIR))
+    from make_golden_verb import verb_pcm16
+
+    with np.load(GOLDEN_DIR / "verb_1151844.npz") as z:
+        d = {k: z[k] for k in z.files}
+    pcm = verb_pcm16()
+    assert int(pcm.astype(np.int64).sum()) == int(d["pcm_checksum"]) and np.array_equal(pcm[24000:24064], d["pcm_head"])
+    d["x"] = (pcm.astype(np.float32) / 32768.0).astype(np.float32)
+    d["mono"] = (0.5 * (d["x"][:, 0] + d["x"][:, 1])).astype(np.float32)
+    return d
+
+
 @pytest.fixture(params=GOLDEN_CASES)
 def golden(request):
     d = load_golden(request.param)

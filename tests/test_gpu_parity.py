@@ -12,7 +12,7 @@ import pytest
 import oracle
 from _parity import (CSD_TOL_DB, FIT_ABS_TOL_S, FIT_REL_TOL, check_band_table, check_edc, check_fit_rows, note,
                      seconds_close)
-from conftest import GOLDEN_CASES, load_golden
+from conftest import GOLDEN_CASES, load_golden, load_verb_case
 
 pytestmark = pytest.mark.gpu
 
@@ -380,6 +380,44 @@ def test_band_decimation_against_oracle_and_switch():
         lib.aa_bands_set_decimation(16)
 
 
+def test_verb_sized_stereo_file_configs_1_and_2(dec):
+    """BASELINE.json configs 1-2 at their real shape (plots/example/verb_report.md:6): a stereo file of 1,151,844
+    samples per channel = 2^2 * 3 * 95987, so the band filter's circular FFT (rt60bands.py:170-175, over the WHOLE
+    file, :345-350) goes through Bluestein at 2^21 and the EDC runs at 4x the bench's row length.
+    config 1 = rt60bands --mono third-octave; config 2 = decay + waterfall per channel; fixture from the unmodified
+    reference (tests/golden/make_golden_verb.py)."""
+    from audio_analysis_b200 import rt60bands as rb, waterfall as wf
+    g = load_verb_case()
+    n = int(g["n"])
+    assert n == 1151844 and g["x"].shape == (n, 2)
+    for c, name in enumerate(("left", "right")):
+        x = np.ascontiguousarray(g["x"][:, c])
+        r = dec.analyse_decay_for_channel(x, SR, name, dec.DecayAnalysisSettings(compute_edt=True))
+        assert r.analysis_start_sample_index == int(g[f"{name}_decay_start"])
+        assert r.edc_db.size == int(g[f"{name}_decay_len"])
+        check_edc(f"verb/{name}", r.edc_db[::64], g[f"{name}_decay_edc_db_dec64"])
+        check_fit_rows(f"verb/{name}", _fits_table(r.fits), g[f"{name}_decay_fits"])
+        assert r.early_decay_10db_time_seconds == pytest.approx(float(g[f"{name}_decay_early10"]), abs=1e-4)
+        w = wf.analyse_waterfall_for_channel(x, SR, name, wf.WaterfallAnalysisSettings())
+        assert w.analysis_start_sample_index == int(g[f"{name}_wf_start"])
+        assert w.analysis_length_samples == int(g[f"{name}_wf_length"])
+        assert np.array_equal(w.slice_times_seconds, g[f"{name}_wf_times"])
+        assert np.array_equal(w.frequency_hz, g["wf_freq"])
+        _check_slices(f"verb/{name}", w.slice_magnitude_rel_db, g[f"{name}_wf_rel_db"])
+    s = rb.Rt60BandsAnalysisSettings(band_mode="third", include_t20=True, include_edt=True)
+    r = rb.analyse_rt60_bands_for_channel(g["mono"], SR, "mono", s)
+    names = [b.name for b in r.band_definitions]
+    assert names == [str(v) for v in g["mono_bands_third_names"]]
+    check_band_table("verb/mono/third", _band_table(r, names), g["mono_bands_third_metrics"])
+    # the stereo file as one batch of two rows (the file-level entry points loop channels; the batch path must agree)
+    both = rb.analyse_rt60_bands_batch(np.ascontiguousarray(g["x"].T), SR, ["left", "right"],
+                                       rb.Rt60BandsAnalysisSettings(band_mode="third"))
+    for c in range(2):
+        ob = oracle.band_metrics(np.ascontiguousarray(g["x"][:, c]), SR, oracle.BandParams(band_mode="third"))
+        want = np.array([[np.nan if ob["metrics"][nm][0] is None else ob["metrics"][nm][0]] for nm in names])
+        check_band_table(f"verb/ch{c}/third", _band_table(both[c], names)[:, :1], want)
+
+
 def _band_tail(got: np.ndarray, ref: np.ndarray):
     rel = np.abs(got - ref) / np.abs(ref)
     outside = (rel > FIT_REL_TOL) & (np.abs(got - ref) > FIT_ABS_TOL_S)
@@ -724,6 +762,46 @@ def test_full_size_properties_config5_rows():
     assert rel <= 5e-3
 
 
+def test_hot_path_batch_of_2048_config5_rows_sampled_against_the_oracle():
+    """pipeline.run_hot_path at the bench's shape (rows of 288,000 samples, 2048 of them in one batch: one peak search,
+    decay + third-octave bands + CSD): rows sampled across the batch are checked against the oracle, and the whole
+    batch against the properties that need no oracle."""
+    import torch
+    from audio_analysis_b200 import decay, engine, rt60bands as rb, waterfall as wf
+    from audio_analysis_b200.pipeline import run_hot_path
+    from audio_analysis_b200.synth import synth_batch_torch
+    rows_n, n = 2048, 288000
+    x = synth_batch_torch(rows_n, n, SR, device="cuda", first_index=60000)
+    ds = decay.DecayAnalysisSettings(compute_edt=True)
+    bs = rb.Rt60BandsAnalysisSettings(band_mode="third", decay_settings=ds)
+    out = run_hot_path(engine.make_rows(x), SR, ds, bs, wf.WaterfallAnalysisSettings(), want_edc=True)
+    torch.cuda.synchronize()
+    start = out.decay.start.cpu().numpy()
+    assert np.array_equal(start, x.abs().argmax(dim=1).cpu().numpy())
+    assert int(out.decay.status.abs().sum()) == 0
+    fits = out.decay.fits.cpu().numpy()
+    bands = out.band_metrics.cpu().numpy()
+    assert np.isfinite(fits[:, :, 5]).all() and np.isfinite(bands[:, :, 0]).all()
+    csd = out.csd.cpu().numpy()
+    assert csd.shape == (rows_n, 18, 1705) and csd.max() == 0.0 and csd.min() >= -80.0
+    names = [b.name for b in out.bands]
+    for i in (0, 1, 511, 1024, 1777, rows_n - 1):
+        xi = x[i].cpu().numpy()
+        od = oracle.decay_metrics(xi, SR, oracle.DecayParams(compute_edt=True))
+        assert start[i] == od["start"]
+        check_edc(f"batch2048/row{i}", out.decay.edc_db[i, start[i]:n].cpu().numpy(), od["edc_db"])
+        for r, name in enumerate(("EDT", "T20", "T30")):
+            want = od["fits"][name]["rt60"]
+            assert seconds_close(fits[i, r, 5], want), (i, name, fits[i, r, 5], want)
+        ob = oracle.band_metrics(xi, SR, oracle.BandParams(band_mode="third"))
+        want = np.array([[np.nan if ob["metrics"][nm][0] is None else ob["metrics"][nm][0]] for nm in names])
+        check_band_table(f"batch2048/row{i}", bands[i][:, :1], want)
+        ow = oracle.waterfall(xi, SR, oracle.CsdParams())
+        _check_slices(f"batch2048/row{i}", csd[i][:ow["rel_db"].shape[0]], ow["rel_db"])
+    del x
+    torch.cuda.empty_cache()
+
+
 def test_host_streaming_pipeline_equals_resident_batch():
     """run_hot_path_host (chunked H2D / kernels / D2H on three streams) returns exactly what the resident batch
     returns, for a chunk size that does not divide the batch."""
@@ -882,3 +960,127 @@ def test_bundle_end_to_end(tmp_path):
     order = [md.index(h) for h in ("## Decay / EDC", "## RT60 by band", "## Spectrogram", "## Waterfall", "## Modal cloud")]
     assert order == sorted(order)
     assert "stft(n_fft=4096, frames=" in md and "] metric=t30 start_sample=" in md
+
+
+def test_bundle_wire_path_equals_per_file_analysis_and_isolates_a_bad_tap(tmp_path):
+    """run_bundle_report on recorder-format taps (PCM16, staged once, decoded on the device, one peak search per
+    channel) writes, for every tap, exactly the text the per-file functions produce; a mixed batch (one float32 WAV)
+    takes the loader path with the same result; a tap that is too short for the waterfall raises the reference's
+    ValueError after the taps before it have been written (bundle.py:56-67)."""
+    import json
+    from scipy.io import wavfile
+    from audio_analysis_b200 import decay, rt60bands as rb, waterfall as wf, wire
+    from audio_analysis_b200.bundle import BundleRunSettings, run_bundle_report
+    from audio_analysis_b200.report import ReportSettings, run_reports_batch
+    from audio_analysis_b200.synth import synth_ir_numpy
+    n = 48000
+    taps = {}
+    for i in range(3):
+        ch = np.stack([synth_ir_numpy(900 + 2 * i + c, n, SR) for c in range(2)], axis=1)
+        taps[f"tap_{i:03d}"] = np.round(ch * 32767.0).astype(np.int16)
+    root = tmp_path / "run"
+    (root / "taps").mkdir(parents=True)
+    for name, pcm in taps.items():
+        wire.write_pcm16_wav(root / "taps" / f"{name}.wav", pcm, SR)
+    (root / "meta.json").write_text(json.dumps({"sample_rate_hz": SR, "length_samples": n, "taps": list(taps)}))
+    rs = ReportSettings(rt60_bands_settings=rb.Rt60BandsAnalysisSettings(band_mode="third"), run_spectrogram=False,
+                        run_modal_cloud=False)
+    run_bundle_report(root, BundleRunSettings(report_settings=rs))
+    for name, pcm in taps.items():
+        md = (root / "reports" / name / f"{name}_report.md").read_text()
+        path = root / "taps" / f"{name}.wav"
+        assert decay.summarise_decay_results_text(decay.analyse_decay_from_wav_file(path)).strip() in md
+        bands = rb.analyse_rt60_bands_from_wav_file(path, rb.Rt60BandsAnalysisSettings(band_mode="third"))
+        assert rb.summarise_rt60_bands_results_text(bands, False, False).strip() in md
+        assert wf.summarise_waterfall_results_text(wf.analyse_waterfall_from_wav_file(path)).strip() in md
+        assert f"**Channels:** 2" in md and f"**Samples:** {n}" in md
+    # the loader path (one file is float32) renders the same report for the PCM16 taps
+    other = tmp_path / "float.wav"
+    wavfile.write(str(other), SR, (taps["tap_000"].astype(np.float32) / 32768.0))
+    outs = run_reports_batch([root / "taps" / "tap_001.wav", other], [tmp_path / "o" / "tap_001", tmp_path / "o" / "b"], rs)
+    wired = (root / "reports" / "tap_001" / "tap_001_report.md").read_text()
+    assert outs[0].summary_markdown.split("---", 1)[1] == wired.split("---", 1)[1]
+    # error isolation: the second of three files is too short for n_fft 4096
+    short = tmp_path / "short.wav"
+    wire.write_pcm16_wav(short, taps["tap_000"][:3000], SR)
+    with pytest.raises(ValueError, match="need at least n_fft"):
+        run_reports_batch([root / "taps" / "tap_000.wav", short, root / "taps" / "tap_002.wav"],
+                          [tmp_path / "e" / "a", tmp_path / "e" / "b", tmp_path / "e" / "c"], rs)
+    assert (tmp_path / "e" / "a_report.md").exists() and not (tmp_path / "e" / "c_report.md").exists()
+
+
+def test_deconvolve_api_and_cli(tmp_path):
+    """analyse.deconvolve mirror (deconvolve.py:124-268) and the `deconvolve` subcommand (cli.py:1219-1246)."""
+    from scipy.io import wavfile
+    from audio_analysis_b200 import cli, deconvolve as dv
+    g = load_golden("deconvolve")
+    want = g["ir"]
+    got = dv.deconvolve_impulse_response(g["recorded"], g["sweep"], SR, dv.DeconvolveSettings())
+    assert got.shape == want.shape and got.dtype == np.float32
+    err = float(np.max(np.abs(got - want)))
+    note("deconvolve_api_max_abs_err", err)
+    assert err <= 2e-4 * float(np.max(np.abs(want)))
+    # settings variants against the oracle
+    for st in (dv.DeconvolveSettings(normalise_peak=False), dv.DeconvolveSettings(remove_dc=False, target_peak=0.5),
+               dv.DeconvolveSettings(output_length_mode="full_fft")):
+        got = dv.deconvolve_impulse_response(g["recorded"], g["sweep"], SR, st)
+        ref = oracle.deconvolve(g["recorded"], g["sweep"], st.regularization_relative, st.normalise_peak,
+                                st.target_peak, st.remove_dc, st.output_length_mode == "full_fft")
+        assert got.shape == ref.shape and float(np.max(np.abs(got - ref))) <= 2e-4 * float(np.abs(ref).max())
+    with pytest.raises(ValueError, match="at least a few samples"):
+        dv.deconvolve_impulse_response(np.zeros((4, 1), np.float32), g["sweep"], SR, dv.DeconvolveSettings())
+    with pytest.raises(ValueError, match="Unknown output_length_mode"):
+        dv.deconvolve_impulse_response(g["recorded"], g["sweep"], SR, dv.DeconvolveSettings(output_length_mode="x"))
+    # files + CLI: same numbers, float32 WAV written next to the recording by default
+    rec_path, sw_path = tmp_path / "capture.wav", tmp_path / "sweep.wav"
+    pad = np.zeros((SR // 4, 2), np.float32)
+    wavfile.write(str(rec_path), SR, np.concatenate([g["recorded"], pad]))
+    wavfile.write(str(sw_path), SR, g["sweep"])
+    import io as _io
+    from contextlib import redirect_stdout
+    buf = _io.StringIO()
+    with redirect_stdout(buf):
+        cli.main(["deconvolve", "--recorded_wav_file_path", str(rec_path), "--sweep_wav_file_path", str(sw_path)])
+    out_path = tmp_path / "capture_ir.wav"
+    assert f"Wrote IR WAV: {out_path}" in buf.getvalue() and "channels=2" in buf.getvalue()
+    rate, written = wavfile.read(str(out_path))
+    ref = oracle.deconvolve(np.concatenate([g["recorded"], pad]), g["sweep"])
+    assert rate == SR and written.dtype == np.float32 and written.shape == ref.shape
+    assert float(np.max(np.abs(written - ref))) <= 2e-4 * float(np.abs(ref).max())
+
+
+def test_waterfall_db_reference_strings_and_smoothing_on_the_device():
+    """Every db_reference other than "slice_max" means the global maximum (waterfall.py:328-336) - also the string
+    "none", which used to select the library's internal raw mode; the log-frequency smoothing option
+    (waterfall.py:140-185) runs in csd_smooth_kernel for both reference levels."""
+    from audio_analysis_b200 import waterfall as wf
+    from audio_analysis_b200.synth import synth_batch_numpy
+    x = synth_batch_numpy(3, 96000, SR, first_index=70)
+    for ref in ("global_max", "none", "whatever", "slice_max"):
+        for smooth in (0, 7):
+            s = wf.WaterfallAnalysisSettings(db_reference=ref, smoothing_log_bins=smooth, f_min_hz=40.0, f_max_hz=15000.0)
+            got = wf.analyse_waterfall_batch(x, SR, None, s)
+            p = oracle.CsdParams(db_reference=ref, smoothing_log_bins=smooth, f_min_hz=40.0, f_max_hz=15000.0)
+            for i in range(x.shape[0]):
+                w = oracle.waterfall(x[i], SR, p)
+                assert got[i].slice_magnitude_rel_db.max() == 0.0
+                _check_slices(f"dbref_{ref}/smooth{smooth}", got[i].slice_magnitude_rel_db, w["rel_db"])
+
+
+def test_band_smoothing_path_beyond_65535_units():
+    """edc_smoothing_window_samples > 1 in rt60bands goes through box_smooth_kernel with one grid row per (row, band)
+    unit: more than 65,535 units in one call (3000 rows x 26 bands) must work (grid.y limit) and agree with a
+    small batch of the same rows."""
+    from audio_analysis_b200 import decay, engine, rt60bands as rb
+    from audio_analysis_b200.synth import synth_batch_torch
+    n = 4800
+    x = synth_batch_torch(3000, n, SR, device="cuda", first_index=12)
+    s = rb.Rt60BandsAnalysisSettings(band_mode="third",
+                                     decay_settings=decay.DecayAnalysisSettings(edc_smoothing_window_samples=5))
+    big = rb.run_rt60_bands(engine.make_rows(x), SR, s)[0].cpu().numpy()
+    small = rb.run_rt60_bands(engine.make_rows(x[2990:]), SR, s)[0].cpu().numpy()
+    assert np.array_equal(big[2990:], small, equal_nan=True)
+    ob = oracle.band_metrics(x[2999].cpu().numpy(), SR, oracle.BandParams(
+        band_mode="third", decay=oracle.DecayParams(edc_smoothing_window_samples=5)))
+    want = np.array([[np.nan if ob["metrics"][b["name"]][0] is None else ob["metrics"][b["name"]][0]] for b in ob["bands"]])
+    check_band_table("band_smoothing/65535", big[2999][:, :1], want)

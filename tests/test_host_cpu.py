@@ -138,6 +138,12 @@ def test_cli_surface_matches_the_reference_arguments():
     a = cli.parse_arguments(["modalcloud", "--input", "x.wav", "--metric", "edt", "--no-show_median_curve"])
     assert a.n_fft == 8192 and a.hop_length == 512 and a.metric == "edt" and a.log_bins_per_octave == 24
     assert a.min_fit_points == 10 and a.min_peak_db_above_floor == 20.0 and a.show_median_curve is False
+    a = cli.parse_arguments(["deconvolve", "--recorded_wav_file_path", "r.wav", "--sweep_wav_file_path", "s.wav"])
+    assert a.output_ir_wav_file_path is None and a.regularization_relative == 1e-10 and a.normalise_peak is True
+    assert a.target_peak == 0.95 and a.remove_dc is True and a.output_length_mode == "recorded"
+    a = cli.parse_arguments(["deconvolve", "--recorded_wav_file_path", "r.wav", "--sweep_wav_file_path", "s.wav",
+                             "--no-normalise_peak", "--no-remove_dc", "--output_length_mode", "full_fft"])
+    assert a.normalise_peak is False and a.remove_dc is False and a.output_length_mode == "full_fft"
     with pytest.raises(SystemExit):
         cli.parse_arguments(["zplane", "--input", "x.wav"])  # outside the accelerated path
     out = subprocess.run([sys.executable, "-m", "analyse.cli", "--help"], capture_output=True, text=True, cwd=ROOT)
@@ -172,6 +178,77 @@ def test_analyse_package_aliases_the_reference_module_names():
                  "summarise_modal_cloud_results_text"):
         assert hasattr(analyse.modalcloud, name)
     assert hasattr(analyse.bundle, "run_bundle_report") and hasattr(analyse, "load_wav_file")
+    import analyse.deconvolve
+    import audio_analysis_b200.deconvolve
+    assert analyse.deconvolve is audio_analysis_b200.deconvolve
+    for name in ("DeconvolveSettings", "DeconvolvedImpulseResponse", "deconvolve_impulse_response",
+                 "deconvolve_from_wav_files", "default_output_ir_path"):
+        assert hasattr(analyse.deconvolve, name)
+    assert str(analyse.deconvolve.default_output_ir_path("a/b/capture.wav")).endswith("a/b/capture_ir.wav")
+
+
+def test_bundle_wire_format_staging(tmp_path):
+    """wire.py: the recorder's PCM16 WAV layout (recorder.hpp:55-90) is parsed and its payloads land, untouched, in one
+    staging buffer; anything else is left to the scipy loader."""
+    from scipy.io import wavfile
+    from audio_analysis_b200 import wire
+    rng = np.random.default_rng(3)
+    taps = [rng.integers(-32768, 32767, size=(1000, 2), dtype=np.int16) for _ in range(3)]
+    paths = []
+    for i, t in enumerate(taps):
+        p = tmp_path / f"tap{i}.wav"
+        wire.write_pcm16_wav(p, t, 48000)
+        paths.append(p)
+        rate, back = wavfile.read(str(p))          # scipy reads what the writer wrote
+        assert rate == 48000 and np.array_equal(back, t) and p.stat().st_size == 44 + t.nbytes
+    info = wire.probe_pcm16(paths[0])
+    assert (info.sample_rate_hz, info.channels, info.frames, info.data_offset) == (48000, 2, 1000, 44)
+    st = wire.stage_pcm16(paths, pin=False)
+    assert st is not None and (st.sample_rate_hz, st.channels, st.frames) == (48000, 2, 1000)
+    assert np.array_equal(st.pcm.numpy().reshape(3, 1000, 2), np.stack(taps))
+    # a float32 WAV, a file of another length, a missing file: no staging
+    fl = tmp_path / "float.wav"
+    wavfile.write(str(fl), 48000, np.zeros((1000, 2), np.float32))
+    assert wire.probe_pcm16(fl) is None and wire.stage_pcm16([paths[0], fl], pin=False) is None
+    short = tmp_path / "short.wav"
+    wire.write_pcm16_wav(short, taps[0][:500], 48000)
+    assert wire.stage_pcm16([paths[0], short], pin=False) is None
+    assert wire.probe_pcm16(tmp_path / "nope.wav") is None
+
+
+def test_waterfall_smoothing_tables_reproduce_numpy_interp():
+    """waterfall.smoothing_tables: the host half of the device log-frequency smoothing.  Doing the kernel's arithmetic
+    with those tables in numpy gives the oracle's (= the reference's, waterfall.py:140-185) smoothed curve bit for bit."""
+    import oracle
+    from audio_analysis_b200 import waterfall as wf
+    s = wf.WaterfallAnalysisSettings(smoothing_log_bins=9, f_min_hz=30.0, f_max_hz=18000.0)
+    bin_lo, freq = wf.frequency_selection(s, 48000)
+    k0, f_in, grid, grid_seg, bin_seg = wf.smoothing_tables(freq, s)
+    rng = np.random.default_rng(5)
+    raw = (rng.standard_normal(freq.size) * 10.0 - 40.0).astype(np.float32)
+
+    def interp(x, seg, xp, fp):
+        out = np.empty(x.size)
+        for i in range(x.size):
+            j = int(seg[i])
+            if j == -1:
+                out[i] = fp[0]
+            elif j == -2 or j >= xp.size - 1:
+                out[i] = fp[-1]
+            else:
+                out[i] = (fp[j + 1] - fp[j]) / (xp[j + 1] - xp[j]) * (x[i] - xp[j]) + fp[j]
+        return out
+
+    cur = raw[k0:k0 + f_in.size].astype(np.float64)
+    on_grid = interp(grid, grid_seg, f_in, cur).astype(np.float32).astype(np.float64)
+    w = 9
+    back, fwd = w // 2, (w - 1) // 2
+    smooth = np.array([sum(on_grid[m] * (1.0 / w) for m in range(max(0, g - back), min(grid.size - 1, g + fwd) + 1))
+                       for g in range(grid.size)]).astype(np.float32).astype(np.float64)
+    got = raw.copy()
+    got[k0:k0 + f_in.size] = interp(f_in, bin_seg, grid, smooth).astype(np.float32)
+    want = oracle.ref_port._smooth_logf(freq, raw, 30.0, 18000.0, 9, s.log_bins_per_octave)
+    assert np.allclose(got, want, rtol=0, atol=2e-6) and np.array_equal(got[:k0], raw[:k0])
 
 
 def test_wav_io_rules(tmp_path):

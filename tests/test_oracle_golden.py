@@ -11,7 +11,7 @@ import numpy as np
 import pytest
 
 import oracle
-from conftest import load_golden
+from conftest import load_golden, load_verb_case
 
 SR = 48000
 
@@ -102,6 +102,27 @@ def test_waterfall_matches_reference(golden):
                                                    slice_spacing_seconds=0.08))
     assert np.array_equal(w3["slice_times"], golden["wf3_times"])
     assert np.array_equal(w3["rel_db"], golden["wf3_rel_db"])
+
+
+def test_verb_sized_stereo_file_matches_reference():
+    """Configs 1-2 of BASELINE.json at their real shape: 1,151,844 samples x 2 channels (2^2 * 3 * 95987)."""
+    g = load_verb_case()
+    for c, name in enumerate(("left", "right")):
+        x = g["x"][:, c]
+        d = oracle.decay_metrics(x, SR, oracle.DecayParams(compute_edt=True))
+        assert d["start"] == int(g[f"{name}_decay_start"]) and d["edc_db"].size == int(g[f"{name}_decay_len"])
+        assert np.array_equal(d["edc_db"][::64], g[f"{name}_decay_edc_db_dec64"])
+        assert_rows_equal(rows_from_fits(d["fits"]), g[f"{name}_decay_fits"])
+        assert d["early10"] == pytest.approx(float(g[f"{name}_decay_early10"]), rel=1e-12)
+        w = oracle.waterfall(x, SR, oracle.CsdParams())
+        assert w["start"] == int(g[f"{name}_wf_start"]) and w["length"] == int(g[f"{name}_wf_length"])
+        assert np.array_equal(w["slice_times"], g[f"{name}_wf_times"]) and np.array_equal(w["freq"], g["wf_freq"])
+        assert np.array_equal(w["rel_db"], g[f"{name}_wf_rel_db"])
+    r = oracle.band_metrics(g["mono"], SR, oracle.BandParams(band_mode="third", include_t20=True, include_edt=True))
+    names = [b["name"] for b in r["bands"]]
+    assert names == [str(s) for s in g["mono_bands_third_names"]]
+    got = np.array([[np.nan if v is None else v for v in r["metrics"][n]] for n in names])
+    assert_rows_equal(got, g["mono_bands_third_metrics"])
 
 
 def test_analytic_exponential_known_answers():
