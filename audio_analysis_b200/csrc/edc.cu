@@ -39,6 +39,7 @@ namespace aa {
 namespace {
 
 using namespace edc;
+using namespace edc::base;
 
 template <bool kWriteDb>
 __global__ void __launch_bounds__(kThreads, 1024 / kThreads) edc_kernel(EdcArgs a) {
@@ -116,6 +117,9 @@ int pick_cluster_for_batch(int max_len, int n_rows) {
 
 }  // namespace
 
+// edc_staged.cu: the same kernel body with the row kept in the cluster's shared memory between the phases
+int launch_edc_staged(const edc::EdcArgs& a, int n_rows, int max_len, bool write_db, cudaStream_t stream, bool* launched);
+
 // Shared launcher: decay (full rows of fits) and band metrics (rt60 table) both come here.
 int launch_edc(const float* d_x, long long row_stride, const int* d_lengths, int uniform_len, int max_len, int n_rows,
                const aa_decay_params* p, const int* d_start_in, int start_div, int min_samples, float* d_edc_out,
@@ -157,6 +161,11 @@ int launch_edc(const float* d_x, long long row_stride, const int* d_lengths, int
     a.ignore = d_start_in ? 0 : (p->ignore_leading_samples > 0 ? p->ignore_leading_samples : 0);
     a.min_samples = min_samples;
 
+    {   // large batches of rows that fit a cluster's shared memory: read the row from HBM once
+        bool launched = false;
+        int rc = launch_edc_staged(a, n_rows, max_len, d_edc_out != nullptr, stream, &launched);
+        if (rc != AA_OK || launched) return rc;
+    }
     const int T = pick_cluster_for_batch(max_len, n_rows);
     const int nt_max = (max_len + kTile - 1) / kTile;
     int tpw = (nt_max + T * kWarps - 1) / (T * kWarps);

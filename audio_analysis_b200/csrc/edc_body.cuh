@@ -16,8 +16,15 @@ namespace cg = cooperative_groups;
 #ifndef AA_EDC_THREADS
 #define AA_EDC_THREADS 256   /* 4 CTAs per SM: the serial resolve phase of one row hides behind the streaming phases of three others (512 x 2: 3.5 % slower, 384 x 2: 9 % slower) */
 #endif
-constexpr int kThreads = AA_EDC_THREADS;
-constexpr int kWarps = kThreads / 32;
+// The kernel body below is compiled once per VARIANT (translation unit): `base` (edc.cu: AA_EDC_THREADS threads, the
+// row is read from global memory in both phases) and `staged` (edc_staged.cu: AA_EDC_STAGE = 1, each CTA of the cluster
+// keeps its span of the row in shared memory after phase 1, so the row crosses HBM once).
+#ifndef AA_EDC_VARIANT
+#define AA_EDC_VARIANT base
+#endif
+#ifndef AA_EDC_STAGE
+#define AA_EDC_STAGE 0
+#endif
 constexpr int kTile = 128;  // samples per warp tile: one float4 per lane
 constexpr int kMaxTargets = 2 + 2 * AA_MAX_FITS;
 constexpr int kMaxCluster = 8;
@@ -57,6 +64,11 @@ struct Crossing {
     float y0, y1;
 };
 
+namespace AA_EDC_VARIANT {
+constexpr int kThreads = AA_EDC_THREADS;
+constexpr int kWarps = kThreads / 32;
+constexpr bool kStage = AA_EDC_STAGE != 0;
+
 struct CtaShared {
     float warp_amax[kWarps];
     int warp_aidx[kWarps];
@@ -81,6 +93,7 @@ struct CtaShared {
     int cross_idx[kMaxTargets];
     double warp_acc[kWarps][AA_MAX_FITS * 3];
 };
+}  // namespace AA_EDC_VARIANT
 
 struct TileScan {
     float s[4];  // suffix sums inside the lane's 4 samples
@@ -135,6 +148,8 @@ __device__ __forceinline__ float to_db(double e, double eps, double inv_e0, floa
     return fmaxf(db10_from_ratio(r), floor_db);  // decay.py:158,167
 }
 
+namespace AA_EDC_VARIANT {
+
 // One row analysed by the calling cluster (every thread of every CTA of the cluster calls this).
 //   row      index into the per-row arguments (lengths, start_in, outputs)
 //   x        the row's samples
@@ -158,7 +173,14 @@ __device__ __forceinline__ void edc_row(const EdcArgs& a, int row, const float* 
     const int tpc = tpw * kWarps;
     double* carry = reinterpret_cast<double*>(dyn_smem);            // [tpc] exclusive suffix (this CTA only)
     float* tile_sum = reinterpret_cast<float*>(carry + tpc);         // [tpc]
+    // staged variant: the CTA's span of the row, one float4 per lane and tile, written in phase 1 and read by
+    // everything after it (the tile reload of the peak, E0, the crossings, phase 2)
+    [[maybe_unused]] float4* stage = reinterpret_cast<float4*>(dyn_smem + (((size_t)tpc * 12 + 15) / 16) * 16);
     const int cta_tile0 = rank * tpc;
+    auto tile_again = [&](int k) -> float4 {
+        if constexpr (kStage) return stage[(k - cta_tile0) * 32 + lane];
+        else return load_tile<kCg>(x, k, lane, len);
+    };
     const int my_tile0 = cta_tile0 + warp * tpw;
     const int my_tile1 = min(nt, my_tile0 + tpw);
 
@@ -179,6 +201,9 @@ __device__ __forceinline__ void edc_row(const EdcArgs& a, int row, const float* 
             for (int u = 0; u < kUnroll; ++u) {  // all loads first: kUnroll x 512 B in flight per warp
                 const int k = kb + u;
                 v[u] = (k < my_tile1 && k >= k_skip) ? load_tile<kCg>(x, k, lane, len) : make_float4(0.f, 0.f, 0.f, 0.f);
+                if constexpr (kStage) {
+                    if (k < my_tile1 && k >= k_skip) stage[(k - cta_tile0) * 32 + lane] = v[u];
+                }
             }
             if constexpr (!kWriteDb) {
                 // metrics only: tile totals by one 4-way transpose-reduce (6 shuffles for 4 tiles).  The totals
@@ -230,7 +255,7 @@ __device__ __forceinline__ void edc_row(const EdcArgs& a, int row, const float* 
     }
     if (find_peak) {
         if (atile >= 0) {  // first sample of the lane's four that attains its maximum (first index wins ties, decay.py:136)
-            const float4 w = load_tile<kCg>(x, atile, lane, len);
+            const float4 w = tile_again(atile);
             const int i0 = atile * kTile + lane * 4;
             aidx = (fabsf(w.x) == amax) ? i0 : (fabsf(w.y) == amax) ? i0 + 1 : (fabsf(w.z) == amax) ? i0 + 2 : i0 + 3;
         }
@@ -293,26 +318,36 @@ __device__ __forceinline__ void edc_row(const EdcArgs& a, int row, const float* 
     }
     cluster.sync();  // A: (peak, energy) of every CTA visible
 
-    if (threadIdx.x == 0) {
-        int start = start_known;
-        double cc = 0.0;
+    if (warp == 0) {   // lane r reads CTA r's record: one remote-memory latency instead of a chain of 3 T loads
+        double tot = 0.0;
         float bm = -1.0f;
         int bi = 0x7fffffff;
-        for (int r = 0; r < T; ++r) {
-            const CtaShared* o = cluster.map_shared_rank(&sh, r);
-            if (r > rank) cc += o->cta_total;
+        if (lane < T) {
+            const CtaShared* o = cluster.map_shared_rank(&sh, lane);
+            tot = o->cta_total;
             if (find_peak) {
-                float om = o->cta_amax;
-                int oi = o->cta_aidx;
+                bm = o->cta_amax;
+                bi = o->cta_aidx;
+            }
+        }
+        const double cc = warp_sum((lane > rank && lane < T) ? tot : 0.0);
+        if (find_peak) {
+#pragma unroll
+            for (int d = 16; d > 0; d >>= 1) {
+                const float om = __shfl_xor_sync(kFullMask, bm, d);
+                const int oi = __shfl_xor_sync(kFullMask, bi, d);
                 if (om > bm || (om == bm && oi < bi)) { bm = om; bi = oi; }
             }
         }
-        if (find_peak) {
-            int peak = (bi == 0x7fffffff) ? 0 : bi;
-            start = min(len, peak + a.ignore);  // decay.py:140-144
+        if (lane == 0) {
+            int start = start_known;
+            if (find_peak) {
+                const int peak = (bi == 0x7fffffff) ? 0 : bi;
+                start = min(len, peak + a.ignore);  // decay.py:140-144
+            }
+            sh.start = start;
+            sh.cta_carry = cc;
         }
-        sh.start = start;
-        sh.cta_carry = cc;
     }
     __syncthreads();
     const int start = sh.start;
@@ -342,7 +377,7 @@ __device__ __forceinline__ void edc_row(const EdcArgs& a, int row, const float* 
 
     // ------------------------------------------------------------------ E0 = E[start]
     if (rank == owner && warp == 0) {
-        float4 v = load_tile<kCg>(x, start_tile, lane, len);
+        float4 v = tile_again(start_tile);
         TileScan t = tile_scan(v, masks);
         const int p = start - start_tile * kTile;
         const int pl = p >> 2, pj = p & 3;
@@ -391,7 +426,7 @@ __device__ __forceinline__ void edc_row(const EdcArgs& a, int row, const float* 
             if (hit >= 0) {
                 const int k = hit;
                 const double base = carry[k - cta_tile0] + cta_carry;
-                float4 v = load_tile<kCg>(x, k, lane, len);
+                float4 v = tile_again(k);
                 TileScan t = tile_scan(v, masks);
                 float db[4];
                 int first_j = 4;
@@ -425,19 +460,23 @@ __device__ __forceinline__ void edc_row(const EdcArgs& a, int row, const float* 
     }
     cluster.sync();  // D: candidates visible
 
-    if (threadIdx.x < n_targets) {
-        const int tg = threadIdx.x;
+    if (warp < n_targets) {   // warp tg collects target tg: lane r reads CTA r's candidate, the lowest rank that found one wins
+        const int tg = warp;
         Crossing c;
         c.found = 0; c.idx = 0; c.y0 = 0.f; c.y1 = 0.f;
-        for (int r = 0; r < T; ++r) {
-            const CtaShared* o = cluster.map_shared_rank(&sh, r);
-            Crossing oc = o->cand[tg];
-            if (oc.found) { c = oc; break; }
+        if (lane < T) c = cluster.map_shared_rank(&sh, lane)->cand[tg];
+        const unsigned m = __ballot_sync(kFullMask, c.found != 0);
+        const int src = m ? (__ffs(m) - 1) : 0;
+        c.found = m ? 1 : 0;
+        c.idx = __shfl_sync(kFullMask, c.idx, src);
+        c.y0 = __shfl_sync(kFullMask, c.y0, src);
+        c.y1 = __shfl_sync(kFullMask, c.y1, src);
+        if (lane == 0) {
+            const double tc = c.found ? crossing_time_rel(c.idx - start, c.y0, c.y1, a.target[tg], srf) : 0.0;
+            sh.cross_ok[tg] = c.found;
+            sh.cross_t[tg] = tc;
+            sh.cross_idx[tg] = c.idx;
         }
-        const double tc = c.found ? crossing_time_rel(c.idx - start, c.y0, c.y1, a.target[tg], srf) : 0.0;
-        sh.cross_ok[tg] = c.found;
-        sh.cross_t[tg] = tc;
-        sh.cross_idx[tg] = c.idx;
     }
     __syncthreads();
     if (threadIdx.x < a.n_fits) {
@@ -484,7 +523,7 @@ __device__ __forceinline__ void edc_row(const EdcArgs& a, int row, const float* 
 #pragma unroll
             for (int f = 0; f < AA_MAX_FITS; ++f) fit_here |= (ffirst[f] <= t_hi && flast[f] >= t_lo);
             need[u] = (k < my_tile1) && (kWriteDb || fit_here);
-            v[u] = need[u] ? load_tile<kCg>(x, k, lane, len) : make_float4(0.f, 0.f, 0.f, 0.f);
+            v[u] = need[u] ? tile_again(k) : make_float4(0.f, 0.f, 0.f, 0.f);
         }
 #pragma unroll
         for (int u = 0; u < kUnroll; ++u) {
@@ -544,41 +583,48 @@ __device__ __forceinline__ void edc_row(const EdcArgs& a, int row, const float* 
     }
     cluster.sync();  // E: per-CTA regression sums visible
 
-    if (rank == 0 && threadIdx.x == 0) {
-        if (a.start_out) a.start_out[row] = start;
-        if (a.status_out) a.status_out[row] = AA_ROW_OK;
-        if (a.early10_out) {
-            double e10 = nan("");
-            if (a.want_early10 && sh.cross_ok[0] && sh.cross_ok[1] && sh.cross_t[1] >= sh.cross_t[0])
-                e10 = sh.cross_t[1] - sh.cross_t[0];  // decay.py:283-286
-            a.early10_out[row] = e10;
+    if (rank == 0 && warp == 0) {
+        // lane r reads CTA r's nine regression sums (independent remote loads), then nine warp reductions
+        double part[AA_MAX_FITS * 3];
+#pragma unroll
+        for (int q = 0; q < AA_MAX_FITS * 3; ++q) part[q] = 0.0;
+        if (lane < T) {
+            const CtaShared* o = cluster.map_shared_rank(&sh, lane);
+#pragma unroll
+            for (int q = 0; q < AA_MAX_FITS * 3; ++q) part[q] = o->fit_sums[q / 3][q % 3];
         }
-        for (int f = 0; f < AA_MAX_FITS; ++f) {
-            double res[AA_FIT_COLS];
-            for (int c = 0; c < 6; ++c) res[c] = nan("");
-            res[6] = 0.0;
-            res[7] = 0.0;
-            double rt60 = nan("");
-            if (f < a.n_fits && sh.fit_valid[f]) {
-                double s0 = 0.0, s1 = 0.0, s2 = 0.0;
-                for (int r = 0; r < T; ++r) {
-                    const CtaShared* o = cluster.map_shared_rank(&sh, r);
-                    s0 += o->fit_sums[f][0];
-                    s1 += o->fit_sums[f][1];
-                    s2 += o->fit_sums[f][2];
+#pragma unroll
+        for (int q = 0; q < AA_MAX_FITS * 3; ++q) part[q] = warp_sum(part[q]);
+        if (lane == 0) {
+            if (a.start_out) a.start_out[row] = start;
+            if (a.status_out) a.status_out[row] = AA_ROW_OK;
+            if (a.early10_out) {
+                double e10 = nan("");
+                if (a.want_early10 && sh.cross_ok[0] && sh.cross_ok[1] && sh.cross_t[1] >= sh.cross_t[0])
+                    e10 = sh.cross_t[1] - sh.cross_t[0];  // decay.py:283-286
+                a.early10_out[row] = e10;
+            }
+            for (int f = 0; f < AA_MAX_FITS; ++f) {
+                double res[AA_FIT_COLS];
+                for (int c = 0; c < 6; ++c) res[c] = nan("");
+                res[6] = 0.0;
+                res[7] = 0.0;
+                double rt60 = nan("");
+                if (f < a.n_fits && sh.fit_valid[f])
+                    rt60 = fit_finalize(part[f * 3 + 0], part[f * 3 + 1], part[f * 3 + 2], sh.fit_first[f] - start,
+                                        sh.fit_last[f] - start, (double)ymid_f[f], a.sr, sh.fit_ts[f], sh.fit_te[f], res);
+                if (a.fits_out) {
+                    double* o = a.fits_out + ((long long)row * AA_MAX_FITS + f) * AA_FIT_COLS;
+                    for (int c = 0; c < AA_FIT_COLS; ++c) o[c] = res[c];
                 }
-                rt60 = fit_finalize(s0, s1, s2, sh.fit_first[f] - start, sh.fit_last[f] - start, (double)ymid_f[f], a.sr,
-                                    sh.fit_ts[f], sh.fit_te[f], res);
+                if (a.rt60_out) a.rt60_out[(long long)row * AA_MAX_FITS + f] = rt60;
             }
-            if (a.fits_out) {
-                double* o = a.fits_out + ((long long)row * AA_MAX_FITS + f) * AA_FIT_COLS;
-                for (int c = 0; c < AA_FIT_COLS; ++c) o[c] = res[c];
-            }
-            if (a.rt60_out) a.rt60_out[(long long)row * AA_MAX_FITS + f] = rt60;
         }
     }
     cluster.sync();  // F: rank 0 has finished reading remote shared memory
 }
+
+}  // namespace AA_EDC_VARIANT
 
 // Settings -> kernel arguments (the per-call pointers are filled in by the caller).
 inline int fill_edc_args(const aa_decay_params* p, EdcArgs* out) {

@@ -20,6 +20,8 @@ _warned = False
 def pyplot(optional: bool = True):
     """Return matplotlib.pyplot, or None when it is not installed (and optional)."""
     global _warned
+    if _warned and optional:   # already known to be missing: do not walk sys.path again for every report
+        return None
     try:
         import matplotlib
 

@@ -250,10 +250,16 @@ def _analyse_group(rows: engine.Rows, sr: int, names: List[str], settings: Repor
     out = {"decay": None, "bands": None, "water": None, "spec": None, "modal": None}
     smoothing = int(decay_s.edc_smoothing_window_samples or 0) > 1
     do_bands = bool(settings.run_rt60_bands) and rows.uniform
-    hot = run_hot_path(rows, sr, decay_s, bands_s, water_s, want_edc=bool(settings.run_decay),
+    from .plotting import pyplot as _pyplot
+
+    hot = run_hot_path(rows, sr, decay_s, bands_s, water_s, want_edc=bool(settings.run_decay) and _pyplot() is not None,
                        do_bands=do_bands, do_csd=bool(settings.run_waterfall), validate=False)
     if settings.run_decay:
-        out["decay"] = decay_results(hot.decay, rows, names, decay_s, sr, return_curves=True, strict=False)
+        # the EDC curves are plot data: they leave the device only when there is a backend to draw them
+        from .plotting import pyplot
+
+        out["decay"] = decay_results(hot.decay, rows, names, decay_s, sr, return_curves=pyplot() is not None,
+                                     strict=False)
     if settings.run_rt60_bands:
         if do_bands:
             out["bands"] = metrics_to_results(hot.band_metrics.cpu().numpy(), hot.bands, hot.band_fit_plan, names, sr)

@@ -581,7 +581,8 @@ def bench_config3(world, rank, dev, barrier, n_taps=256, seconds=4.0, steps=3):
                         "decay (T20/T30, EDC curves) + third-octave rt60bands per channel, reports written",
             "value": round(ir_s / (wall_ms / 1e3), 1), "unit": UNIT, "ms_per_bundle": round(wall_ms, 2),
             "timed": "run_bundle_report wall clock (WAV payloads -> pinned int16 -> device decode -> kernels -> "
-                     "result records incl. EDC curves -> Markdown), max over ranks",
+                     "result records -> Markdown; EDC curves are fetched only when matplotlib can draw them), "
+                     "max over ranks",
             "resident_kernels": {"value": round(ir_s / (dev_ms / 1e3), 1), "unit": UNIT, "ms": round(dev_ms, 3)},
             "file_seconds_per_s": round(n_taps * seconds / (wall_ms / 1e3), 1), "steps": steps}
 

@@ -1084,3 +1084,26 @@ def test_band_smoothing_path_beyond_65535_units():
         band_mode="third", decay=oracle.DecayParams(edc_smoothing_window_samples=5)))
     want = np.array([[np.nan if ob["metrics"][b["name"]][0] is None else ob["metrics"][b["name"]][0]] for b in ob["bands"]])
     check_band_table("band_smoothing/65535", big[2999][:, :1], want)
+
+
+def test_edc_staged_variant_is_bit_identical(monkeypatch):
+    """edc_staged_kernel (csrc/edc_staged.cu, opt-in through AA_EDC_STAGED): every CTA of the row's cluster keeps its
+    span of the row in shared memory between the two phases, so the row crosses HBM once.  Same arithmetic as
+    edc_kernel: curves, fits and start indices must be bit-identical."""
+    import torch
+    from audio_analysis_b200 import decay, engine
+    from audio_analysis_b200.synth import synth_batch_torch
+    s = decay.DecayAnalysisSettings(compute_edt=True)
+    for n in (288000, 50022, 624000):
+        rows = engine.make_rows(synth_batch_torch(5, n, SR, device="cuda", first_index=3))
+        monkeypatch.delenv("AA_EDC_STAGED", raising=False)
+        base = decay.run_decay(rows, SR, s)
+        for t in ("8", "16"):
+            monkeypatch.setenv("AA_EDC_STAGED", t)
+            got = decay.run_decay(rows, SR, s)
+            assert torch.equal(got.start, base.start) and torch.equal(got.status, base.status)
+            st = base.start.cpu().numpy()
+            for r in range(5):
+                assert torch.equal(got.edc_db[r, st[r]:n], base.edc_db[r, st[r]:n])
+            assert torch.allclose(got.fits, base.fits, rtol=1e-12, atol=0, equal_nan=True)
+    monkeypatch.delenv("AA_EDC_STAGED", raising=False)
