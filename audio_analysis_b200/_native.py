@@ -49,6 +49,8 @@ EXPORTED_SYMBOLS = (
     "aa_bands_workspace_bytes",
     "aa_rt60bands_batch",
     "aa_rt60bands_batch_ex",
+    "aa_sos_workspace_bytes",
+    "aa_rt60bands_sos_batch",
     "aa_csd_batch",
     "aa_csd_smooth_batch",
     "aa_stft_db_batch",
@@ -181,6 +183,11 @@ def _declare(lib: C.CDLL) -> None:
     lib.aa_rt60bands_batch_ex.argtypes = [vp, vp, i64, i32, vp, C.POINTER(Band), i32, C.c_double,
                                           C.POINTER(DecayParams), vp, vp, vp, sz, vp, C.POINTER(BandsOptions),
                                           C.POINTER(BandsStats)]
+    lib.aa_sos_workspace_bytes.restype = sz
+    lib.aa_sos_workspace_bytes.argtypes = [i32, i32, i32, i32]
+    lib.aa_rt60bands_sos_batch.restype = C.c_int
+    lib.aa_rt60bands_sos_batch.argtypes = [vp, i64, i32, i32, vp, vp, vp, vp, i32, i32, C.POINTER(DecayParams), vp, vp,
+                                           vp, sz, vp]
     lib.aa_csd_batch.restype = C.c_int
     lib.aa_csd_batch.argtypes = [vp, i64, vp, i32, i32, vp, vp, vp, i32, C.POINTER(CsdParams), vp, vp]
     lib.aa_csd_smooth_batch.restype = C.c_int

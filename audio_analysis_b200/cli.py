@@ -112,6 +112,10 @@ def build_parser() -> argparse.ArgumentParser:
     bands.add_argument("--edc_floor_db", type=float, default=-120.0)
     bands.add_argument("--fit_lower_limit_db", type=float, default=-80.0)
     bands.add_argument("--smoothing", dest="edc_smoothing_window_samples", type=int, default=0)
+    bands.add_argument("--filterbank", type=str, choices=["fft_mask", "butterworth"], default="fft_mask",
+                       help="Extension of the B200 build: 'fft_mask' = the reference's circular FFT mask (default), "
+                            "'butterworth' = zero-phase Butterworth sections (not the reference's filter).")
+    bands.add_argument("--butterworth_order", type=int, default=4, help="Order of the Butterworth prototype (default 4).")
 
     wf = sub.add_parser("waterfall", help="Waterfall (CSD-style): spectral slices over time (3D default, 2D ridges).")
     _io_arguments(wf, "PNG(s): <basename>_waterfall_<CH>.png")
@@ -235,6 +239,8 @@ def run_rt60bands_command(a: argparse.Namespace) -> str:
         include_t20=bool(a.include_t20),
         include_edt=bool(a.include_edt),
         decay_settings=decay_settings_from_args(a, a.include_edt),
+        filterbank=str(a.filterbank),
+        butterworth_order=int(a.butterworth_order),
     )
     legend = (str(a.band_mode) == "three") if a.legend_values is None else bool(a.legend_values)
     results = plot_rt60_bands_from_wav_file(

@@ -70,6 +70,10 @@ int rt60bands_batch(const aa_bands_plan* plan, const float* d_x, long long row_s
                     const int* d_start_idx, const aa_band* bands, int nb, double tw_oct, const aa_decay_params* p,
                     double* d_metrics_out, float* d_band_signal_out, void* d_ws, size_t ws_bytes, cudaStream_t stream,
                     const aa_bands_options* opts, aa_bands_stats* stats);
+size_t sos_workspace_bytes(int n, int n_sec_max, int rows, int nb);
+int rt60bands_sos_batch(const float* d_x, long long row_stride, int n, int n_rows, const int* d_start_idx,
+                        const double* sos, const double* zi, const int* edges, int nb, int n_sec, const aa_decay_params* p,
+                        double* d_metrics_out, float* d_band_signal_out, void* d_ws, size_t ws_bytes, cudaStream_t stream);
 int deconv_plan_create(int n_fft, aa_deconv_plan** out);
 void deconv_plan_destroy(aa_deconv_plan* p);
 size_t deconv_workspace_bytes(const aa_deconv_plan* p, int rows);
@@ -200,6 +204,18 @@ int aa_rt60bands_batch_ex(const aa_bands_plan* plan, const float* d_x, int64_t r
     return aa::rt60bands_batch(plan, d_x, row_stride, n_rows, d_start_idx, bands, n_bands, transition_width_octaves, p,
                                d_metrics_out, d_band_signal_out, d_workspace, workspace_bytes,
                                static_cast<cudaStream_t>(stream), options, stats_out);
+}
+
+size_t aa_sos_workspace_bytes(int32_t n, int32_t n_sections, int32_t rows_per_chunk, int32_t n_bands) {
+    return aa::sos_workspace_bytes(n, n_sections, rows_per_chunk, n_bands);
+}
+int aa_rt60bands_sos_batch(const float* d_x, int64_t row_stride, int32_t n, int32_t n_rows, const int32_t* d_start_idx,
+                           const double* h_sos, const double* h_zi, const int32_t* h_edge, int32_t n_bands,
+                           int32_t n_sections, const aa_decay_params* p, double* d_metrics_out, float* d_band_signal_out,
+                           void* d_workspace, size_t workspace_bytes, void* stream) {
+    return aa::rt60bands_sos_batch(d_x, row_stride, n, n_rows, d_start_idx, h_sos, h_zi, h_edge, n_bands, n_sections, p,
+                                   d_metrics_out, d_band_signal_out, d_workspace, workspace_bytes,
+                                   static_cast<cudaStream_t>(stream));
 }
 
 int aa_csd_smooth_batch(float* d_slices, int32_t n_rows, const int32_t* d_n_slices, int32_t max_slices, int32_t n_bins,

@@ -398,6 +398,33 @@ def rt60bands(rows: Rows, start_idx: torch.Tensor, bands: Sequence[Tuple[int, Op
     return metrics, sig
 
 
+def rt60bands_sos(rows: Rows, start_idx: torch.Tensor, sos: np.ndarray, zi: np.ndarray, edges: np.ndarray,
+                  params: nat.DecayParams, want_band_signals: bool = False, workspace_bytes: Optional[int] = None):
+    """RT60 table [B, n_bands, 3] with the opt-in Butterworth filterbank (aa_rt60bands_sos_batch): `sos`
+    [n_bands, n_sections, 6], `zi` [n_bands, n_sections, 2], `edges` [n_bands] from butterworth.band_sections."""
+    if not rows.uniform:
+        raise ValueError("rt60bands needs rows of equal length (group channels by length)")
+    lib = nat.load()
+    dev = rows.x.device
+    b = rows.n_rows
+    sos = np.ascontiguousarray(sos, dtype=np.float64)
+    zi = np.ascontiguousarray(zi, dtype=np.float64)
+    edges = np.ascontiguousarray(edges, dtype=np.int32)
+    nb, n_sec = int(sos.shape[0]), int(sos.shape[1])
+    budget = int(workspace_bytes or os.environ.get("AA_BANDS_WORKSPACE_BYTES") or DEFAULT_WORKSPACE_BYTES)
+    one = int(lib.aa_sos_workspace_bytes(rows.n, n_sec, 1, nb))
+    allrows = int(lib.aa_sos_workspace_bytes(rows.n, n_sec, b, nb))
+    ws_bytes = min(max(budget, one), allrows)
+    ws = workspace(ws_bytes, dev)
+    metrics = torch.empty((b, nb, nat.AA_MAX_FITS), dtype=torch.float64, device=dev)
+    sig = torch.empty((b, nb, rows.n), dtype=torch.float32, device=dev) if want_band_signals else None
+    with torch.cuda.device(dev):
+        nat.check(lib.aa_rt60bands_sos_batch(
+            _ptr(rows.x), rows.stride, rows.n, b, _ptr(start_idx), sos.ctypes.data, zi.ctypes.data, edges.ctypes.data,
+            nb, n_sec, C.byref(params), _ptr(metrics), _ptr(sig), _ptr(ws), ws_bytes, _stream_ptr()))
+    return metrics, sig
+
+
 # --------------------------------------------------------------------------------------
 # waterfall / CSD
 # --------------------------------------------------------------------------------------

@@ -36,6 +36,13 @@ class Rt60BandsAnalysisSettings:
     include_t20: bool = False
     include_edt: bool = False
     decay_settings: DecayAnalysisSettings = DecayAnalysisSettings()
+    # Extension of this build (not a reference field; defaults reproduce the reference): the band filter.
+    #   "fft_mask"    - the reference's circular FFT-domain raised-cosine mask (rt60bands.py:116-175)
+    #   "butterworth" - Butterworth sections of `butterworth_order`, zero-phase forward-backward filtering
+    #                   (scipy.signal.sosfiltfilt semantics; csrc/sos.cu).  Results differ from the reference's by
+    #                   0.04 - 11 % depending on the band: parity with the reference is NOT claimed.
+    filterbank: str = "fft_mask"
+    butterworth_order: int = 4
 
 
 @dataclass(frozen=True)
@@ -201,6 +208,21 @@ def run_rt60_bands(rows: engine.Rows, sample_rate_hz: int, settings: Rt60BandsAn
         ign = int(params.ignore_leading_samples)
         if ign > 0:
             start_idx = torch.clamp(start_idx + min(ign, rows.n), max=rows.n).to(torch.int32)
+    mode = str(getattr(settings, "filterbank", "fft_mask")).lower()
+    if mode == "butterworth":
+        from . import butterworth
+
+        if int(params.smoothing_window) > 1:
+            raise ValueError("edc_smoothing_window_samples is not available with filterbank='butterworth'")
+        nyq = 0.5 * float(sample_rate_hz)
+        triples = [(b.kind, None if b.low_edge_hz is None else float(np.clip(b.low_edge_hz, 1.0, nyq - 1.0)),
+                    None if b.high_edge_hz is None else float(np.clip(b.high_edge_hz, 1.0, nyq - 1.0))) for b in bands]
+        sos, zi, edges = butterworth.band_sections(triples, int(settings.butterworth_order), float(sample_rate_hz))
+        metrics, sig = engine.rt60bands_sos(rows, start_idx, sos, zi, edges, params,
+                                            want_band_signals=want_band_signals, workspace_bytes=workspace_bytes)
+        return metrics, bands, plan, start_idx, sig
+    if mode != "fft_mask":
+        raise ValueError(f"Unknown filterbank: {settings.filterbank}")
     metrics, sig = engine.rt60bands(rows, start_idx, band_triples(bands), float(settings.transition_width_octaves),
                                     params, want_band_signals=want_band_signals, workspace_bytes=workspace_bytes,
                                     options=options)

@@ -51,6 +51,7 @@ typedef enum aa_status {
 #define AA_FIT_COLS 8  /* t_start, t_end, slope_db_per_s, intercept_db, r2, rt60_s, n_points, valid */
 #define AA_MAX_BANDS 64
 #define AA_MAX_SLICES 64
+#define AA_SOS_MAX_SECTIONS 8
 
 /* per-row status written by the batched kernels */
 #define AA_ROW_OK 0
@@ -241,6 +242,23 @@ int aa_rt60bands_batch(const aa_bands_plan* plan, const float* d_x, int64_t row_
                        const int32_t* d_start_idx, const aa_band* bands, int32_t n_bands,
                        double transition_width_octaves, const aa_decay_params* p, double* d_metrics_out,
                        float* d_band_signal_out, void* d_workspace, size_t workspace_bytes, void* stream);
+
+/*
+ * aa_rt60bands_sos_batch - OPT-IN band filterbank: Butterworth second-order sections, zero-phase forward-backward
+ * filtering as a chunked parallel linear-recurrence scan with float64 states and carries (csrc/sos.cu), then the same
+ * band EDC + fits as aa_rt60bands_batch.  This is NOT the reference's band filter (a circular FFT-domain mask,
+ * analyse/rt60bands.py:116-175); it implements scipy.signal.sosfiltfilt (odd extension of 3 * ntaps samples, steady-
+ * state initial conditions) and is validated against it.  The host designs the sections.
+ *  h_sos[n_bands][n_sections][6] : b0 b1 b2 1 a1 a2 per section (HOST, float64); n_sections <= AA_SOS_MAX_SECTIONS
+ *  h_zi[n_bands][n_sections][2]  : scipy.signal.sosfilt_zi of each band (HOST)
+ *  h_edge[n_bands]               : odd extension at each end = sosfiltfilt's default padlen of the band (HOST)
+ *  other arguments as aa_rt60bands_batch; aa_sos_workspace_bytes sizes the workspace.
+ */
+size_t aa_sos_workspace_bytes(int32_t n, int32_t n_sections, int32_t rows_per_chunk, int32_t n_bands);
+int aa_rt60bands_sos_batch(const float* d_x, int64_t row_stride, int32_t n, int32_t n_rows, const int32_t* d_start_idx,
+                           const double* h_sos, const double* h_zi, const int32_t* h_edge, int32_t n_bands,
+                           int32_t n_sections, const aa_decay_params* p, double* d_metrics_out, float* d_band_signal_out,
+                           void* d_workspace, size_t workspace_bytes, void* stream);
 
 /*
  * aa_csd_batch - waterfall / cumulative-spectral-decay slices for a batch of rows.

@@ -1107,3 +1107,50 @@ def test_edc_staged_variant_is_bit_identical(monkeypatch):
                 assert torch.equal(got.edc_db[r, st[r]:n], base.edc_db[r, st[r]:n])
             assert torch.allclose(got.fits, base.fits, rtol=1e-12, atol=0, equal_nan=True)
     monkeypatch.delenv("AA_EDC_STAGED", raising=False)
+
+
+def test_butterworth_filterbank_mode_against_scipy_sosfiltfilt():
+    """filterbank="butterworth" (opt-in; BASELINE.json north_star stage 1; csrc/sos.cu: chunked 2 x 2 state-matrix
+    scan with float64 carries, forward-backward).  PARITY UNPINNED against the reference - it has no such filter
+     - so the pin is SciPy: band signals equal scipy.signal.sosfiltfilt of scipy.signal.butter sections,
+    and the band RT60s equal the oracle's decay fits run on those SciPy-filtered signals."""
+    from scipy import signal
+    from audio_analysis_b200 import engine, rt60bands as rb
+    from audio_analysis_b200.synth import synth_batch_numpy
+    for mode, n in (("third", 96000), ("three", 60000), ("octave", 50022)):
+        x = synth_batch_numpy(3, n, SR, first_index=21)
+        s = rb.Rt60BandsAnalysisSettings(band_mode=mode, filterbank="butterworth", butterworth_order=4, include_t20=True)
+        metrics, bands, plan, start, sig = rb.run_rt60_bands(engine.make_rows(x), SR, s, want_band_signals=True)
+        metrics, sig, start = metrics.cpu().numpy(), sig.cpu().numpy(), start.cpu().numpy()
+        nyq = 0.5 * SR
+        for bi, b in enumerate(bands):
+            lo = None if b.low_edge_hz is None else float(np.clip(b.low_edge_hz, 1.0, nyq - 1.0))
+            hi = None if b.high_edge_hz is None else float(np.clip(b.high_edge_hz, 1.0, nyq - 1.0))
+            if b.kind == "bandpass":
+                sos = signal.butter(4, [lo, hi], btype="bandpass", fs=SR, output="sos")
+            elif b.kind == "lowpass":
+                sos = signal.butter(4, hi, btype="lowpass", fs=SR, output="sos")
+            else:
+                sos = signal.butter(4, lo, btype="highpass", fs=SR, output="sos")
+            for r in range(x.shape[0]):
+                want = signal.sosfiltfilt(sos, x[r].astype(np.float64))
+                err = float(np.max(np.abs(sig[r, bi] - want))) / float(np.max(np.abs(want)))
+                note(f"butterworth_band_signal_rel_err[{mode}]", err)
+                assert err <= 2e-5, (mode, b.name, r, err)
+                y = want.astype(np.float32)[start[r]:]
+                t, curve, _ = oracle.ref_port.schroeder_edc_db(y, SR, oracle.DecayParams(trim_to_peak=False))
+                for c, rng in enumerate(((-5.0, -35.0), (-5.0, -25.0))):
+                    f = oracle.ref_port.line_fit(t, curve, rng, -80.0)
+                    got = metrics[r, bi, c]
+                    assert (f is None) == bool(np.isnan(got)), (mode, b.name, r, c)
+                    if f is not None:
+                        assert seconds_close(got, f["rt60"]), (mode, b.name, r, c, got, f["rt60"])
+    # the default is the reference's filter, and the two filters are different estimators
+    s0 = rb.Rt60BandsAnalysisSettings(band_mode="third")
+    assert s0.filterbank == "fft_mask"
+    x = synth_batch_numpy(1, 96000, SR, first_index=21)
+    a = rb.run_rt60_bands(engine.make_rows(x), SR, s0)[0].cpu().numpy()
+    b = rb.run_rt60_bands(engine.make_rows(x), SR, rb.Rt60BandsAnalysisSettings(band_mode="third", filterbank="butterworth"))[0].cpu().numpy()
+    assert not np.allclose(a[:, :, 0], b[:, :, 0], rtol=1e-4)
+    with pytest.raises(ValueError, match="Unknown filterbank"):
+        rb.run_rt60_bands(engine.make_rows(x), SR, rb.Rt60BandsAnalysisSettings(filterbank="elliptic"))

@@ -187,6 +187,32 @@ def test_analyse_package_aliases_the_reference_module_names():
     assert str(analyse.deconvolve.default_output_ir_path("a/b/capture.wav")).endswith("a/b/capture_ir.wav")
 
 
+def test_butterworth_design_matches_scipy():
+    """butterworth.py designs the sections of the opt-in filterbank without scipy.signal; same response, same
+    sosfiltfilt result, same sosfilt_zi and padlen as SciPy's own design."""
+    from scipy import signal
+    from audio_analysis_b200 import butterworth as bw
+    rng = np.random.default_rng(0)
+    x = rng.standard_normal(6000) * np.exp(-np.arange(6000) / 1500.0)
+    for kind, lo, hi, order in (("bandpass", 890.9, 1122.5, 4), ("bandpass", 35.0, 44.1, 4), ("lowpass", None, 250.0, 4),
+                                ("highpass", 4000.0, None, 4), ("lowpass", None, 250.0, 3), ("bandpass", 11313.0, 14254.0, 2)):
+        sos = bw.butter_sos(order, kind, lo, hi, 48000)
+        wn = [lo, hi] if kind == "bandpass" else (hi if kind == "lowpass" else lo)
+        ref = signal.butter(order, wn, btype=kind, fs=48000, output="sos")
+        assert sos.shape == ref.shape
+        _, h = signal.sosfreqz(sos, 1024, fs=48000)
+        _, hr = signal.sosfreqz(ref, 1024, fs=48000)
+        assert np.max(np.abs(h - hr)) <= 1e-9
+        y, yr = signal.sosfiltfilt(sos, x), signal.sosfiltfilt(ref, x)
+        assert np.max(np.abs(y - yr)) <= 1e-9 * np.max(np.abs(yr))
+        assert np.allclose(bw.sosfilt_zi(sos), signal.sosfilt_zi(sos), rtol=0, atol=1e-12)
+        ntaps = 2 * ref.shape[0] + 1 - min(int((ref[:, 2] == 0).sum()), int((ref[:, 5] == 0).sum()))
+        assert bw.filtfilt_padlen(sos) == 3 * ntaps
+    sos, zi, edges = bw.band_sections([("lowpass", None, 250.0), ("bandpass", 707.0, 1414.0), ("highpass", 4000.0, None)], 4, 48000)
+    assert sos.shape == (3, 4, 6) and zi.shape == (3, 4, 2) and list(edges) == [15, 27, 15]
+    assert np.array_equal(sos[0, 2:], np.tile([1.0, 0, 0, 1.0, 0, 0], (2, 1)))
+
+
 def test_bundle_wire_format_staging(tmp_path):
     """wire.py: the recorder's PCM16 WAV layout (recorder.hpp:55-90) is parsed and its payloads land, untouched, in one
     staging buffer; anything else is left to the scipy loader."""
