@@ -52,6 +52,7 @@ EXPORTED_SYMBOLS = (
     "aa_sos_workspace_bytes",
     "aa_rt60bands_sos_batch",
     "aa_csd_batch",
+    "aa_csd_plan_batch",
     "aa_csd_smooth_batch",
     "aa_stft_db_batch",
     "aa_modal_cloud_batch",
@@ -190,6 +191,8 @@ def _declare(lib: C.CDLL) -> None:
                                            vp, sz, vp]
     lib.aa_csd_batch.restype = C.c_int
     lib.aa_csd_batch.argtypes = [vp, i64, vp, i32, i32, vp, vp, vp, i32, C.POINTER(CsdParams), vp, vp]
+    lib.aa_csd_plan_batch.restype = C.c_int
+    lib.aa_csd_plan_batch.argtypes = [vp, i32, i32, vp, i32, i32, i32, i32, vp, vp, i32, i32, vp, vp, vp, vp, vp]
     lib.aa_csd_smooth_batch.restype = C.c_int
     lib.aa_csd_smooth_batch.argtypes = [vp, i32, vp, i32, i32, i32, i32, vp, vp, i32, vp, vp, i32, i32, C.c_double, vp]
     lib.aa_stft_db_batch.restype = C.c_int

@@ -218,6 +218,17 @@ int aa_rt60bands_sos_batch(const float* d_x, int64_t row_stride, int32_t n, int3
                                    static_cast<cudaStream_t>(stream));
 }
 
+int aa_csd_plan_batch(const int32_t* d_lengths, int32_t uniform_length, int32_t n_rows, const int32_t* d_peak_idx,
+                      int32_t ignore_leading_samples, int32_t analysis_duration_samples, int32_t n_fft, int32_t hop_length,
+                      const int32_t* d_slice_table, const int32_t* d_slice_counts, int32_t max_frames, int32_t table_width,
+                      int32_t* d_start_out, int32_t* d_span_out, int32_t* d_frame_idx_out, int32_t* d_n_slices_out,
+                      void* stream) {
+    return aa::launch_csd_plan(d_lengths, uniform_length, n_rows, d_peak_idx, ignore_leading_samples,
+                               analysis_duration_samples, n_fft, hop_length, d_slice_table, d_slice_counts, max_frames,
+                               table_width, d_start_out, d_span_out, d_frame_idx_out, d_n_slices_out,
+                               static_cast<cudaStream_t>(stream));
+}
+
 int aa_csd_smooth_batch(float* d_slices, int32_t n_rows, const int32_t* d_n_slices, int32_t max_slices, int32_t n_bins,
                         int32_t first_bin_inside, int32_t n_bins_inside, const double* d_freq_inside,
                         const double* d_grid_hz, int32_t n_grid, const int32_t* d_grid_segment,

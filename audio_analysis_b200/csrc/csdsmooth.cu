@@ -114,6 +114,49 @@ __global__ void __launch_bounds__(kSmoothThreads) csd_smooth_kernel(SmoothArgs a
 
 }  // namespace
 
+namespace {
+
+// Which samples and frames of a row the waterfall analyses (analyse/waterfall.py:358-372, :208, :233-286): pure integer
+// bookkeeping per row, done here so that no host round trip and no framework kernel sits between the decay kernel
+// (which finds the peak) and the CSD kernel.  The slice selection itself depends only on the number of frames: the
+// host tabulates it once per settings (the reference's numpy expressions), the kernel copies the row's line.
+__global__ void csd_plan_kernel(const int* __restrict__ lengths, int uniform_len, int n_rows, const int* __restrict__ peak,
+                                int ignore, int keep, int n_fft, int hop, const int* __restrict__ table,
+                                const int* __restrict__ counts, int max_frames, int width, int* __restrict__ start_out,
+                                int* __restrict__ span_out, int* __restrict__ frames_out, int* __restrict__ nslices_out) {
+    const int row = blockIdx.x * blockDim.x + threadIdx.x;
+    if (row >= n_rows) return;
+    const int len = lengths ? lengths[row] : uniform_len;
+    int start = peak ? min(max(peak[row], 0), len) : 0;          // waterfall.py:358-361
+    int span = len - start;
+    const int skip = min(max(ignore, 0), span);                  // :363-367
+    start += skip;
+    span -= skip;
+    if (keep >= 0) span = min(span, keep);                       // :369-372
+    int nf = (span >= n_fft) ? 1 + (span - n_fft) / hop : 0;     // :208
+    nf = min(nf, max_frames);
+    start_out[row] = start;
+    span_out[row] = span;
+    nslices_out[row] = counts[nf];
+    for (int s = 0; s < width; ++s) frames_out[(long long)row * width + s] = table[(long long)nf * width + s];
+}
+
+}  // namespace
+
+int launch_csd_plan(const int* d_lengths, int uniform_len, int n_rows, const int* d_peak, int ignore, int keep, int n_fft,
+                    int hop, const int* d_table, const int* d_counts, int max_frames, int width, int* d_start_out,
+                    int* d_span_out, int* d_frames_out, int* d_nslices_out, cudaStream_t stream) {
+    AA_REQUIRE(d_table && d_counts && d_start_out && d_span_out && d_frames_out && d_nslices_out, AA_ERR_INVALID_ARGUMENT,
+               "null argument");
+    AA_REQUIRE(n_fft > 0 && hop > 0 && width >= 1 && width <= AA_MAX_SLICES && max_frames >= 0, AA_ERR_INVALID_ARGUMENT,
+               "bad plan sizes");
+    if (n_rows <= 0) return AA_OK;
+    csd_plan_kernel<<<(unsigned)((n_rows + 127) / 128), 128, 0, stream>>>(d_lengths, uniform_len, n_rows, d_peak, ignore, keep,
+                                                                         n_fft, hop, d_table, d_counts, max_frames, width,
+                                                                         d_start_out, d_span_out, d_frames_out, d_nslices_out);
+    return launch_check("csd_plan_kernel");
+}
+
 int launch_csd_smooth(float* d_data, int n_rows, const int* d_n_slices, int max_slices, int n_bins, int k0, int n_in,
                       const double* d_f_in, const double* d_grid, int n_grid, const int* d_grid_seg,
                       const int* d_bin_seg, int window, int slice_max, double dynamic_range_db, cudaStream_t stream) {

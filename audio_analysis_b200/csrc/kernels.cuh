@@ -21,6 +21,10 @@ int launch_stft_db(const float* d_x, long long row_stride, const int* d_lengths,
                    const int* d_start_idx, const int* d_span, int n_fft, int hop, int use_hann, double floor_db,
                    int frames_max, float* d_out, cudaStream_t stream);
 
+int launch_csd_plan(const int* d_lengths, int uniform_len, int n_rows, const int* d_peak, int ignore, int keep, int n_fft,
+                    int hop, const int* d_table, const int* d_counts, int max_frames, int width, int* d_start_out,
+                    int* d_span_out, int* d_frames_out, int* d_nslices_out, cudaStream_t stream);
+
 int launch_csd_smooth(float* d_data, int n_rows, const int* d_n_slices, int max_slices, int n_bins, int k0, int n_in,
                       const double* d_f_in, const double* d_grid, int n_grid, const int* d_grid_seg,
                       const int* d_bin_seg, int window, int slice_max, double dynamic_range_db, cudaStream_t stream);

@@ -465,6 +465,24 @@ def csd(rows: Rows, start_idx: torch.Tensor, frame_idx: torch.Tensor, n_slices: 
     return out
 
 
+def csd_plan(rows: Rows, peaks: Optional[torch.Tensor], ignore_samples: int, keep_samples: int, n_fft: int, hop_length: int,
+             table: torch.Tensor, counts: torch.Tensor):
+    """(start [B], span [B], frames [B, S_max], n_slices [B]) int32 on the device (aa_csd_plan_batch)."""
+    lib = nat.load()
+    dev = rows.x.device
+    b = rows.n_rows
+    width = int(table.shape[1])
+    start = torch.empty(b, dtype=torch.int32, device=dev)
+    span = torch.empty(b, dtype=torch.int32, device=dev)
+    frames = torch.empty((b, width), dtype=torch.int32, device=dev)
+    nslices = torch.empty(b, dtype=torch.int32, device=dev)
+    with torch.cuda.device(dev):
+        nat.check(lib.aa_csd_plan_batch(_ptr(rows.lengths), rows.n, b, _ptr(peaks), int(ignore_samples), int(keep_samples),
+                                        int(n_fft), int(hop_length), _ptr(table), _ptr(counts), int(table.shape[0]) - 1,
+                                        width, _ptr(start), _ptr(span), _ptr(frames), _ptr(nslices), _stream_ptr()))
+    return start, span, frames, nslices
+
+
 def csd_smooth(slices: torch.Tensor, n_slices: torch.Tensor, k0: int, f_in: np.ndarray, grid: np.ndarray,
                grid_seg: np.ndarray, bin_seg: np.ndarray, window: int, db_reference: str,
                dynamic_range_db: float) -> torch.Tensor:

@@ -250,9 +250,9 @@ def _analyse_group(rows: engine.Rows, sr: int, names: List[str], settings: Repor
     out = {"decay": None, "bands": None, "water": None, "spec": None, "modal": None}
     smoothing = int(decay_s.edc_smoothing_window_samples or 0) > 1
     do_bands = bool(settings.run_rt60_bands) and rows.uniform
-    from .plotting import pyplot as _pyplot
-
-    hot = run_hot_path(rows, sr, decay_s, bands_s, water_s, want_edc=bool(settings.run_decay) and _pyplot() is not None,
+    # the curve-writing mode of the decay kernel always runs (same arithmetic, hence the same printed digits, as the
+    # per-file functions); whether the curves then LEAVE the device is decided below
+    hot = run_hot_path(rows, sr, decay_s, bands_s, water_s, want_edc=bool(settings.run_decay),
                        do_bands=do_bands, do_csd=bool(settings.run_waterfall), validate=False)
     if settings.run_decay:
         # the EDC curves are plot data: they leave the device only when there is a backend to draw them

@@ -282,31 +282,25 @@ def run_waterfall(rows: engine.Rows, sample_rate_hz: int, settings: WaterfallAna
     bin_lo, freq = frequency_selection(settings, sample_rate_hz)
     dev = rows.x.device
     b = rows.n_rows
-    lengths = rows.lengths if rows.lengths is not None else torch.full((b,), rows.n, dtype=torch.int32, device=dev)
+    peaks_d = None
     if settings.trim_to_peak:
-        start = (peaks if peaks is not None else engine.peak_index(rows)).to(torch.int32)
-    else:
-        start = torch.zeros(b, dtype=torch.int32, device=dev)
-    remaining = lengths - start
+        peaks_d = (peaks if peaks is not None else engine.peak_index(rows))
+        if peaks_d.dtype != torch.int32:
+            peaks_d = peaks_d.to(torch.int32)
+    skip = 0
     if settings.ignore_leading_seconds > 0.0:  # reference waterfall.py:363-367
-        skip = int(round(float(settings.ignore_leading_seconds) * float(sample_rate_hz)))
-        skip_t = torch.clamp(torch.full_like(remaining, max(0, skip)), max=remaining)
-        start = start + skip_t
-        remaining = remaining - skip_t
+        skip = max(0, int(round(float(settings.ignore_leading_seconds) * float(sample_rate_hz))))
+    keep = -1
     if settings.analysis_duration_seconds is not None:  # reference waterfall.py:369-372
-        keep = int(round(float(settings.analysis_duration_seconds) * float(sample_rate_hz)))
-        remaining = torch.clamp(torch.full_like(remaining, max(0, keep)), max=remaining)
+        keep = max(0, int(round(float(settings.analysis_duration_seconds) * float(sample_rate_hz))))
     max_frames = max(0, 1 + (rows.n - n_fft) // hop)
     table, counts = slice_table(settings, sample_rate_hz, max_frames)
-    n_frames = torch.where(remaining >= n_fft, 1 + torch.div(remaining - n_fft, hop, rounding_mode="floor"),
-                           torch.zeros_like(remaining)).to(torch.int64)
     table_d, counts_d = _device_slice_table(table, counts, dev)
-    frames_d = table_d[n_frames].contiguous()
-    nslices_d = counts_d[n_frames].contiguous()
+    # start / span / frame count / the row's line of the slice table: one small kernel of the library
+    start, remaining, frames_d, nslices_d = engine.csd_plan(rows, peaks_d, skip, keep, n_fft, hop, table_d, counts_d)
     tables = smoothing_tables(freq, settings) if int(settings.smoothing_log_bins or 0) > 1 else None
     params = engine.csd_params(n_fft, hop, settings.use_hann_window, bin_lo, int(freq.size), settings.db_reference,
                                settings.floor_db, settings.dynamic_range_db, raw_db=tables is not None)
-    start = start.contiguous()
     slices = engine.csd(rows, start, frames_d, nslices_d, params)
     if tables is not None:   # reference waterfall.py:312-339 on the device: smooth, then reference level and clip
         engine.csd_smooth(slices, nslices_d, *tables, int(settings.smoothing_log_bins), settings.db_reference,

@@ -278,6 +278,23 @@ int aa_csd_batch(const float* d_x, int64_t row_stride, const int32_t* d_lengths,
                  void* stream);
 
 /*
+ * aa_csd_plan_batch - which samples and frames of every row the waterfall analyses: the trim / ignore / duration rules
+ * of analyse_waterfall_for_channel (analyse/waterfall.py:358-372), the frame count (:208) and the row's line of the
+ * slice-selection table (the host tabulates _select_slice_frame_indices, :233-286, per frame count; the selection
+ * depends on nothing else).  Feeds aa_csd_batch without a host round trip.
+ *  d_peak_idx[n_rows]  : NULL (trim_to_peak off: start at 0) or the peak index per row
+ *  analysis_duration_samples : -1 = whole remainder
+ *  d_slice_table[max_frames + 1][table_width], d_slice_counts[max_frames + 1] : selected frames / their number
+ *  outputs: d_start_out[n_rows], d_span_out[n_rows] (analysed samples), d_frame_idx_out[n_rows][table_width],
+ *           d_n_slices_out[n_rows]
+ */
+int aa_csd_plan_batch(const int32_t* d_lengths, int32_t uniform_length, int32_t n_rows, const int32_t* d_peak_idx,
+                      int32_t ignore_leading_samples, int32_t analysis_duration_samples, int32_t n_fft, int32_t hop_length,
+                      const int32_t* d_slice_table, const int32_t* d_slice_counts, int32_t max_frames, int32_t table_width,
+                      int32_t* d_start_out, int32_t* d_span_out, int32_t* d_frame_idx_out, int32_t* d_n_slices_out,
+                      void* stream);
+
+/*
  * aa_csd_smooth_batch - the optional log-frequency smoothing of the waterfall slices, then reference level and clip.
  * Replaces _smooth_mag_db_log_frequency / _moving_average_1d (analyse/waterfall.py:132-185) and the tail of
  * _build_rel_db_slices (:312-339) when smoothing_log_bins > 1.
