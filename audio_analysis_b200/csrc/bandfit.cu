@@ -229,7 +229,9 @@ __global__ void __launch_bounds__(kFitThreads, AA_FIT_MIN_BLOCKS) band_fit_kerne
     const int n_targets = 2 + 2 * p.n_fits;
 
     // ---- crossings (decay.py:173-199): first sample <= target, by one warp (all lanes return the same values)
-    auto resolve = [&](float tauf, int& found, int& idx, float& y0, float& y1) {
+    // hint_tile >= 0: the tile where the crossing is expected (the certification targets sit within a few samples of a
+    // crossing that is already known): one 32-tile window is tried before the search over all tiles
+    auto resolve = [&](float tauf, int& found, int& idx, float& y0, float& y1, int hint_tile = -1) {
         found = 0;
         idx = 0;
         y0 = y1 = 0.f;
@@ -239,7 +241,8 @@ __global__ void __launch_bounds__(kFitThreads, AA_FIT_MIN_BLOCKS) band_fit_kerne
             return;
         }
         int hit = -1;
-        for (int kb = ks; kb < NT && hit < 0; kb += 32) {
+        // the tile with dB(first sample) > target >= dB(first sample of the next tile) is unique (monotone curve)
+        auto probe = [&](int kb) {
             const int k = kb + lane;
             bool ok = false;
             if (k < NT) {
@@ -250,7 +253,9 @@ __global__ void __launch_bounds__(kFitThreads, AA_FIT_MIN_BLOCKS) band_fit_kerne
             }
             const unsigned m = __ballot_sync(kFullMask, ok);
             if (m) hit = kb + (__ffs(m) - 1);
-        }
+        };
+        if (hint_tile >= 0) probe(max(ks, hint_tile - 2));
+        for (int kb = ks; kb < NT && hit < 0; kb += 32) probe(kb);
         if (hit < 0) return;
         const int k = hit;
         // steps are visited last to first; the curve is monotone, so the last step that reports a
@@ -375,7 +380,7 @@ __global__ void __launch_bounds__(kFitThreads, AA_FIT_MIN_BLOCKS) band_fit_kerne
                 const double tau = tau0 + (minus ? -delta : delta);
                 int found, idx;
                 float y0, y1;
-                resolve((float)tau, found, idx, y0, y1);
+                resolve((float)tau, found, idx, y0, y1, sh.cross_idx[e ? te_i : ts_i] / TL);
                 if (found) cidx = idx;
             }
             if (lane == 0) sh.cert_idx[ct] = cidx;

@@ -72,7 +72,8 @@ constexpr double kCertSafety = 9.0;     // crossing window half-width = safety x
 constexpr double kCertWindow = 0.015;   // a crossing window may cover at most this fraction of the fit span
 constexpr double kCertTol = 3.0e-3;     // modelled relative slope change allowed from both crossing windows together
 constexpr int kCertMinSpan = 240;       // decimated samples between the end points of a certified 30 dB fit, at least
-constexpr int kRefineLimit = 4;         // decimation limit of the middle level
+constexpr int kRefineLimit = 4;         // decimation limit of the last decimated level (and the first one of short fits)
+constexpr int kRefineLimitMid = 8;      // ... of the level between max_decimation and kRefineLimit
 
 namespace {
 
@@ -239,7 +240,7 @@ struct Layout {
     size_t off_bands, off_mask, off_X, off_y, off_scratch, off_part, off_counts, off_lists, off_db0, off_db1,
         off_unit_start, total;
 };
-constexpr int kMaxLevels = 3;
+constexpr int kMaxLevels = 4;
 constexpr int kMaxLists = (kMaxLevels - 1) * (aa_bands_plan::kDecims + 1);
 
 // Largest per-row footprint over the decimation classes of a call (elements per row): the buffers are shared by
@@ -351,6 +352,7 @@ void level_limits(const aa_decay_params* fits, int max_decimation, bool refine, 
     limits->clear();
     limits->push_back(top);
     if (!refine || top <= 1) return;
+    if (top > kRefineLimitMid) limits->push_back(kRefineLimitMid);
     if (top > kRefineLimit) limits->push_back(kRefineLimit);
     limits->push_back(1);
 }

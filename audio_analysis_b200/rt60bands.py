@@ -232,20 +232,19 @@ def run_rt60_bands(rows: engine.Rows, sample_rate_hz: int, settings: Rt60BandsAn
 def metrics_to_results(table: np.ndarray, bands: Sequence[BandDefinition], plan, names: Sequence[str],
                        sample_rate_hz: int) -> List[Rt60BandsChannelResult]:
     col = {name: i for i, (name, _) in enumerate(plan)}
-
-    def pick(row: np.ndarray, key: str) -> Optional[float]:
-        if key not in col:
-            return None
-        v = row[col[key]]
-        return None if np.isnan(v) else float(v)
-
+    # one conversion to Python floats for the whole table (NaN -> None), then plain indexing
+    vals = np.where(np.isnan(table), None, table.astype(object)).tolist()
+    c30, c20, cedt = col.get("T30"), col.get("T20"), col.get("EDT")
+    band_list = list(bands)
     results = []
     for b, name in enumerate(names):
+        rows_b = vals[b]
         by_name = {
-            band.name: Rt60BandMetrics(pick(table[b, k], "T30"), pick(table[b, k], "T20"), pick(table[b, k], "EDT"))
-            for k, band in enumerate(bands)
+            band.name: Rt60BandMetrics(None if c30 is None else rows_b[k][c30], None if c20 is None else rows_b[k][c20],
+                                       None if cedt is None else rows_b[k][cedt])
+            for k, band in enumerate(band_list)
         }
-        results.append(Rt60BandsChannelResult(str(name), int(sample_rate_hz), list(bands), by_name))
+        results.append(Rt60BandsChannelResult(str(name), int(sample_rate_hz), band_list, by_name))
     return results
 
 

@@ -68,9 +68,30 @@ class StagedTaps:
     frames: int
 
 
+_staging_cache = {}   # (files, width, pinned) -> tensor: pinning hundreds of MB costs more than reading them
+
+
+def _staging_buffer(files: int, width: int, pin: bool):
+    import torch
+
+    key = (int(files), int(width), bool(pin))
+    buf = _staging_cache.get(key)
+    if buf is None:
+        _staging_cache.clear()          # one live buffer: bundles are processed one after the other
+        try:
+            buf = torch.empty((files, width), dtype=torch.int16, pin_memory=bool(pin))
+        except RuntimeError:
+            buf = torch.empty((files, width), dtype=torch.int16)
+        _staging_cache[key] = buf
+    return buf
+
+
 def stage_pcm16(paths: Sequence[str | Path], pin: bool = True) -> Optional[StagedTaps]:
-    """Read the payloads of PCM16 WAV files of one common shape into a pinned staging buffer.  None when any file is
-    not PCM16 or the files differ in sample rate, channel count or length (the caller then loads them one by one)."""
+    """Read the payloads of PCM16 WAV files of one common shape into a pinned staging buffer (reused between calls: the
+    returned tensor is valid until the next call).  None when any file is not PCM16 or the files differ in sample rate,
+    channel count or length (the caller then loads them one by one).  Files are read by a small thread pool."""
+    from concurrent.futures import ThreadPoolExecutor
+
     import torch
 
     infos: List[Pcm16Info] = []
@@ -85,17 +106,22 @@ def stage_pcm16(paths: Sequence[str | Path], pin: bool = True) -> Optional[Stage
     if any((i.sample_rate_hz, i.channels, i.frames) != (first.sample_rate_hz, first.channels, first.frames) for i in infos):
         return None
     width = first.frames * first.channels
-    try:
-        buf = torch.empty((len(infos), width), dtype=torch.int16, pin_memory=bool(pin and torch.cuda.is_available()))
-    except RuntimeError:
-        buf = torch.empty((len(infos), width), dtype=torch.int16)
+    buf = _staging_buffer(len(infos), width, bool(pin and torch.cuda.is_available()))
     view = buf.numpy()
-    for row, (p, info) in enumerate(zip(paths, infos)):
-        with open(p, "rb") as f:
-            f.seek(info.data_offset)
+
+    def read_one(row: int) -> None:
+        with open(paths[row], "rb") as f:
+            f.seek(infos[row].data_offset)
             got = f.readinto(memoryview(view[row]).cast("B"))
         if got != 2 * width:
-            raise ValueError(f"{p}: data chunk shorter than its header says")
+            raise ValueError(f"{paths[row]}: data chunk shorter than its header says")
+
+    if len(infos) >= 8:
+        with ThreadPoolExecutor(max_workers=8) as pool:
+            list(pool.map(read_one, range(len(infos))))
+    else:
+        for row in range(len(infos)):
+            read_one(row)
     return StagedTaps(buf, first.sample_rate_hz, first.channels, first.frames)
 
 

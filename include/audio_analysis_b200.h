@@ -193,7 +193,7 @@ int aa_bands_plan_kind(const aa_bands_plan* plan);
  * distance of the curve from the fitted line at the end points; window <= cert_window x span, >= cert_min_span
  * decimated points per 30 dB fit).  The line fit itself (decay.py:224-249) weights the first and last decimated
  * sample by the part of their cell inside the reference's sample range.  Units that fail are redone on the next level: D <= max_decimation (default 16, or the environment
- * variable AA_BANDS_DECIMATION) -> D <= 4 -> full rate, whose results are the reference's estimator itself.
+ * variable AA_BANDS_DECIMATION) -> D <= 8 -> D <= 4 -> full rate, whose results are the reference's estimator itself.
  * A call with a fit shorter than 28 dB or starting above -2.5 dB (T20, EDT) starts at D <= 4.
  * D in {2, 3, 4, 6, 8, 12, 16, 24}; max_decimation 1 = everything at full rate.
  * aa_bands_classify reports the first-level factor of each band (host only, no device work).

@@ -441,7 +441,7 @@ def test_band_certification_at_scale(n):
     assert engine.last_bands_stats["limits"] == [1]
     got = rb.run_rt60_bands(rows, SR, s)[0].cpu().numpy()[:, :, 0]
     stats = dict(engine.last_bands_stats)
-    assert stats["limits"] == [16, 4, 1] and stats["units"][0] == rows_n * 26
+    assert stats["limits"] == [16, 8, 4, 1] and stats["units"][0] == rows_n * 26
     redo = sum(stats["units"][1:]) / float(rows_n * 26)
     note(f"band_certification_redo_fraction[n{n}]", redo)
     assert 0.0 < redo < 0.2, stats
