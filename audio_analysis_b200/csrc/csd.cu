@@ -575,6 +575,15 @@ __global__ void pcm16_kernel(const short* __restrict__ pcm, long long pcm_stride
     }
 }
 
+// slices a row does not have (n_slices < max_slices) read as zero: the caller's buffer need not be cleared
+__global__ void csd_clear_unused_kernel(float* __restrict__ out, const int* __restrict__ n_slices, int max_slices, int n_bins) {
+    const int row = blockIdx.x;
+    const int ns = min(max(n_slices[row], 0), max_slices);
+    float* __restrict__ p = out + ((long long)row * max_slices + ns) * n_bins;
+    const long long total = (long long)(max_slices - ns) * n_bins;
+    for (long long i = threadIdx.x; i < total; i += blockDim.x) p[i] = 0.0f;
+}
+
 }  // namespace
 
 int launch_csd(const float* d_x, long long row_stride, const int* d_lengths, int uniform_len, int n_rows,
@@ -616,6 +625,9 @@ int launch_csd(const float* d_x, long long row_stride, const int* d_lengths, int
     a.twN = t.d_twN;
     a.hann = t.d_hann;
     a.twc = t.d_twc;
+    csd_clear_unused_kernel<<<(unsigned)n_rows, 128, 0, stream>>>(d_out, d_n_slices, max_slices, p->n_bins);
+    rc = launch_check("csd_clear_unused_kernel");
+    if (rc != AA_OK) return rc;
     {
         const int rc_tma = csd_tma_dispatch(a, n_rows, stream);
         if (rc_tma != AA_ERR_UNSUPPORTED) return rc_tma;

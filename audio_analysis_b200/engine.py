@@ -457,7 +457,7 @@ def csd(rows: Rows, start_idx: torch.Tensor, frame_idx: torch.Tensor, n_slices: 
     dev = rows.x.device
     b = rows.n_rows
     max_slices = int(frame_idx.shape[1])
-    out = torch.zeros((b, max_slices, int(params.n_bins)), dtype=torch.float32, device=dev)
+    out = torch.empty((b, max_slices, int(params.n_bins)), dtype=torch.float32, device=dev)   # unused slices: kernel
     with torch.cuda.device(dev):
         nat.check(lib.aa_csd_batch(_ptr(rows.x), rows.stride, _ptr(rows.lengths), rows.n, b, _ptr(start_idx),
                                    _ptr(frame_idx), _ptr(n_slices), max_slices, C.byref(params), _ptr(out),
@@ -555,7 +555,9 @@ def pcm16_to_rows(pcm: torch.Tensor, n_frames: int, n_channels: int, mono_downmi
     files = int(pcm.shape[0])
     per_file = 1 if (mono_downmix or n_channels == 1) else n_channels
     stride = round_up4(n_frames)
-    out = torch.zeros((files * per_file, stride), dtype=torch.float32, device=dev)
+    out = torch.empty((files * per_file, stride), dtype=torch.float32, device=dev)
+    if stride > n_frames:
+        out[:, n_frames:].zero_()          # row padding (< 4 samples): nothing else needs clearing
     with torch.cuda.device(dev):
         nat.check(lib.aa_pcm16_to_float_batch(_ptr(pcm), _pitch(pcm), files, int(n_frames), int(n_channels),
                                               1 if (mono_downmix and n_channels == 2) else 0, _ptr(out), stride,
