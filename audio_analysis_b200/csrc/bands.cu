@@ -625,14 +625,25 @@ int rt60bands_batch(const aa_bands_plan* plan, const float* d_x, long long row_s
             s.base = xin;
             s.unit_stride = row_stride;
             s.n_valid = N;
-            rc = c2c_exec(plan->c2c, s, make_dst_complex(d_Z, M, M, 0, 1.0f), rows, d_scr, stream);
-            if (rc != AA_OK) return rc;
-            dim3 grid((unsigned)((M / 2 + 1 + 255) / 256 > 36 ? 36 : (M / 2 + 1 + 255) / 256), (unsigned)rows);  // ~8 pairs per thread: amortises the index set-up
-            ProfScope prof("untangle", stream);
-            untangle_kernel<<<grid, 256, 0, stream>>>(d_Z, d_X, M, plan->x_stride, plan->twN.dev,
-                                                      one_class ? nullptr : d_start_idx + r0);
-            rc = launch_check("untangle_kernel");
-            if (rc != AA_OK) return rc;
+            if (c2c_can_untangle(plan->c2c)) {
+                // pass 2 untangles in shared memory and writes the (time-advanced) half spectrum directly
+                DstDesc d = make_dst_complex(d_Z, M, M, 0, 1.0f);
+                d.untangle_X = d_X;
+                d.untangle_stride = plan->x_stride;
+                d.untangle_twN = plan->twN.dev;
+                d.untangle_advance = one_class ? nullptr : d_start_idx + r0;
+                rc = c2c_exec(plan->c2c, s, d, rows, d_scr, stream);
+                if (rc != AA_OK) return rc;
+            } else {
+                rc = c2c_exec(plan->c2c, s, make_dst_complex(d_Z, M, M, 0, 1.0f), rows, d_scr, stream);
+                if (rc != AA_OK) return rc;
+                dim3 grid((unsigned)((M / 2 + 1 + 255) / 256 > 36 ? 36 : (M / 2 + 1 + 255) / 256), (unsigned)rows);  // ~8 pairs per thread: amortises the index set-up
+                ProfScope prof("untangle", stream);
+                untangle_kernel<<<grid, 256, 0, stream>>>(d_Z, d_X, M, plan->x_stride, plan->twN.dev,
+                                                          one_class ? nullptr : d_start_idx + r0);
+                rc = launch_check("untangle_kernel");
+                if (rc != AA_OK) return rc;
+            }
         } else {
             SrcDesc s{};
             s.mode = SRC_REAL_AS_COMPLEX;

@@ -354,6 +354,83 @@ __global__ void __launch_bounds__(P::kThreads) fft_rows_reg(const float2* __rest
     }
 }
 
+#ifndef AA_ROWS_PLAIN_G
+#define AA_ROWS_PLAIN_G 4   /* 96-thread CTAs, 12 per SM: 5.53 -> 5.11 ms per 8192 forward transforms against groups of 8 */
+#endif
+
+// forward real transform: pass 2 + untangle in one kernel (fft_reg.cuh).  Threads [0, kThreads) own group A,
+// [kThreads, 2 kThreads) the mirrored group B; CTA 0 of a transform handles the self-paired rows 0 and M1 / 2.
+template <class P, int M1>
+__global__ void __launch_bounds__(2 * P::kThreads) fft_rows_untangle_reg(const float2* __restrict__ scratch, float2* __restrict__ X,
+                                                                         long long x_stride, const float2* __restrict__ tw_full,
+                                                                         TwoLevelTwiddle twN, const int* __restrict__ advance) {
+    static_assert(M1 % 2 == 0 && M1 / 2 >= P::G, "mirrored row groups need an even M1");
+    constexpr int half_groups = (M1 / 2 - 1 + P::G - 1) / P::G;
+    constexpr int groups = half_groups + 1;
+    extern __shared__ float2 smem[];
+    float2* bufA = smem;
+    float2* bufB = smem + P::kBufElems;
+    float2* tws = bufB + P::kBufElems;
+    const int unit = blockIdx.x / groups;
+    const int c = blockIdx.x - unit * groups;
+    const int half = (int)threadIdx.x / P::kThreads;
+    const int t = (int)threadIdx.x - half * P::kThreads;
+    const float2* scratch_unit = scratch + (size_t)unit * ((size_t)M1 * P::L);
+    UntangleOut u;
+    u.X = X + (size_t)unit * x_stride;
+    u.M1 = M1;
+    u.M2 = P::L;
+    u.twN = twN;
+    u.advance = advance ? advance[unit] : 0;
+    const int rA0 = 1 + (c - 1) * P::G, rB0 = M1 - rA0 - P::G + 1;
+    if (c == 0) {
+        if (half == 0) reg_rows_stage_a_rows<P>(t, scratch_unit, RowsSelfPaired{M1 / 2}, bufA);
+    } else if (half == 0) {
+        reg_rows_stage_a_rows<P>(t, scratch_unit, RowsFrom{rA0}, bufA);
+    } else {
+        reg_rows_stage_a_rows<P>(t, scratch_unit, RowsFrom{rB0}, bufB);
+    }
+    reg_fill_twiddles<P>((int)threadIdx.x, 2 * P::kThreads, tws, tw_full);
+    __syncthreads();
+    const bool active = t < P::kThreadsB && (c != 0 || half == 0);
+    float2 v[P::RB];
+    if (active) reg_rows_stage_b_regs<P>(t, half ? bufB : bufA, tws, v);
+    __syncthreads();
+    if (active) reg_rows_store_local<P>(t, v, half ? bufB : bufA);
+    __syncthreads();
+    if (c == 0) reg_untangle_special<P>((int)threadIdx.x, 2 * P::kThreads, bufA, u);
+    else reg_untangle_general<P>((int)threadIdx.x, 2 * P::kThreads, bufA, bufB, u, rA0);
+}
+
+bool launch_rows_untangle_reg(const C2CPlan* p, const float2* scratch, const DstDesc& dst, long long units, cudaStream_t stream,
+                              bool dry_run) {
+#define X(ra1, rb1, g1, ra2, rb2, g2)                                                                         \
+    if (p->M1 == ra1 * rb1 && p->M2 == ra2 * rb2) {                                                           \
+        constexpr int m1 = ra1 * rb1;                                                                         \
+        constexpr int gp = (m1 % AA_ROWS_PLAIN_G == 0) ? AA_ROWS_PLAIN_G : g2;                                \
+        if constexpr (m1 % 2 == 0 && m1 / 2 >= gp) {                                                          \
+            using PP = RegCfg<ra2, rb2, gp>;                                                                  \
+            if (dry_run) return true;                                                                         \
+            constexpr int groups = (m1 / 2 - 1 + gp - 1) / gp + 1;                                            \
+            constexpr size_t smem = sizeof(float2) * (size_t)(2 * PP::kBufElems + PP::L);                     \
+            auto k = fft_rows_untangle_reg<PP, m1>;                                                           \
+            static bool once = false;                                                                         \
+            if (!once) {                                                                                      \
+                cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);              \
+                once = true;                                                                                  \
+            }                                                                                                 \
+            k<<<(unsigned)(units * groups), 2 * PP::kThreads, smem, stream>>>(scratch, dst.untangle_X, dst.untangle_stride, \
+                                                                              p->s2.dev.tw, dst.untangle_twN,  \
+                                                                              dst.untangle_advance);          \
+            return true;                                                                                      \
+        }                                                                                                     \
+        return false;                                                                                         \
+    }
+    AA_REG_LIST(X)
+#undef X
+    return false;
+}
+
 template <int kSrc>
 bool launch_cols_reg(const C2CPlan* p, const SrcDesc& src, float2* scratch, long long units, cudaStream_t stream) {
 #define X(ra1, rb1, g1, ra2, rb2, g2)                                                                         \
@@ -374,9 +451,6 @@ bool launch_cols_reg(const C2CPlan* p, const SrcDesc& src, float2* scratch, long
     return false;
 }
 
-#ifndef AA_ROWS_PLAIN_G
-#define AA_ROWS_PLAIN_G 4   /* 96-thread CTAs, 12 per SM: 5.53 -> 5.11 ms per 8192 forward transforms against groups of 8 */
-#endif
 bool launch_rows_reg(const C2CPlan* p, const float2* scratch, const DstDesc& dst, long long units, cudaStream_t stream) {
 #define X(ra1, rb1, g1, ra2, rb2, g2)                                                                         \
     if (p->M1 == ra1 * rb1 && p->M2 == ra2 * rb2) {                                                           \
@@ -484,6 +558,13 @@ int exec_direct(const C2CPlan* p, const SrcDesc& src, const DstDesc& dst, long l
     const unsigned g = (unsigned)grid;
     const bool src_plain = (src2.mode == SRC_COMPLEX && src2.chirp == nullptr);
     const bool dst_plain = plain_complex_dst(dst);
+    if (dst.untangle_X != nullptr) {   // forward real transform: pass 2 and the untangle step in one kernel
+        ProfScope prof("fft_rows_untangle", stream);
+        AA_REQUIRE(p->M1 > 1 && src_plain && dst.conj1 == 0 && dst.scale1 == 1.0f && getenv("AA_FFT_GENERIC") == nullptr &&
+                       launch_rows_untangle_reg(p, scratch, dst, units, stream, false),
+                   AA_ERR_UNSUPPORTED, "no fused untangle pass for this plan (see c2c_can_untangle)");
+        return launch_check("fft_rows_untangle_reg");
+    }
     ProfScope prof(dst.energy ? "fft_rows_band" : "fft_rows", stream);
     const bool spec2 = getenv("AA_FFT_GENERIC") == nullptr && p->M1 > 1 && src_plain && dst_plain &&
                        units * (long long)p->M < 2147483647LL &&
@@ -528,6 +609,13 @@ int build_direct(int M, C2CPlan* p) {
 }  // namespace
 
 bool is_smooth(long long n) { return is_smooth_host(n); }
+
+bool c2c_can_untangle(const C2CPlan* p) {
+    if (!p || p->bluestein || p->M1 <= 1 || getenv("AA_FFT_GENERIC") != nullptr || getenv("AA_NO_FUSED_UNTANGLE") != nullptr)
+        return false;
+    if ((long long)p->M2 * 2LL * (long long)p->M >= 2147483647LL) return false;   // 32-bit phase arithmetic
+    return launch_rows_untangle_reg(p, nullptr, DstDesc{}, 0, nullptr, true);
+}
 
 // Tiles of the energy partials a DstDesc may request from c2c_exec: rows are transformed in groups of 8, so a
 // transform's outputs fall into M2 tiles of M1 consecutive complex values and M1 / G2 partial sums per tile.

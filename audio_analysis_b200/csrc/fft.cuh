@@ -35,6 +35,8 @@ struct C2CPlan {
 
 // layout of the optional energy partials (DstDesc::energy); false when this plan cannot produce them
 bool c2c_energy_layout(const C2CPlan* p, int* tile_complex, int* n_tiles, int* n_groups);
+// true when c2c_exec can fuse the real-FFT untangle step into pass 2 (DstDesc::untangle_X)
+bool c2c_can_untangle(const C2CPlan* p);
 // true if n factors completely into the supported radices
 bool is_smooth(long long n);
 int build_two_level(long long len, TwoLevelTable* out);

@@ -232,6 +232,13 @@ struct DstDesc {
     // energy[unit * energy_stride + row_group * M2 + k2] = sum over the group's rows k1 of |out[k2 * M1 + k1]|^2
     float* energy;
     long long energy_stride;
+    // optional (register-pass lengths with an even M1, see c2c_can_untangle): the transform is the packed transform of
+    // a real signal; pass 2 untangles it in shared memory and stores the half spectrum X[unit][0..M] here instead of
+    // the packed output (base is then unused).  untangle_advance[unit] = s stores X[k] exp(+2 pi i k s / N).
+    float2* untangle_X;
+    long long untangle_stride;
+    TwoLevelTwiddle untangle_twN;   // exp(-2 pi i m / N), N = 2 M
+    const int* untangle_advance;
 };
 
 AA_HD void dst_put(const DstDesc& d, long long unit, int idx, float2 v) {

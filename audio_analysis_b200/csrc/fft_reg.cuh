@@ -271,4 +271,136 @@ AA_HD void reg_rows_stage_b(int t, const float2* buf, const float2* tws, float2*
     });
 }
 
+// ---- pass 2 of the forward REAL transform fused with the untangle step ---------------------------------------------
+// The packed transform Z = FFT_M(x[2m] + i x[2m+1]) becomes the half spectrum through pairs:
+//   X[k] = untangle(Z[k], Z[M - k], w^k),  X[M - k] = untangle(Z[M - k], Z[k], -conj w^k),  w = exp(-2 pi i / N).
+// With k = k2 M1 + k1 the partner M - k is (M2 - 1 - k2) M1 + (M1 - k1) for k1 > 0: row k1 of the rows pass pairs with
+// row M1 - k1.  A CTA therefore transforms a group A of G rows k1 = rA0 .. rA0 + G - 1 (1 <= k1 < M1 / 2) AND the
+// mirrored group B = rows M1 - k1, keeps both groups' outputs in shared memory and writes X directly - the packed
+// spectrum never goes to memory and the separate untangle pass (a read and a write of the whole spectrum) disappears.
+// The self-paired rows 0 and M1 / 2 (M1 even) are handled by one extra CTA per transform.
+// Optionally the spectrum is stored time-advanced by s samples (X[k] e^{+2 pi i k s / N}, bands.cu).
+
+struct RowsFrom {      // slot g -> row r0 + g
+    int r0;
+    AA_HD int operator()(int g) const { return r0 + g; }
+};
+struct RowsSelfPaired {   // slot 0 -> row 0, slot 1 -> row M1 / 2 (the other slots repeat row 0 and are ignored)
+    int half;
+    AA_HD int operator()(int g) const { return g == 1 ? half : 0; }
+};
+
+// stage A with an arbitrary row per slot g (row_of(g)); same shared-memory layout as reg_rows_stage_a
+template <class P, class RowOf>
+AA_HD void reg_rows_stage_a_rows(int t, const float2* scratch_unit, RowOf row_of, float2* buf) {
+    if (t >= P::kThreadsA) return;
+    const int ja = t / P::G, g = t - ja * P::G;
+    const float2* in = scratch_unit + (long long)row_of(g) * P::L + ja;
+    float2 v[P::RA];
+    static_for<0, P::RA>([&](auto r_) {
+        constexpr int r = decltype(r_)::value;
+        v[r] = load_c(in + r * P::RB);
+    });
+    dft_r<P::RA>(v);
+    static_for<0, P::RA>([&](auto r_) {
+        constexpr int r = decltype(r_)::value;
+        buf[P::slot(g, ja, r)] = v[r];
+    });
+}
+
+// stage B into registers: v[q] = output k2 = jb + q RA of the row in slot g (t = jb G + g)
+template <class P>
+AA_HD void reg_rows_stage_b_regs(int t, const float2* buf, const float2* tws, float2* v) {
+    const int jb = t / P::G, g = t - jb * P::G;
+    static_for<0, P::RB>([&](auto r_) {
+        constexpr int r = decltype(r_)::value;
+        const float2 x = buf[P::slot(g, r, jb)];
+        v[r] = (r == 0) ? x : cmul(x, tws[r * P::RA + jb]);
+    });
+    dft_r<P::RB>(v);
+}
+
+// ... and from registers into the group's local output table out[k2 * G + g] (may alias the stage buffer once every
+// thread of the group has finished reg_rows_stage_b_regs)
+template <class P>
+AA_HD void reg_rows_store_local(int t, const float2* v, float2* out) {
+    const int jb = t / P::G, g = t - jb * P::G;
+    static_for<0, P::RB>([&](auto q_) {
+        constexpr int q = decltype(q_)::value;
+        out[(jb + q * P::RA) * P::G + g] = v[q];
+    });
+}
+
+struct UntangleOut {
+    float2* X;              // half spectrum of this transform, M + 1 entries
+    int M1, M2;             // M = M1 M2, N = 2 M
+    TwoLevelTwiddle twN;    // exp(-2 pi i m / N)
+    int advance;            // s: store X[k] exp(+2 pi i k s / N); 0 = plain
+};
+
+AA_HD void untangle_store_pair(const UntangleOut& u, int k, int mk, float2 zk, float2 zm, unsigned rk) {
+    // rk = (k s) mod N; ((M - k) s) mod N = (M s mod N) - rk
+    const unsigned N = 2u * (unsigned)u.M1 * (unsigned)u.M2;
+    const float2 w = twiddle2(u.twN, k);
+    float2 a = untangle_half_spectrum(zk, zm, w);
+    float2 b = untangle_half_spectrum(zm, zk, make_float2(-w.x, w.y));
+    if (u.advance != 0) {
+        const unsigned half_turn = (u.advance & 1) ? N / 2u : 0u;
+        const unsigned rm = (half_turn >= rk) ? half_turn - rk : half_turn + N - rk;
+        a = cmulc(a, twiddle2(u.twN, rk));
+        b = cmulc(b, twiddle2(u.twN, rm == N ? 0u : rm));
+    }
+    u.X[k] = a;
+    u.X[mk] = b;
+}
+
+// general groups: element e = k2 G + g of group A (row k1 = rA0 + g) with its partner in group B, whose slot G - 1 - g
+// holds row M1 - k1
+template <class P>
+AA_HD void reg_untangle_general(int t, int nthreads, const float2* outA, const float2* outB, const UntangleOut& u, int rA0) {
+    const unsigned N = 2u * (unsigned)u.M1 * (unsigned)u.M2;
+    const unsigned s = (unsigned)u.advance;
+    const unsigned a_step = (unsigned)(((unsigned long long)u.M1 * s) % N);   // (M1 s) mod N
+    for (int e = t; e < P::G * P::L; e += nthreads) {
+        const int k2 = e / P::G, g = e - k2 * P::G;
+        const int k1 = rA0 + g;
+        if (2 * k1 >= u.M1) continue;                      // beyond the last mirrored pair
+        const int k = k2 * u.M1 + k1;
+        const int mk = (u.M2 - 1 - k2) * u.M1 + (u.M1 - k1);
+        unsigned rk = 0;
+        if (s) rk = (unsigned)(((unsigned long long)k2 * a_step + ((unsigned long long)k1 * s) % N) % N);
+        untangle_store_pair(u, k, mk, outA[e], outB[(u.M2 - 1 - k2) * P::G + (P::G - 1 - g)], rk);
+    }
+}
+
+// the self-paired rows: slot 0 holds row 0, slot 1 row M1 / 2
+template <class P>
+AA_HD void reg_untangle_special(int t, int nthreads, const float2* out, const UntangleOut& u) {
+    const unsigned N = 2u * (unsigned)u.M1 * (unsigned)u.M2;
+    const unsigned s = (unsigned)u.advance;
+    const unsigned a_step = (unsigned)(((unsigned long long)u.M1 * s) % N);
+    const int M = u.M1 * u.M2;
+    for (int e = t; e < 2 * P::L; e += nthreads) {
+        const int which = e / P::L, k2 = e - which * P::L;
+        if (which == 0) {   // row 0: k = k2 M1 pairs with (M2 - k2) M1; k2 = 0 pairs bin 0 with bin M (both from Z[0])
+            const int p2 = (k2 == 0) ? 0 : u.M2 - k2;
+            if (k2 > p2 && k2 != 0) continue;
+            if (k2 != 0 && 2 * k2 > u.M2) continue;
+            const int k = k2 * u.M1;
+            const int mk = (k2 == 0) ? M : p2 * u.M1;
+            unsigned rk = 0;
+            if (s) rk = (unsigned)(((unsigned long long)k2 * a_step) % N);
+            untangle_store_pair(u, k, mk, out[k2 * P::G + 0], out[p2 * P::G + 0], rk);
+        } else {            // row M1 / 2: k2 pairs with M2 - 1 - k2
+            const int p2 = u.M2 - 1 - k2;
+            if (k2 > p2) continue;
+            const int k1 = u.M1 / 2;
+            const int k = k2 * u.M1 + k1, mk = p2 * u.M1 + k1;
+            unsigned rk = 0;
+            if (s) rk = (unsigned)(((unsigned long long)k2 * a_step + ((unsigned long long)k1 * s) % N) % N);
+            untangle_store_pair(u, k, mk, out[k2 * P::G + 1], out[p2 * P::G + 1], rk);
+        }
+    }
+}
+
 }  // namespace aa

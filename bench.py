@@ -264,7 +264,8 @@ def run_ours(args):
     band_levels = dict(engine.last_bands_stats)
     gather_ms = (sum(a.elapsed_time(b) for a, b in gather_events) / len(gather_events)) if gather_events else None
     lib.aa_profile_collect()
-    stage_names = ["edc", "fft_cols", "fft_rows", "untangle", "fft_cols_band", "fft_rows_band", "band_fit", "band_edc", "csd"]
+    stage_names = ["edc", "fft_cols", "fft_rows", "untangle", "fft_rows_untangle", "fft_cols_band", "fft_rows_band",
+                   "band_fit", "band_edc", "csd"]
     stage_ms = {k: lib.aa_profile_ms(k.encode()) / args.steps for k in stage_names}
     stage_scopes = {k: int(lib.aa_profile_scopes(k.encode())) // args.steps for k in stage_names}
     # band stage per decimation class (nested scopes around the class's kernels)
@@ -298,6 +299,9 @@ def run_ours(args):
         "fft_cols": (8.0 * rows_n * n, "hbm", "fft_cols_reg: first pass of the forward real FFT"),
         "fft_rows": (8.0 * rows_n * n, "hbm", "fft_rows_reg: second pass of the forward real FFT"),
         "untangle": (8.0 * rows_n * n, "hbm", "untangle_kernel: packed spectrum -> half spectrum"),
+        # second pass + untangle in one kernel: reads the scratch matrix, writes the half spectrum
+        "fft_rows_untangle": (8.0 * rows_n * n, "hbm / latency",
+                              "fft_rows_untangle_reg: second pass of the forward real FFT fused with the untangle step"),
         # per (row, band) unit: the masked spectrum is generated on the fly, the pass writes N/2 complex values
         "fft_cols_band": (4.0 * band_units_total, "fp32 issue (band source + butterflies); writes 4 B per synthesised sample",
                           "fft_cols_reg<band>: first pass of the masked inverse FFT"),
@@ -345,8 +349,8 @@ def run_ours(args):
                 "note": "dominant kernel by device time inside the timed region; the band stage as a whole has 4 B/sample "
                         "of algorithmic traffic (SURVEY 8d) and is bound by fp32 issue, not HBM (SURVEY D7): see "
                         "roofline_by_kernel"}
-    ms_bands = sum(stage_ms[k] for k in ("fft_cols", "fft_rows", "untangle", "fft_cols_band", "fft_rows_band", "band_fit",
-                                          "band_edc"))
+    ms_bands = sum(stage_ms[k] for k in ("fft_cols", "fft_rows", "untangle", "fft_rows_untangle", "fft_cols_band",
+                                          "fft_rows_band", "band_fit", "band_edc"))
     by_kernel["rt60bands_stage"] = {**roof(4.0 * rows_n * n, ms_bands), "bound": "fp32 issue / intermediate traffic",
                                     "kernel": "whole band stage against SURVEY 8d's 4 B/sample (read x once)",
                                     "share_of_step": round(ms_bands / ms_step, 4)}

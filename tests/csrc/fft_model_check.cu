@@ -372,6 +372,123 @@ static BandDev make_bandpass(double low, double high, double tw_oct, double nyq,
     return b;
 }
 
+// serial emulation of fft_rows_untangle_reg (fft.cu): forward real transform, pass 1 as above, pass 2 fused with the
+// untangle step.  x: N real samples; X: M + 1 half-spectrum bins, stored time-advanced by `advance` samples.
+template <int RA1, int RB1, int G1, int RA2, int RB2, int GP>
+static void emu_fused_forward(const HostC2C& p, const float* x, int N, float2* X, const HostTwoLevel& twN_h, int advance) {
+    using P1 = RegPass<RA1, RB1, G1, emu_reg_pitch(G1, RB1 * (RA1 | 1))>;
+    using P2 = RegPass<RA2, RB2, GP, emu_reg_pitch(GP, RB2 * (RA2 | 1))>;
+    const int M1 = P1::L, M2 = P2::L;
+    std::vector<float2> scratch((size_t)M1 * M2), buf((size_t)P1::kBufElems), tws((size_t)P1::L), colq((size_t)P1::kColQElems);
+    TwoLevelTwiddle twM = dev_view(p.twM);
+    for (int t = 0; t < P1::kThreads; ++t) reg_fill_twiddles<P1>(t, P1::kThreads, tws.data(), p.s1.tw.data());
+    for (int cta = 0; cta < M2 / G1; ++cta) {
+        const int col0 = cta * G1;
+        RegSrcComplex s{(const float2*)x};
+        for (int t = 0; t < P1::kThreads; ++t) reg_cols_stage_a<P1>(t, s, M2, col0, buf.data());
+        for (int t = 0; t < P1::kThreads; ++t) reg_cols_fill_colq<P1>(t, colq.data(), col0, twM);
+        for (int t = 0; t < P1::kThreads; ++t)
+            reg_cols_stage_b<P1>(t, buf.data(), tws.data(), colq.data(), scratch.data(), M2, col0, twM);
+    }
+    std::vector<float2> bufA((size_t)P2::kBufElems), bufB((size_t)P2::kBufElems), tws2((size_t)P2::L);
+    const int nthreads = 2 * P2::kThreads;
+    for (int t = 0; t < nthreads; ++t) reg_fill_twiddles<P2>(t, nthreads, tws2.data(), p.s2.tw.data());
+    UntangleOut u;
+    u.X = X;
+    u.M1 = M1;
+    u.M2 = M2;
+    u.twN = dev_view(twN_h);
+    u.advance = advance;
+    const int half_groups = (M1 / 2 - 1 + GP - 1) / GP, groups = half_groups + 1;
+    for (int c = 0; c < groups; ++c) {
+        const int rA0 = 1 + (c - 1) * GP, rB0 = M1 - rA0 - GP + 1;
+        for (int tt = 0; tt < nthreads; ++tt) {
+            const int half = tt / P2::kThreads, t = tt - half * P2::kThreads;
+            if (c == 0) {
+                if (half == 0) reg_rows_stage_a_rows<P2>(t, scratch.data(), RowsSelfPaired{M1 / 2}, bufA.data());
+            } else if (half == 0) {
+                reg_rows_stage_a_rows<P2>(t, scratch.data(), RowsFrom{rA0}, bufA.data());
+            } else {
+                reg_rows_stage_a_rows<P2>(t, scratch.data(), RowsFrom{rB0}, bufB.data());
+            }
+        }
+        std::vector<float2> regs((size_t)nthreads * P2::RB);
+        for (int tt = 0; tt < nthreads; ++tt) {
+            const int half = tt / P2::kThreads, t = tt - half * P2::kThreads;
+            if (t < P2::kThreadsB && (c != 0 || half == 0))
+                reg_rows_stage_b_regs<P2>(t, half ? bufB.data() : bufA.data(), tws2.data(), &regs[(size_t)tt * P2::RB]);
+        }
+        for (int tt = 0; tt < nthreads; ++tt) {
+            const int half = tt / P2::kThreads, t = tt - half * P2::kThreads;
+            if (t < P2::kThreadsB && (c != 0 || half == 0))
+                reg_rows_store_local<P2>(t, &regs[(size_t)tt * P2::RB], half ? bufB.data() : bufA.data());
+        }
+        for (int tt = 0; tt < nthreads; ++tt) {
+            if (c == 0) reg_untangle_special<P2>(tt, nthreads, bufA.data(), u);
+            else reg_untangle_general<P2>(tt, nthreads, bufA.data(), bufB.data(), u, rA0);
+        }
+    }
+}
+
+static void check_fused_untangle(int N, int advance) {
+    const int M = N / 2;
+    std::vector<float> x((size_t)N);
+    double norm = 0;
+    for (int n = 0; n < N; ++n) {
+        x[(size_t)n] = (float)(urand() * exp(-6.0 * n / N));
+        norm += (double)x[(size_t)n] * x[(size_t)n];
+    }
+    norm = sqrt(norm);
+    HostC2C h;
+    if (!host_direct_plan(M, &h)) {
+        ++failures;
+        return;
+    }
+    HostTwoLevel twN;
+    host_two_level(N, &twN);
+    std::vector<float2> X((size_t)M + 1, make_float2(1e30f, 1e30f));
+    bool used = false;
+#define X_(ra1, rb1, g1, ra2, rb2, g2)                                                                   \
+    if (!used && h.M1 == (ra1) * (rb1) && h.M2 == (ra2) * (rb2)) {                                       \
+        constexpr int m1 = (ra1) * (rb1);                                                                \
+        constexpr int gp = (m1 % 4 == 0) ? 4 : (g2);                                                     \
+        if constexpr (m1 % 2 == 0 && m1 / 2 >= gp) {                                                     \
+            emu_fused_forward<ra1, rb1, g1, ra2, rb2, gp>(h, x.data(), N, X.data(), twN, advance);       \
+            used = true;                                                                                 \
+        }                                                                                                \
+    }
+    AA_REG_LIST(X_)
+#undef X_
+    if (!used) {
+        printf("fused untangle: no register-pass plan for N = %d\n", N);
+        ++failures;
+        return;
+    }
+    // every bin must have been written, and a sample of them must equal the direct sums (time-advanced)
+    double worst = 0;
+    for (int k = 0; k <= M; ++k)
+        if (X[(size_t)k].x > 1e29f) {
+            printf("fused untangle N=%d: bin %d not written\n", N, k);
+            ++failures;
+            return;
+        }
+    for (int c = 0; c < 40; ++c) {
+        int k = (c == 0) ? 0 : (c == 1) ? M : (c == 2) ? M / 2 : (c == 3) ? h.M1 / 2 : (c == 4) ? h.M1 : (c == 5) ? M - h.M1 / 2
+                : (c == 6) ? 1 : (c == 7) ? M - 1 : (int)(urand() * 0.5 * M + 0.5 * M) % (M + 1);
+        if (k < 0) k = -k;
+        cd acc = 0;
+        for (int n = 0; n < N; ++n) {
+            double ang = -2.0 * M_PI * (double)(((long long)(n - advance + (long long)N * 4) % N * k) % N) / N;
+            acc += (double)x[(size_t)n] * cd(cos(ang), sin(ang));
+        }
+        double e = std::abs(acc - cd(X[(size_t)k].x, X[(size_t)k].y)) / norm;
+        if (e > worst) worst = e;
+    }
+    char name[64];
+    snprintf(name, sizeof(name), "rfft fused untangle, advance %d", advance);
+    report(name, N, worst, 5e-6);
+}
+
 static void check_real_band(int N, double lo0 = 890.9, double hi0 = 1122.5) {
     const double sr = 48000.0;
     const double freq_scale = 1.0 / ((double)N * (1.0 / sr));
@@ -671,6 +788,10 @@ int main() {
     for (int N : real_sizes) check_real_band(N);
     check_real_band(288000, 111.4, 140.3);  // the register-pass splits (narrow bands keep the direct sums cheap)
     check_real_band(192000, 7127.2, 7300.0);
+    check_fused_untangle(288000, 0);
+    check_fused_untangle(288000, 17041);
+    check_fused_untangle(192000, 9999);
+    check_fused_untangle(192000, 1);
     check_decimated_band(288000, 4, 111.4, 140.3, 17041);
     check_decimated_band(288000, 2, 5610.0, 5700.0, 23456);
     check_decimated_band(192000, 4, 222.7, 280.6, 9999);

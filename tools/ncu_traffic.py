@@ -18,6 +18,8 @@ UNIT = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
 def stage_of(name: str):
     if "edc_kernel" in name:
         return "edc"
+    if "fft_rows_untangle_reg" in name:
+        return "fft_rows_untangle"
     if "untangle_kernel" in name:
         return "untangle"
     if "band_fit_kernel" in name:
