@@ -358,6 +358,10 @@ __global__ void __launch_bounds__(P::kThreads) fft_rows_reg(const float2* __rest
 #define AA_ROWS_PLAIN_G 4   /* 96-thread CTAs, 12 per SM: 5.53 -> 5.11 ms per 8192 forward transforms against groups of 8 */
 #endif
 
+#ifndef AA_UNTANGLE_G
+#define AA_UNTANGLE_G 4     /* rows per group of the fused pass 2 + untangle kernel */
+#endif
+
 // forward real transform: pass 2 + untangle in one kernel (fft_reg.cuh).  Threads [0, kThreads) own group A,
 // [kThreads, 2 kThreads) the mirrored group B; CTA 0 of a transform handles the self-paired rows 0 and M1 / 2.
 template <class P, int M1>
@@ -371,6 +375,8 @@ __global__ void __launch_bounds__(2 * P::kThreads) fft_rows_untangle_reg(const f
     float2* bufA = smem;
     float2* bufB = smem + P::kBufElems;
     float2* tws = bufB + P::kBufElems;
+    float2* w2 = tws + P::L;
+    float2* a2 = w2 + P::L;
     const int unit = blockIdx.x / groups;
     const int c = blockIdx.x - unit * groups;
     const int half = (int)threadIdx.x / P::kThreads;
@@ -382,6 +388,9 @@ __global__ void __launch_bounds__(2 * P::kThreads) fft_rows_untangle_reg(const f
     u.M2 = P::L;
     u.twN = twN;
     u.advance = advance ? advance[unit] : 0;
+    u.w2 = w2;
+    u.a2 = a2;
+    static_assert((2 * P::kThreads) % P::G == 0, "a thread keeps its row slot across the untangle loop");
     const int rA0 = 1 + (c - 1) * P::G, rB0 = M1 - rA0 - P::G + 1;
     if (c == 0) {
         if (half == 0) reg_rows_stage_a_rows<P>(t, scratch_unit, RowsSelfPaired{M1 / 2}, bufA);
@@ -391,6 +400,7 @@ __global__ void __launch_bounds__(2 * P::kThreads) fft_rows_untangle_reg(const f
         reg_rows_stage_a_rows<P>(t, scratch_unit, RowsFrom{rB0}, bufB);
     }
     reg_fill_twiddles<P>((int)threadIdx.x, 2 * P::kThreads, tws, tw_full);
+    reg_untangle_fill_tables<P>((int)threadIdx.x, 2 * P::kThreads, w2, a2, u);
     __syncthreads();
     const bool active = t < P::kThreadsB && (c != 0 || half == 0);
     float2 v[P::RB];
@@ -407,12 +417,12 @@ bool launch_rows_untangle_reg(const C2CPlan* p, const float2* scratch, const Dst
 #define X(ra1, rb1, g1, ra2, rb2, g2)                                                                         \
     if (p->M1 == ra1 * rb1 && p->M2 == ra2 * rb2) {                                                           \
         constexpr int m1 = ra1 * rb1;                                                                         \
-        constexpr int gp = (m1 % AA_ROWS_PLAIN_G == 0) ? AA_ROWS_PLAIN_G : g2;                                \
+        constexpr int gp = (m1 % AA_UNTANGLE_G == 0) ? AA_UNTANGLE_G : g2;                                    \
         if constexpr (m1 % 2 == 0 && m1 / 2 >= gp) {                                                          \
             using PP = RegCfg<ra2, rb2, gp>;                                                                  \
             if (dry_run) return true;                                                                         \
             constexpr int groups = (m1 / 2 - 1 + gp - 1) / gp + 1;                                            \
-            constexpr size_t smem = sizeof(float2) * (size_t)(2 * PP::kBufElems + PP::L);                     \
+            constexpr size_t smem = sizeof(float2) * (size_t)(2 * PP::kBufElems + 3 * PP::L);                     \
             auto k = fft_rows_untangle_reg<PP, m1>;                                                           \
             static bool once = false;                                                                         \
             if (!once) {                                                                                      \

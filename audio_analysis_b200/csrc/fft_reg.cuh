@@ -336,40 +336,55 @@ struct UntangleOut {
     int M1, M2;             // M = M1 M2, N = 2 M
     TwoLevelTwiddle twN;    // exp(-2 pi i m / N)
     int advance;            // s: store X[k] exp(+2 pi i k s / N); 0 = plain
+    // per-CTA tables (shared memory), filled by reg_untangle_fill_tables: the twiddles of bin k = k2 M1 + k1 factor
+    // into a k2 part (these tables, read with consecutive k2: coalesced) and a k1 part (one value per thread);
+    // looking w^k up per element scatters 32 sectors per warp request over the twiddle tables
+    const float2* w2;       // [M2] exp(-2 pi i (k2 M1) / N)
+    const float2* a2;       // [M2] exp(-2 pi i ((k2 M1 s) mod N) / N)
 };
 
-AA_HD void untangle_store_pair(const UntangleOut& u, int k, int mk, float2 zk, float2 zm, unsigned rk) {
-    // rk = (k s) mod N; ((M - k) s) mod N = (M s mod N) - rk
+template <class P>
+AA_HD void reg_untangle_fill_tables(int t, int nthreads, float2* w2, float2* a2, const UntangleOut& u) {
     const unsigned N = 2u * (unsigned)u.M1 * (unsigned)u.M2;
-    const float2 w = twiddle2(u.twN, k);
+    const unsigned s = (unsigned)u.advance;
+    const unsigned a_step = (unsigned)(((unsigned long long)u.M1 * s) % N);   // (M1 s) mod N
+    for (int k2 = t; k2 < P::L; k2 += nthreads) {
+        w2[k2] = twiddle2(u.twN, (long long)k2 * u.M1);
+        a2[k2] = s ? twiddle2(u.twN, (long long)(((unsigned long long)k2 * a_step) % N)) : make_float2(1.f, 0.f);
+    }
+}
+
+// X[k], X[mk] from the pair (zk, zm); w = exp(-2 pi i k / N), adv = exp(-2 pi i ((k s) mod N) / N)
+AA_HD void untangle_store_pair(const UntangleOut& u, int k, int mk, float2 zk, float2 zm, float2 w, float2 adv) {
     float2 a = untangle_half_spectrum(zk, zm, w);
     float2 b = untangle_half_spectrum(zm, zk, make_float2(-w.x, w.y));
     if (u.advance != 0) {
-        const unsigned half_turn = (u.advance & 1) ? N / 2u : 0u;
-        const unsigned rm = (half_turn >= rk) ? half_turn - rk : half_turn + N - rk;
-        a = cmulc(a, twiddle2(u.twN, rk));
-        b = cmulc(b, twiddle2(u.twN, rm == N ? 0u : rm));
+        // exp(+2 pi i k s / N) = conj(adv);  exp(+2 pi i (M - k) s / N) = (-1)^s adv
+        a = cmulc(a, adv);
+        b = cmul(b, adv);
+        if (u.advance & 1) b = make_float2(-b.x, -b.y);
     }
     u.X[k] = a;
     u.X[mk] = b;
 }
 
-// general groups: element e = k2 G + g of group A (row k1 = rA0 + g) with its partner in group B, whose slot G - 1 - g
-// holds row M1 - k1
+// general groups: element (k2, g) of group A (row k1 = rA0 + g) with its partner in group B, whose slot G - 1 - g
+// holds row M1 - k1.  nthreads must be a multiple of G: a thread keeps its slot g, hence its row, in every iteration.
 template <class P>
 AA_HD void reg_untangle_general(int t, int nthreads, const float2* outA, const float2* outB, const UntangleOut& u, int rA0) {
     const unsigned N = 2u * (unsigned)u.M1 * (unsigned)u.M2;
     const unsigned s = (unsigned)u.advance;
-    const unsigned a_step = (unsigned)(((unsigned long long)u.M1 * s) % N);   // (M1 s) mod N
-    for (int e = t; e < P::G * P::L; e += nthreads) {
-        const int k2 = e / P::G, g = e - k2 * P::G;
-        const int k1 = rA0 + g;
-        if (2 * k1 >= u.M1) continue;                      // beyond the last mirrored pair
+    const int g = t % P::G;
+    const int k1 = rA0 + g;
+    if (2 * k1 >= u.M1) return;                            // beyond the last mirrored pair
+    const int dk2 = nthreads / P::G;
+    const float2 w1 = twiddle2(u.twN, k1);
+    const float2 b1 = s ? twiddle2(u.twN, (long long)(((unsigned long long)k1 * s) % N)) : make_float2(1.f, 0.f);
+    for (int k2 = t / P::G; k2 < P::L; k2 += dk2) {
         const int k = k2 * u.M1 + k1;
         const int mk = (u.M2 - 1 - k2) * u.M1 + (u.M1 - k1);
-        unsigned rk = 0;
-        if (s) rk = (unsigned)(((unsigned long long)k2 * a_step + ((unsigned long long)k1 * s) % N) % N);
-        untangle_store_pair(u, k, mk, outA[e], outB[(u.M2 - 1 - k2) * P::G + (P::G - 1 - g)], rk);
+        untangle_store_pair(u, k, mk, outA[k2 * P::G + g], outB[(u.M2 - 1 - k2) * P::G + (P::G - 1 - g)],
+                            cmul(u.w2[k2], w1), cmul(u.a2[k2], b1));
     }
 }
 
@@ -378,27 +393,23 @@ template <class P>
 AA_HD void reg_untangle_special(int t, int nthreads, const float2* out, const UntangleOut& u) {
     const unsigned N = 2u * (unsigned)u.M1 * (unsigned)u.M2;
     const unsigned s = (unsigned)u.advance;
-    const unsigned a_step = (unsigned)(((unsigned long long)u.M1 * s) % N);
     const int M = u.M1 * u.M2;
+    const int kh = u.M1 / 2;
+    const float2 w1h = twiddle2(u.twN, kh);
+    const float2 b1h = s ? twiddle2(u.twN, (long long)(((unsigned long long)kh * s) % N)) : make_float2(1.f, 0.f);
     for (int e = t; e < 2 * P::L; e += nthreads) {
         const int which = e / P::L, k2 = e - which * P::L;
         if (which == 0) {   // row 0: k = k2 M1 pairs with (M2 - k2) M1; k2 = 0 pairs bin 0 with bin M (both from Z[0])
             const int p2 = (k2 == 0) ? 0 : u.M2 - k2;
-            if (k2 > p2 && k2 != 0) continue;
             if (k2 != 0 && 2 * k2 > u.M2) continue;
             const int k = k2 * u.M1;
             const int mk = (k2 == 0) ? M : p2 * u.M1;
-            unsigned rk = 0;
-            if (s) rk = (unsigned)(((unsigned long long)k2 * a_step) % N);
-            untangle_store_pair(u, k, mk, out[k2 * P::G + 0], out[p2 * P::G + 0], rk);
+            untangle_store_pair(u, k, mk, out[k2 * P::G + 0], out[p2 * P::G + 0], u.w2[k2], u.a2[k2]);
         } else {            // row M1 / 2: k2 pairs with M2 - 1 - k2
             const int p2 = u.M2 - 1 - k2;
             if (k2 > p2) continue;
-            const int k1 = u.M1 / 2;
-            const int k = k2 * u.M1 + k1, mk = p2 * u.M1 + k1;
-            unsigned rk = 0;
-            if (s) rk = (unsigned)(((unsigned long long)k2 * a_step + ((unsigned long long)k1 * s) % N) % N);
-            untangle_store_pair(u, k, mk, out[k2 * P::G + 1], out[p2 * P::G + 1], rk);
+            const int k = k2 * u.M1 + kh, mk = p2 * u.M1 + kh;
+            untangle_store_pair(u, k, mk, out[k2 * P::G + 1], out[p2 * P::G + 1], cmul(u.w2[k2], w1h), cmul(u.a2[k2], b1h));
         }
     }
 }

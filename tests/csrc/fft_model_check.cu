@@ -399,6 +399,10 @@ static void emu_fused_forward(const HostC2C& p, const float* x, int N, float2* X
     u.M2 = M2;
     u.twN = dev_view(twN_h);
     u.advance = advance;
+    std::vector<float2> w2((size_t)M2), a2((size_t)M2);
+    u.w2 = w2.data();
+    u.a2 = a2.data();
+    for (int t = 0; t < nthreads; ++t) reg_untangle_fill_tables<P2>(t, nthreads, w2.data(), a2.data(), u);
     const int half_groups = (M1 / 2 - 1 + GP - 1) / GP, groups = half_groups + 1;
     for (int c = 0; c < groups; ++c) {
         const int rA0 = 1 + (c - 1) * GP, rB0 = M1 - rA0 - GP + 1;
