@@ -356,6 +356,89 @@ def test_metric_tables_gather_over_gloo_world_size_2():
     assert all(results) and all(p.exitcode == 0 for p in procs)
 
 
+def _bundle_shard_worker(rank, world, port, root, q):
+    import torch.distributed as dist
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    from audio_analysis_b200 import bundle, distributed as d
+    d.init_from_env("gloo")
+    seen = []
+    # the analysis itself needs a GPU; here only the sharding / index logic of run_bundle_report is under test
+    bundle.run_reports_batch = lambda wavs, bases, settings=None: seen.extend(p.stem for p in wavs) or []
+    index = bundle.run_bundle_report(root)
+    q.put((rank, seen, index.exists() if rank == 0 else None))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_bundle_taps_are_sharded_over_ranks_gloo_world_size_2(tmp_path):
+    """run_bundle_report under torch.distributed: contiguous blocks of taps per rank, every tap exactly once, the
+    index written by rank 0 after a barrier (the multi-GPU form of analyse/bundle.py:35-74)."""
+    import json
+    import torch.multiprocessing as mp
+    root = tmp_path / "run"
+    (root / "taps").mkdir(parents=True)
+    taps = [f"tap_{i:02d}" for i in range(7)]
+    (root / "meta.json").write_text(json.dumps({"sample_rate_hz": 48000, "length_samples": 10, "taps": taps}))
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 31000 + (os.getpid() % 2000)
+    procs = [ctx.Process(target=_bundle_shard_worker, args=(r, 2, port, str(root), q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    results = sorted(q.get(timeout=120) for _ in procs)
+    for p in procs:
+        p.join(timeout=60)
+    assert all(p.exitcode == 0 for p in procs)
+    assert results[0][1] == taps[:4] and results[1][1] == taps[4:] and results[0][2] is True
+    text = (root / "reports" / "bundle_report.md").read_text()
+    assert all(f"- [{t}](reports/{t}/{t}_report.md)" in text for t in taps)
+
+
+def _gatherer_worker(rank, world, port, q):
+    import torch
+    import torch.distributed as dist
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    from audio_analysis_b200 import distributed as d
+    d.init_from_env("gloo")
+    per = 5
+    base = rank * per
+    tables = {"band_rt60": (torch.arange(per * 26 * 3, dtype=torch.float64).view(per, 26, 3) + 1000.0 * rank),
+              "fits": torch.full((per, 3, 8), float(rank), dtype=torch.float64),
+              "early10": torch.arange(base, base + per, dtype=torch.float64) * 0.5,
+              "start": torch.arange(base, base + per, dtype=torch.int32)}
+    tables["band_rt60"][0, 0, 0] = float("nan")
+    g = d.TableGatherer(tables, per)
+    ok = g.record % 16 == 0 and g.record >= 26 * 3 * 8 + 3 * 8 * 8 + 8 + 4
+    for step in range(3):           # the same buffers every step
+        tables["early10"] += 1.0
+        got = g.gather(tables)
+        if rank == 0:
+            ok = ok and got["start"].tolist() == list(range(world * per))
+            ok = ok and torch.equal(got["early10"], torch.arange(world * per, dtype=torch.float64) * 0.5 + (step + 1))
+            ok = ok and bool(torch.isnan(got["band_rt60"][0, 0, 0])) and bool(torch.isnan(got["band_rt60"][per, 0, 0]))
+            ok = ok and float(got["band_rt60"][per, 1, 2]) == 1000.0 + 5.0 and float(got["fits"][per + 1, 2, 7]) == 1.0
+        else:
+            ok = ok and got is None
+    q.put(ok)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_packed_table_gatherer_reuses_its_buffers_gloo_world_size_2():
+    """distributed.TableGatherer: one packed record per row, one collective per step, buffers allocated once."""
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 33000 + (os.getpid() % 2000)
+    procs = [ctx.Process(target=_gatherer_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    results = [q.get(timeout=120) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+    assert all(results) and all(p.exitcode == 0 for p in procs)
+
+
 def test_synthetic_generator_is_deterministic_and_has_leading_silence():
     from audio_analysis_b200.synth import ir_parameters, synth_ir_numpy
     a, b = synth_ir_numpy(3, 48000), synth_ir_numpy(3, 48000)
