@@ -7,7 +7,7 @@
 // sample, a level crossing (decay.py:173-199) or fit points (decay.py:224-249) are read again at sample
 // resolution - about a tenth of the signal - instead of streaming it twice as the general kernel (edc.cu) does.
 //
-// One CTA of 4 warps per (row, band) unit (kFitThreads).  Semantics are those of edc.cu / edc_body.cuh: float32 squares and
+// One CTA of 2 warps per (row, band) unit (kFitThreads).  Semantics are those of edc.cu / edc_body.cuh: float32 squares and
 // in-tile sums, float64 carries, float32 dB curve and times, first sample <= target, fit mask on float32 times,
 // closed-form least squares in float64 (fit_math.cuh).
 #include "edc_body.cuh"
@@ -26,7 +26,7 @@ using edc::make_scan_masks;
 using edc::to_db;
 
 #ifndef AA_FIT_THREADS
-#define AA_FIT_THREADS 128
+#define AA_FIT_THREADS 64
 #endif
 constexpr int kFitThreads = AA_FIT_THREADS;
 constexpr int kFitWarps = kFitThreads / 32;
@@ -114,11 +114,12 @@ __device__ __forceinline__ void visit_tile_reverse(const float* __restrict__ y, 
 }
 
 template <int NS>
-// ten resident CTAs of four warps per SM (48 registers per thread, a few hundred bytes of spills): the kernel is a
+// sixteen resident CTAs of two warps per SM: the kernel is a
 // chain of short phases separated by barriers, and more, smaller CTAs in flight hide them - per 8192 rows x 26 bands
-// 8.05 ms (256 threads, 3 CTAs) -> 6.83 (256 x 5) -> 4.29 ms (128 x 10)
+// 8.05 ms (256 threads, 3 CTAs) -> 6.83 (256 x 5) -> 4.29 ms (128 x 10); with the certification phases of round 2:
+// 8.84 ms (256 x 4), 6.97 (128 x 10), 6.62 ms (64 x 16), 8.05 (32 x 32)
 #ifndef AA_FIT_MIN_BLOCKS
-#define AA_FIT_MIN_BLOCKS 10
+#define AA_FIT_MIN_BLOCKS 16
 #endif
 __global__ void __launch_bounds__(kFitThreads, AA_FIT_MIN_BLOCKS) band_fit_kernel(BandFitArgs a) {
     extern __shared__ __align__(16) unsigned char dyn_smem[];

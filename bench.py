@@ -372,8 +372,10 @@ def run_ours(args):
         ms = float(t.item()) / steps
         return {"value": round(ir_seconds_per_step / (ms / 1e3), 1), "unit": UNIT, "ms_per_step": round(ms, 3)}
 
-    variants = {"full_rate_bands": timed_variant(engine.bands_options(max_decimation=1)),
-                "uncertified_first_level": timed_variant(engine.bands_options(refine=False))}
+    variants = None
+    if not args.no_variants:
+        variants = {"full_rate_bands": timed_variant(engine.bands_options(max_decimation=1)),
+                    "uncertified_first_level": timed_variant(engine.bands_options(refine=False))}
 
     # ---- end to end through the public batch API: pinned host input -> chunked H2D overlapped with the kernels ->
     # tables and CSD slices D2H (run_hot_path_host)
@@ -702,6 +704,8 @@ def main():
                     help="IRs per GPU per step (default 8192: config 5 sharded over 8 GPUs)")
     ap.add_argument("--samples", type=int, default=N_SAMPLES)
     ap.add_argument("--no-cpu-baseline", dest="no_cpu_baseline", action="store_true")
+    ap.add_argument("--no-variants", dest="no_variants", action="store_true",
+                    help="skip the full-rate / uncertified comparison steps (used for ncu launch lists)")
     ap.add_argument("--no-other-configs", dest="no_other_configs", action="store_true",
                     help="skip the config-3 (bundle) and config-4 (deconvolve chain) lines")
     args = ap.parse_args()
