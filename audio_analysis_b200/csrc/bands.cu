@@ -600,6 +600,17 @@ int rt60bands_batch(const aa_bands_plan* plan, const float* d_x, long long row_s
         rc_rows = lo;
     }
     AA_REQUIRE(rc_rows >= 1, AA_ERR_WORKSPACE, "workspace too small for one row (see aa_bands_workspace_bytes)");
+    {   // the register-pass kernels index a chunk's transforms with 32 bits: units x M of every class stays below 2^31
+        long long widest = (long long)nb * M;   // one class at full rate
+        if (!one_class) {
+            widest = M;                          // the forward transform of the rows
+            for (const BandClass& bc : classes)
+                widest = std::max(widest, (long long)bc.bands.size() * (long long)(bc.sub ? bc.sub->M : M));
+        }
+        const long long cap = (2147483647LL - 1) / widest;
+        if (rc_rows > cap) rc_rows = cap;
+        AA_REQUIRE(rc_rows >= 1, AA_ERR_TOO_LONG, "row too long for one chunk");
+    }
     const Layout lay = make_layout(plan, rc_rows, nb, smoothing, fpp);
     if (stats) {
         stats->rows_per_chunk = (int)rc_rows;

@@ -284,7 +284,8 @@ class _BandsPlan:
 
 _bands_plans: Dict[Tuple[int, int], _BandsPlan] = {}
 _workspaces: Dict[int, torch.Tensor] = {}
-DEFAULT_WORKSPACE_BYTES = 12 << 30   # of 180 GB; 6 -> 12 GB is worth 1.2 % of the resident step, 48 GB another 0.2 %
+DEFAULT_WORKSPACE_BYTES = 40 << 30   # of 180 GB: the bench's 8192 rows in ONE chunk.  Every chunk pays the refinement levels'
+# small launches and stream synchronisations again: 12 GB (3 chunks) 55.3 ms per step, 24 GB 54.6, 40 GB 53.8
 
 
 def slice_rows(rows: Rows, r0: int, r1: int) -> Rows:
