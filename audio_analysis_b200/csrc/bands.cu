@@ -583,6 +583,7 @@ int rt60bands_batch(const aa_bands_plan* plan, const float* d_x, long long row_s
                 const C2CPlan* c2c = bc.sub ? bc.sub->c2c : plan->c2c;
                 int tile_c = 0, n_tiles = 0, n_groups = 0;
                 c2c_energy_layout(c2c, &tile_c, &n_tiles, &n_groups);
+                if (bc.D > 1 && band_fused_supported(bc.sub ? bc.sub->M : M)) continue;   // stays inside its CTAs
                 const size_t nbc = (li == 0) ? bc.bands.size() : 1;   // later levels run unit lists in batches that fit
                 fp.y_floats = std::max(fp.y_floats, nbc * (size_t)(bc.sub ? bc.sub->y_stride : plan->y_stride));
                 fp.scratch_c = std::max(fp.scratch_c, nbc * (size_t)(bc.sub ? bc.sub->M : M));
@@ -605,7 +606,8 @@ int rt60bands_batch(const aa_bands_plan* plan, const float* d_x, long long row_s
         if (!one_class) {
             widest = M;                          // the forward transform of the rows
             for (const BandClass& bc : classes)
-                widest = std::max(widest, (long long)bc.bands.size() * (long long)(bc.sub ? bc.sub->M : M));
+                if (!(bc.D > 1 && band_fused_supported(bc.sub ? bc.sub->M : M)))
+                    widest = std::max(widest, (long long)bc.bands.size() * (long long)(bc.sub ? bc.sub->M : M));
         }
         const long long cap = (2147483647LL - 1) / widest;
         if (rc_rows > cap) rc_rows = cap;
@@ -740,6 +742,17 @@ int rt60bands_batch(const aa_bands_plan* plan, const float* d_x, long long row_s
                         const long long by_s = (long long)((size_t)rows * fp.scratch_c / (size_t)M_c);
                         const long long by_p = (long long)((size_t)rows * fp.part_floats / ((size_t)n_tiles * (size_t)n_groups));
                         batch = std::max(1LL, std::min(by_y, std::min(by_s, by_p)));
+                    }
+                    // classes whose transform fits one CTA's shared memory: spectrum -> band signal -> fits in ONE
+                    // kernel (bandfused.cu); nothing of the unit goes through the signal / scratch / partial buffers
+                    if (D > 1 && band_fused_supported(M_c)) {
+                        ProfScope prof("band_fused", stream);
+                        rc = launch_band_fused(M_c, d_X, plan->x_stride, d_class_bands, freq_scale, bc.sub->twN.dev,
+                                               1.0f / ((float)M_c * (float)D), todo, &pk, d_start_idx + r0, nbc, nb,
+                                               (li == 0) ? nullptr : d_lists + list_off[list_id], &cert, 8,
+                                               d_metrics_out + r0 * nb * AA_MAX_FITS, stream, D, N);
+                        if (rc != AA_OK) return rc;
+                        continue;
                     }
                     for (long long u0 = 0; u0 < todo; u0 += batch) {
                         const long long units_c = std::min(batch, todo - u0);

@@ -81,6 +81,15 @@ int launch_band_fit(const float* d_y, long long y_stride, const float* d_part, l
                     int min_samples, double* d_rt60_out, cudaStream_t stream, int decim = 1, int full_n = 0,
                     int aligned = 0);
 
+// bandfused.cu: the same per-unit analysis with the band signal synthesised into shared memory by the CTA that
+// fits it (classes whose transform of M complex points fits one CTA).  d_X: time-advanced half spectra of the rows,
+// d_bands: the class's bands, twN: exp(-2 pi i k / 2M), scale: 1 / (M D)
+bool band_fused_supported(int M);
+int launch_band_fused(int M, const float2* d_X, long long x_stride, const struct BandDev* d_bands, double freq_scale,
+                      struct TwoLevelTwiddle twN, float scale, long long n_units, const aa_decay_params* p,
+                      const int* d_start_idx, int nbc, int out_nb, const int* d_unit_map, const BandFitCert* cert,
+                      int min_samples, double* d_rt60_out, cudaStream_t stream, int decim, int full_n);
+
 }  // namespace aa
 
 namespace aa {

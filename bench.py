@@ -265,7 +265,7 @@ def run_ours(args):
     gather_ms = (sum(a.elapsed_time(b) for a, b in gather_events) / len(gather_events)) if gather_events else None
     lib.aa_profile_collect()
     stage_names = ["edc", "fft_cols", "fft_rows", "untangle", "fft_rows_untangle", "fft_cols_band", "fft_rows_band",
-                   "band_fit", "band_edc", "csd"]
+                   "band_fit", "band_fused", "band_edc", "csd"]
     stage_ms = {k: lib.aa_profile_ms(k.encode()) / args.steps for k in stage_names}
     stage_scopes = {k: int(lib.aa_profile_scopes(k.encode())) // args.steps for k in stage_names}
     # band stage per decimation class (nested scopes around the class's kernels)
@@ -292,6 +292,12 @@ def run_ours(args):
     dec = rt60bands.decimation_classes(out.bands, n, SR, bs.transition_width_octaves, settings=bs)
     band_samples = float(sum(n // d for d in dec))          # per row, all bands
     band_units_total = rows_n * band_samples                # replaces units * n below
+    # classes whose transform fits one CTA (csrc/bandfused.cu: M = n / 2D in its plan list) never leave shared memory
+    fused_lengths = {9000, 12000, 6000, 8000}
+    fused_samples = float(sum(n // d for d in dec if d > 1 and n % (2 * d) == 0 and n // (2 * d) in fused_lengths))
+    if os.environ.get("AA_NO_FUSED_BANDS"):
+        fused_samples = 0.0
+    band_units_total -= rows_n * fused_samples              # the three-kernel path handles the rest
     stage_bytes = {
         # read x + write edc_db (8 B/sample)
         "edc": (8.0 * rows_n * n, "hbm", "edc_kernel<true>: fused EDC + crossings + fits (aa_decay_batch)"),
@@ -310,6 +316,10 @@ def run_ours(args):
                           "fft_rows_reg<energy>: second pass of the masked inverse FFT + tile energies"),
         "band_fit": (4.0 * band_units_total / 16.0, "latency (reads the partials and ~10% of the band signal)",
                      "band_fit_kernel: band EDC suffix scan + crossings + fits"),
+        # one CTA per unit: masked spectrum -> in-shared-memory inverse -> Schroeder sum -> fits; HBM sees at most the
+        # band's zone of the row spectrum (8 B per complex bin = 4 B per synthesised sample) and three results
+        "band_fused": (4.0 * rows_n * fused_samples, "fp32 issue / shared memory (the band signal never leaves the SM)",
+                       "band_fused_kernel: deep-decimation classes, synthesis + EDC + fits in one CTA"),
         "band_edc": (4.0 * units * n, "hbm", "edc_kernel<false> on band signals (generic lengths)"),
         "csd": (rows_n * (18 * 4096 * 4.0 + 18 * n_bins * 4.0), "hbm",
                 "csd_tma_kernel: TMA-staged frames, FFT, dB, on-chip normalisation"),
@@ -350,7 +360,7 @@ def run_ours(args):
                         "of algorithmic traffic (SURVEY 8d) and is bound by fp32 issue, not HBM (SURVEY D7): see "
                         "roofline_by_kernel"}
     ms_bands = sum(stage_ms[k] for k in ("fft_cols", "fft_rows", "untangle", "fft_rows_untangle", "fft_cols_band",
-                                          "fft_rows_band", "band_fit", "band_edc"))
+                                          "fft_rows_band", "band_fit", "band_fused", "band_edc"))
     by_kernel["rt60bands_stage"] = {**roof(4.0 * rows_n * n, ms_bands), "bound": "fp32 issue / intermediate traffic",
                                     "kernel": "whole band stage against SURVEY 8d's 4 B/sample (read x once)",
                                     "share_of_step": round(ms_bands / ms_step, 4)}

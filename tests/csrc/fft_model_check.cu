@@ -14,6 +14,7 @@
 
 #include "../../audio_analysis_b200/csrc/fft_access.cuh"
 #include "../../audio_analysis_b200/csrc/fft_plan_host.hpp"
+#include "../../audio_analysis_b200/csrc/fft_fused.cuh"
 #include "../../audio_analysis_b200/csrc/fft_reg.cuh"
 
 using namespace aa;
@@ -650,6 +651,30 @@ static void check_real_band(int N, double lo0 = 890.9, double hi0 = 1122.5) {
     }
 }
 
+// serial emulation of band_fused_kernel's transform (bandfused.cu, fft_fused.cuh): every thread of the CTA, stage by stage
+template <class P>
+static void emu_fused_unit(const RegSrcBand& src, int conj, float scale, float2* data) {
+    std::vector<float2> tw2((size_t)P::kTw2), tw3((size_t)P::kTw3);
+    for (int k = 0; k < P::kTw2; ++k) tw2[(size_t)k] = make_float2((float)cos(2.0 * M_PI * k / P::L2), (float)-sin(2.0 * M_PI * k / P::L2));
+    for (int k = 0; k < P::kTw3; ++k) tw3[(size_t)k] = make_float2((float)cos(2.0 * M_PI * k / P::M), (float)-sin(2.0 * M_PI * k / P::M));
+    for (int t = 0; t < P::kThreads; ++t) fused_clear<P>(t, data);
+    for (int t = 0; t < P::kThreads; ++t) fused_scatter<P>(t, src, data);
+    for (int t = 0; t < P::kThreads; ++t) fused_stage1<P>(t, data);
+    for (int t = 0; t < P::kThreads; ++t) fused_stage2<P>(t, data, tw2.data());
+    for (int t = 0; t < P::kThreads; ++t) fused_stage3<P>(t, data, tw3.data(), conj, scale);
+}
+
+static bool emu_fused(int M, const RegSrcBand& src, int conj, float scale, float2* data) {
+#define X(r1, r2, r3, th, mb)                                              \
+    if (M == (r1) * (r2) * (r3)) {                                         \
+        emu_fused_unit<FusedPlan<r1, r2, r3, th>>(src, conj, scale, data); \
+        return true;                                                       \
+    }
+    AA_FUSED_LIST(X)
+#undef X
+    return false;
+}
+
 // ---- 2b. decimated band synthesis (bands.cu): length N / D inverse of the time-advanced masked spectrum must
 // return y[(shift + D j) mod N], every D-th sample of the full-rate band signal from the analysis start
 static void check_decimated_band(int N, int D, double lo0, double hi0, int shift) {
@@ -724,7 +749,20 @@ static void check_decimated_band(int N, int D, double lo0, double hi0, int shift
     s.twShift = dev_view(twNfull);
     DstDesc d = dst_complex((float2*)y.data(), Md, Md, 1, 1.0f / ((float)Md * (float)D));
     emu_exec(ep, s, d, 1);
-    double worst = 0;
+    // the same unit through the in-shared-memory transform of band_fused_kernel, where a plan for this length exists
+    std::vector<float> yf((size_t)Nd, 0.f);
+    RegSrcBand rs;
+    rs.X = X.data();
+    rs.b = band;
+    rs.freq_scale = freq_scale;
+    rs.M = Md;
+    rs.twN = dev_view(twNd);
+    rs.shift = shift;
+    rs.shift_N = N;
+    rs.shift_rcp = 1.0 / (double)N;
+    rs.twShift = dev_view(twNfull);
+    const bool fused = emu_fused(Md, rs, 1, 1.0f / ((float)Md * (float)D), (float2*)yf.data());
+    double worst = 0, worst_f = 0;
     for (int c = 0; c < 60; ++c) {
         const int j = (int)((urand() * 0.5 + 0.5) * (Nd - 1));
         const long long n = ((long long)shift + (long long)D * j) % N;
@@ -735,10 +773,23 @@ static void check_decimated_band(int N, int D, double lo0, double hi0, int shift
         }
         acc /= N;
         worst = fmax(worst, fabs(acc - (double)y[(size_t)j]) / (ynorm / sqrt((double)N) + 1e-30));
+        worst_f = fmax(worst_f, fabs(acc - (double)yf[(size_t)j]) / (ynorm / sqrt((double)N) + 1e-30));
     }
     char name[64];
     snprintf(name, sizeof(name), "decimated band D=%d zone=%d shift=%d (%d bins)", D, band.z_neg ? band.z_off / Md - 1 : band.z_off / Md, shift, (int)ks.size());
     report(name, N, worst, 2e-4);
+    if (fused) {
+        // and sample by sample against the two-pass result (same source arithmetic, different butterfly order)
+        double diff = 0, ymax = 0;
+        for (int j = 0; j < Nd; ++j) {
+            diff = fmax(diff, fabs((double)yf[(size_t)j] - (double)y[(size_t)j]));
+            ymax = fmax(ymax, fabs((double)y[(size_t)j]));
+        }
+        snprintf(name, sizeof(name), "  fused in-CTA transform M=%d vs direct sums", Md);
+        report(name, N, worst_f, 2e-4);
+        snprintf(name, sizeof(name), "  fused vs two-pass, all %d samples (of peak)", Nd);
+        report(name, N, diff / (ymax + 1e-30), 2e-5);
+    }
 }
 
 // the compile-time chains of fft.cu's AA_SPEC_LIST and csd.cu (radix 6, padded shared-memory layout)

@@ -459,6 +459,43 @@ def test_band_certification_at_scale(n):
     torch.cuda.empty_cache()
 
 
+@pytest.mark.parametrize("n", [288000, 192000])
+def test_fused_band_kernel_against_the_three_kernel_path(n, monkeypatch):
+    """band_fused_kernel (csrc/bandfused.cu: masked spectrum -> in-shared-memory inverse -> Schroeder sum -> fits in one
+    CTA, for the classes with n / 2D <= 12,000) against the columns / rows / band_fit kernels it replaces
+    (AA_NO_FUSED_BANDS): the same decimated estimator, so the uncertified first level agrees to rounding, and the
+    certified default path stays inside the tolerance against the full-rate path (rt60bands.py:272-321)."""
+    from audio_analysis_b200 import engine, rt60bands as rb
+    from audio_analysis_b200.synth import synth_batch_torch
+    rows_n = 256
+    rows = engine.make_rows(synth_batch_torch(rows_n, n, SR, device="cuda", first_index=31000))
+    s = rb.Rt60BandsAnalysisSettings(band_mode="third")
+    raw_opt = engine.bands_options(refine=False)
+    monkeypatch.delenv("AA_NO_FUSED_BANDS", raising=False)
+    raw_f = rb.run_rt60_bands(rows, SR, s, options=raw_opt)[0].cpu().numpy()[:, :, 0]
+    got_f = rb.run_rt60_bands(rows, SR, s)[0].cpu().numpy()[:, :, 0]
+    stats_f = dict(engine.last_bands_stats)
+    monkeypatch.setenv("AA_NO_FUSED_BANDS", "1")
+    raw_3 = rb.run_rt60_bands(rows, SR, s, options=raw_opt)[0].cpu().numpy()[:, :, 0]
+    got_3 = rb.run_rt60_bands(rows, SR, s)[0].cpu().numpy()[:, :, 0]
+    stats_3 = dict(engine.last_bands_stats)
+    monkeypatch.delenv("AA_NO_FUSED_BANDS", raising=False)
+    assert np.array_equal(np.isnan(raw_f), np.isnan(raw_3))
+    rel = np.abs(raw_f - raw_3) / np.abs(raw_3)
+    note(f"band_fused_vs_three_kernel_first_level_rel[n{n}]", np.nanmax(rel))
+    # same grid, same estimator; the transforms round differently (1e-6 of the signal) and the tiles are 128 samples
+    # instead of 2 M1, so a crossing can move by one decimated sample on a flat stretch of the curve
+    assert np.nanmedian(rel) <= 2e-6 and np.nanmax(rel) <= 2e-3, (float(np.nanmedian(rel)), float(np.nanmax(rel)))
+    assert np.nanmean(rel > 1e-4) <= 2e-3
+    # certified default: both paths inside the tolerance against the full-rate estimator, nearly the same units redone
+    ref = rb.run_rt60_bands(rows, SR, s, options=engine.bands_options(max_decimation=1))[0].cpu().numpy()[:, :, 0]
+    for got in (got_f, got_3):
+        rel, outside, nan_mismatch = _band_tail(got, ref)
+        assert outside == 0 and nan_mismatch == 0 and np.nanmax(rel) <= 3.5e-3
+    assert stats_f["limits"] == stats_3["limits"] and stats_f["units"][0] == stats_3["units"][0]
+    assert abs(sum(stats_f["units"][1:]) - sum(stats_3["units"][1:])) <= 0.02 * sum(stats_3["units"][1:]) + 8
+
+
 def test_band_certification_with_t20_and_edt():
     """Calls that also ask for T20 / EDT start at D <= 4 and certify every fit (shorter fits need more points)."""
     from audio_analysis_b200 import engine, rt60bands as rb
