@@ -53,6 +53,7 @@ int fill_band_fit_args(bandfit::BandFitArgs* out, int n, const aa_decay_params* 
     AA_REQUIRE(p->n_fits >= 0 && p->n_fits <= AA_MAX_FITS, AA_ERR_INVALID_ARGUMENT, "n_fits out of range");
     int rc = edc::fill_edc_args(p, &a.e);
     if (rc != AA_OK) return rc;
+    for (int tg = 0; tg < bandfit::kMaxTargets; ++tg) a.gain10[tg] = (tg < 2 + 2 * p->n_fits) ? exp10(-0.1 * a.e.target[tg]) : 0.0;
     a.n = n;
     AA_REQUIRE(nbc >= 1 && nbc <= AA_MAX_BANDS && out_nb >= 1, AA_ERR_INVALID_ARGUMENT, "band counts out of range");
     a.e.start_in = d_start_idx;

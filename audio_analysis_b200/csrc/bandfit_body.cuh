@@ -51,6 +51,7 @@ struct BandFitArgs {
     int nbc, out_nb;
     // certification of a decimated unit (launch_band_fit's BandFitCert): see certify_unit below
     BandFitCert cert;
+    double gain10[kMaxTargets];   // 10^(-target / 10) per dB target (certification: one far-end cell in dB at that level)
     EdcArgs e;                // start_in / rt60_out / targets / fit ranges / eps / floor / sr / min_samples
 };
 
@@ -155,10 +156,17 @@ __device__ __forceinline__ void band_fit_unit(const BandFitArgs& a, int row, int
             float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
             const int cnt = min(TL, n - k * TL);   // analysed samples of the tile (<= 0: none)
             const float4* __restrict__ p = reinterpret_cast<const float4*>(y + (long long)k * TL);
-#pragma unroll 4
-            for (int j = 0; j < kSub / 4; ++j) {
-                const int q = (j + k) & (kSub / 4 - 1);
-                if (4 * q < cnt) {
+            if (cnt == kSub) {
+#pragma unroll 8
+                for (int j = 0; j < kSub / 4; ++j) {
+                    const float4 v = p[(j + k) & (kSub / 4 - 1)];
+                    s0 = fmaf(v.x, v.x, s0);
+                    s1 = fmaf(v.y, v.y, s1);
+                    s2 = fmaf(v.z, v.z, s2);
+                    s3 = fmaf(v.w, v.w, s3);
+                }
+            } else {
+                for (int q = 0; 4 * q < cnt; ++q) {
                     const float4 v = p[q];
                     s0 = fmaf(v.x, v.x, s0);
                     if (4 * q + 1 < cnt) s1 = fmaf(v.y, v.y, s1);
@@ -331,8 +339,9 @@ __device__ __forceinline__ void band_fit_unit(const BandFitArgs& a, int row, int
         }
     }
     __syncthreads();
-    if (threadIdx.x < p.n_fits) {
-        const int f = threadIdx.x;
+    // ---- fit index ranges, by the last warp (the certification targets after it keep the other warps busy meanwhile)
+    if (warp == kW - 1 && lane < p.n_fits) {
+        const int f = lane;
         const int ts_i = 2 + 2 * f, te_i = 3 + 2 * f;
         int first = 0, last = -1, valid;
         float wa = 1.0f, wb = 1.0f;
@@ -373,13 +382,12 @@ __device__ __forceinline__ void band_fit_unit(const BandFitArgs& a, int row, int
         sh.fit_ts[f] = sh.cross_t[ts_i];
         sh.fit_te[f] = sh.cross_t[te_i];
     }
-    __syncthreads();
-
     // ---- certification of a decimated unit, part 1.  The sub-sampled Schroeder sum differs from the reference's by
     // at most delta dB near a fit end point: the 2 f ripple of y^2 folds to another frequency on the decimated grid
     // (the host's per-band error model times a safety factor, scaled by the unit's own decay rate), and the far end of
     // the grid is known to about one cell of energy.  The reference's crossing then lies between the first decimated
     // samples <= target + delta and <= target - delta: resolve those four extra targets per fit.
+    // (Runs beside the fit-range computation: it needs the crossings only.)
     if (a.cert.on) {
         const float m_b = a.cert.m[cj];
         const float yl = fit_ld1<kSmem>(y + (n - 1));
@@ -389,10 +397,10 @@ __device__ __forceinline__ void band_fit_unit(const BandFitArgs& a, int row, int
             const int ts_i = 2 + 2 * f, te_i = 3 + 2 * f;
             int cidx = -1;
             const int span = sh.cross_idx[te_i] - sh.cross_idx[ts_i];
-            if (sh.fit_valid[f] && span > 0) {
+            if (sh.cross_ok[ts_i] && sh.cross_ok[te_i] && span > 0) {   // (an invalid fit is flagged whatever these find)
                 const double tau0 = p.target[e ? te_i : ts_i];
                 const double delta = (double)m_b * (p.target[ts_i] - p.target[te_i]) / (double)span +
-                                     4.342944819 * end_cell * exp10(-0.1 * tau0);
+                                     4.342944819 * end_cell * a.gain10[e ? te_i : ts_i];   // 10^(-tau0 / 10), from the host
                 const double tau = tau0 + (minus ? -delta : delta);
                 int found, idx;
                 float y0, y1;
@@ -402,6 +410,7 @@ __device__ __forceinline__ void band_fit_unit(const BandFitArgs& a, int row, int
             if (lane == 0) sh.cert_idx[ct] = cidx;
         }
     }
+    __syncthreads();
 
     // ---- regression sums over the fit ranges (decay.py:224-249)
     double acc[AA_MAX_FITS * 3];

@@ -33,8 +33,7 @@ struct FusedArgs {
     const BandDev* bands;  // the class's bands (zone placement, mask tables)
     double freq_scale;
     TwoLevelTwiddle twN;   // exp(-2 pi i k / n_c), n_c = 2 M
-    const float2* tw2;     // exp(-2 pi i k1 / L2), k1 < R1
-    const float2* tw3;     // exp(-2 pi i k' / M),  k' < L2
+    const float2* tw;      // stage twiddles (FusedPlan::tw_offset)
     float scale;
 };
 
@@ -56,45 +55,55 @@ __global__ void __launch_bounds__(P::kThreads, kMinBlocks) band_fused_kernel(Fus
     s.freq_scale = f.freq_scale;
     s.M = P::M;
     s.twN = f.twN;
+    const FusedSupport sup = fused_support<P>(s);
+    FusedPrefetch pre;
+    fused_scatter_load<P>(t, s, sup, &pre);   // in flight while the buffer is cleared
     fused_clear<P>(t, data);
     __syncthreads();
-    fused_scatter<P>(t, s, data);
+    fused_scatter<P>(t, s, sup, pre, data);
     __syncthreads();
     fused_stage1<P>(t, data);
     __syncthreads();
-    fused_stage2<P>(t, data, f.tw2);
+    fused_stage<P, 2>(t, data, f.tw, 1, f.scale);
     __syncthreads();
-    fused_stage3<P>(t, data, f.tw3, 1, f.scale);
-    __syncthreads();
+    if constexpr (P::kStages >= 3) {
+        fused_stage<P, 3>(t, data, f.tw, 1, f.scale);
+        __syncthreads();
+    }
+    if constexpr (P::kStages >= 4) {
+        fused_stage<P, 4>(t, data, f.tw, 1, f.scale);
+        __syncthreads();
+    }
     band_fit_unit<1, P::kThreads, true>(a, row, cj, reinterpret_cast<const float*>(data), nullptr,
                                         dyn_smem + sizeof(float2) * (size_t)P::M, sh);
 }
 
 struct FusedTables {
-    int M = 0, device = -1;
-    float2* d = nullptr;   // tw2 (R1 entries) followed by tw3 (L2 entries)
+    int M = 0, device = -1, total = 0;
+    float2* d = nullptr;   // per stage j >= 2: exp(-2 pi i k' / L_j), k' < L_{j-1}
 };
 std::mutex g_tables_mu;
 FusedTables g_tables[16];
 
-int fused_tables(int M, int R1, int L2, const float2** tw2, const float2** tw3) {
+template <class P>
+int fused_tables(const float2** tw) {
     int device = 0;
     AA_CUDA_TRY(cudaGetDevice(&device));
     std::lock_guard<std::mutex> lock(g_tables_mu);
     FusedTables* slot = nullptr;
     for (FusedTables& ft : g_tables) {
-        if (ft.d && ft.M == M && ft.device == device) {
-            *tw2 = ft.d;
-            *tw3 = ft.d + R1;
+        if (ft.d && ft.M == P::M && ft.device == device && ft.total == P::kTwTotal) {
+            *tw = ft.d;
             return AA_OK;
         }
         if (!ft.d && !slot) slot = &ft;
     }
     AA_REQUIRE(slot != nullptr, AA_ERR_UNSUPPORTED, "too many fused band plans");
-    std::vector<float2> h((size_t)(R1 + L2));
+    std::vector<float2> h((size_t)P::kTwTotal);
     const double two_pi = 6.283185307179586476925286766559;
-    for (int k = 0; k < R1; ++k) h[(size_t)k] = make_float2((float)cos(two_pi * k / L2), (float)-sin(two_pi * k / L2));
-    for (int k = 0; k < L2; ++k) h[(size_t)(R1 + k)] = make_float2((float)cos(two_pi * k / M), (float)-sin(two_pi * k / M));
+    for (int j = 2; j <= P::kStages; ++j)
+        for (int k = 0; k < P::len(j - 1); ++k)
+            h[(size_t)(P::tw_offset(j) + k)] = make_float2((float)cos(two_pi * k / P::len(j)), (float)-sin(two_pi * k / P::len(j)));
     float2* d = nullptr;
     AA_CUDA_TRY(cudaMalloc(reinterpret_cast<void**>(&d), sizeof(float2) * h.size()));
     // synchronous copy from pageable memory: done once per length and device, before the first launch reads it
@@ -104,20 +113,21 @@ int fused_tables(int M, int R1, int L2, const float2** tw2, const float2** tw3) 
         set_error("upload of the fused band tables failed");
         return AA_ERR_CUDA;
     }
-    slot->M = M;
+    slot->M = P::M;
     slot->device = device;
+    slot->total = P::kTwTotal;
     slot->d = d;
-    *tw2 = d;
-    *tw3 = d + R1;
+    *tw = d;
     return AA_OK;
 }
 
 template <class P, int kMinBlocks>
 int launch_fused(FusedArgs f, const BandFitArgs& a, long long n_units, cudaStream_t stream) {
-    int rc = fused_tables(P::M, P::R1, P::L2, &f.tw2, &f.tw3);
+    int rc = fused_tables<P>(&f.tw);
     if (rc != AA_OK) return rc;
     auto kern = band_fused_kernel<P, kMinBlocks>;
-    constexpr size_t smem = fused_smem(P::M);
+    size_t smem = fused_smem(P::M);
+    if (const char* env = getenv("AA_FUSED_PAD_SMEM")) smem += (size_t)atoi(env);   // tuning: fewer resident CTAs per SM
     AA_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     kern<<<(unsigned)n_units, P::kThreads, smem, stream>>>(f, a);
     return launch_check("band_fused_kernel");
@@ -127,8 +137,8 @@ int launch_fused(FusedArgs f, const BandFitArgs& a, long long n_units, cudaStrea
 
 bool band_fused_supported(int M) {
     if (getenv("AA_NO_FUSED_BANDS") != nullptr) return false;   // A/B switch: the three-kernel path
-#define X(r1, r2, r3, th, mb) \
-    if (M == (r1) * (r2) * (r3)) return true;
+#define X(m, th, mb, ...) \
+    if (M == (m)) return true;
     AA_FUSED_LIST(X)
 #undef X
     return false;
@@ -158,8 +168,9 @@ int launch_band_fused(int M, const float2* d_X, long long x_stride, const BandDe
     f.freq_scale = freq_scale;
     f.twN = twN;
     f.scale = scale;
-#define X(r1, r2, r3, th, mb) \
-    if (M == (r1) * (r2) * (r3)) return launch_fused<FusedPlan<r1, r2, r3, th>, mb>(f, a, n_units, stream);
+#define X(m, th, mb, ...)                                                         \
+    static_assert(FusedPlan<th, __VA_ARGS__>::M == (m), "radices do not multiply to M"); \
+    if (M == (m)) return launch_fused<FusedPlan<th, __VA_ARGS__>, mb>(f, a, n_units, stream);
     AA_FUSED_LIST(X)
 #undef X
     set_error("no fused band plan for M = %d", M);

@@ -3,7 +3,7 @@
 // The deep decimation classes of the rt60bands filterbank (rt60bands.py:170-175 on a grid of every D-th sample,
 // bands.cu) need complex transforms of M = 4,000 ... 12,000 points per (row, band) unit: 32 ... 96 KB, which one CTA
 // keeps in shared memory from the masked spectrum to the decay fits.  The transform is a decimation-in-time chain
-// of three in-place stages with register-resident butterflies (fft_radix.cuh), M = R1 R2 R3:
+// of three (or four) in-place stages with register-resident butterflies (fft_radix.cuh); for M = R1 R2 R3:
 //
 //   input index  n = d3 + R3 (d2 + R2 d1)          output index  k = k1 + R1 (k2 + R2 k3)
 //   source:  the masked, packed, conjugated half spectrum (RegSrcBand) is scattered to address (d3 R2 + d2) R1 + d1 -
@@ -27,22 +27,73 @@
 
 namespace aa {
 
-template <int R1_, int R2_, int R3_, int kThreads_>
+namespace fused_detail {
+template <int... Rs>
+struct Radices {
+    static constexpr int kN = (int)sizeof...(Rs);
+    AA_HD static constexpr int get(int j) {   // radix of stage j = 1 .. kN
+        constexpr int r[] = {Rs...};
+        return r[j - 1];
+    }
+    AA_HD static constexpr int len(int j) {   // L_j = R_1 ... R_j, L_0 = 1
+        constexpr int r[] = {Rs...};
+        int l = 1;
+        for (int q = 0; q < j; ++q) l *= r[q];
+        return l;
+    }
+};
+}  // namespace fused_detail
+
+// FusedPlan<threads, R1, R2, ..., Rs>: s = 3 or 4 stages
+template <int kThreads_, int... Rs>
 struct FusedPlan {
-    static constexpr int R1 = R1_, R2 = R2_, R3 = R3_;
-    static constexpr int L2 = R1_ * R2_, M = R1_ * R2_ * R3_;
+    using Rad = fused_detail::Radices<Rs...>;
+    static constexpr int kStages = Rad::kN;
+    static constexpr int M = Rad::len(kStages);
+    static constexpr int R1 = Rad::get(1);
     static constexpr int kThreads = kThreads_;
-    static constexpr int kTw2 = R1_;        // entries of the stage-2 table  w_L2^{k1}
-    static constexpr int kTw3 = R1_ * R2_;  // entries of the stage-3 table  w_M^{k'}
+    AA_HD static constexpr int radix(int j) { return Rad::get(j); }
+    AA_HD static constexpr int len(int j) { return Rad::len(j); }
+    // stage j >= 2 reads tw[tw_offset(j) + k'] = exp(-2 pi i k' / L_j), k' < L_{j-1}
+    AA_HD static constexpr int tw_offset(int j) {
+        int o = 0;
+        for (int q = 2; q < j; ++q) o += Rad::len(q - 1);
+        return o;
+    }
+    static constexpr int kTwTotal = tw_offset(kStages + 1);
+    static_assert(kStages >= 2 && kStages <= 4, "two to four stages");
 };
 
-// (R1, R2, R3, threads, resident CTAs per SM) per supported length; R1 is odd so that stage 1's stores of R1
-// consecutive values per thread do not collide on banks
-#define AA_FUSED_LIST(X)                                                       \
-    X(25, 18, 20, 256, 3) /* M =  9000: N = 288000 decimated by 16; 73.7 KB */ \
-    X(25, 24, 20, 256, 2) /* M = 12000: 288000 / 12, 192000 / 8;    97.7 KB */ \
-    X(15, 20, 20, 256, 4) /* M =  6000: 192000 / 16;                49.1 KB */ \
-    X(25, 16, 20, 256, 3) /* M =  8000: 192000 / 12;                65.5 KB */
+// (M, threads, resident CTAs per SM, R1, R2, ...) per supported length.  R1 is odd so that stage 1's accesses (R1
+// consecutive values per thread) do not collide on banks.
+#ifndef AA_FUSED_VARIANT
+#define AA_FUSED_VARIANT 0
+#endif
+#if AA_FUSED_VARIANT == 1
+#define AA_FUSED_LIST(X)                       \
+    X(9000, 384, 3, 9, 10, 10, 10)             \
+    X(12000, 384, 2, 25, 24, 20)               \
+    X(6000, 256, 4, 15, 20, 20)                \
+    X(8000, 256, 3, 25, 16, 20)
+#elif AA_FUSED_VARIANT == 2
+#define AA_FUSED_LIST(X)                       \
+    X(9000, 512, 3, 9, 10, 10, 10)             \
+    X(12000, 512, 2, 15, 10, 8, 10)            \
+    X(6000, 256, 4, 15, 20, 20)                \
+    X(8000, 256, 3, 25, 16, 20)
+#elif AA_FUSED_VARIANT == 3
+#define AA_FUSED_LIST(X)                       \
+    X(9000, 384, 3, 15, 15, 8, 5)              \
+    X(12000, 384, 2, 15, 10, 8, 10)            \
+    X(6000, 256, 4, 15, 20, 20)                \
+    X(8000, 256, 3, 25, 16, 20)
+#else
+#define AA_FUSED_LIST(X)                                                                  \
+    X(9000, 256, 3, 25, 18, 20)  /* N = 288000 decimated by 16;           73.7 KB */      \
+    X(12000, 384, 2, 25, 24, 20) /* 288000 / 12, 192000 / 8;              97.7 KB */      \
+    X(6000, 256, 4, 15, 20, 20)  /* 192000 / 16;                          49.1 KB */      \
+    X(8000, 256, 3, 25, 16, 20)  /* 192000 / 12;                          65.5 KB */
+#endif
 
 // v[r] *= w^r, r = 1 .. R-1, with four interleaved power chains
 template <int R>
@@ -77,32 +128,97 @@ template <class P>
 AA_HD void fused_clear(int t, float2* data) {
     static_assert(P::M % 2 == 0, "the buffer is cleared in 16-byte words");
     float4* p = reinterpret_cast<float4*>(data);
-    for (int i = t; i < P::M / 2; i += P::kThreads) p[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    constexpr int kWords = P::M / 2, kFull = kWords / P::kThreads;
+#pragma unroll
+    for (int j = 0; j < kFull; ++j) p[t + j * P::kThreads] = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (t + kFull * P::kThreads < kWords) p[t + kFull * P::kThreads] = make_float4(0.f, 0.f, 0.f, 0.f);
 }
 
-// address of input idx = d3 + R3 (d2 + R2 d1) in the layout stage 1 transforms in place: (d3 R2 + d2) R1 + d1
-template <class P>
-AA_HD int fused_input_address(int idx) {
-    constexpr int S = P::R2 * P::R3;
-    const int d1 = idx / S, i = idx - d1 * S;
-    const int d2 = i / P::R3, d3 = i - d2 * P::R3;
-    return (d3 * P::R2 + d2) * P::R1 + d1;
-}
-
-template <class P>
-AA_HD void fused_scatter(int t, const RegSrcBand& s, float2* data) {
-    if (s.b.k_last < s.b.k_first) return;   // empty band: all zero
-    // support in the coordinates of the decimated transform (bin kp <-> row bin z_off +- kp)
-    const int A = s.b.z_neg ? s.b.z_off - s.b.k_last : s.b.k_first - s.b.z_off;
-    const int B = s.b.z_neg ? s.b.z_off - s.b.k_first : s.b.k_last - s.b.z_off;
-    for (int kp = A + t; kp <= B; kp += P::kThreads) {
-        const int mk = P::M - kp;
-        const bool in_m = mk >= A && mk <= B;   // only when the support straddles the middle of the zone
-        const float2 w = twiddle2(s.twN, kp);   // exp(-2 pi i kp / N), N = 2 M
-        data[fused_input_address<P>(kp)] = s.element(kp, true, in_m, w);
-        // the mirrored point; when mk is in the support itself, its own iteration builds it
-        if (!in_m && mk < P::M) data[fused_input_address<P>(mk)] = s.element(mk, false, true, make_float2(-w.x, w.y));
+// address of input n = d_s + R_s (d_{s-1} + R_{s-1} ( ... + R_2 d_1)) in the layout the stages transform in place:
+// sum over j of d_j L_{j-1}
+template <class P, int J = P::kStages>
+AA_HD int fused_input_address(int n) {
+    if constexpr (J == 1) {
+        return n;
+    } else {
+        const int q = n / P::radix(J), d = n - q * P::radix(J);
+        return d * P::len(J - 1) + fused_input_address<P, J - 1>(q);
     }
+}
+
+// the first kFusedPre rounds of a thread's support bins are loaded BEFORE the buffer is cleared (fused_scatter_load), so
+// that the latency of the spectrum / mask / twiddle loads hides behind the clear and its barrier
+constexpr int kFusedPre = 4;
+struct FusedPrefetch {
+    float2 y[kFusedPre];   // masked (and, for odd zones, conjugated) spectrum value Y[kp]
+    float2 w[kFusedPre];   // exp(-2 pi i kp / N)
+};
+
+struct FusedSupport {
+    int A, B;        // support in the coordinates of the decimated transform (bin kp <-> row bin z_off +- kp)
+    bool straddle;   // the support meets its own mirror image [M - B, M - A] (it crosses the middle of the zone)
+};
+
+template <class P>
+AA_HD FusedSupport fused_support(const RegSrcBand& s) {
+    FusedSupport f;
+    f.A = s.b.z_neg ? s.b.z_off - s.b.k_last : s.b.k_first - s.b.z_off;
+    f.B = s.b.z_neg ? s.b.z_off - s.b.k_first : s.b.k_last - s.b.z_off;
+    if (s.b.k_last < s.b.k_first) f.B = f.A - 1;   // empty band
+    f.straddle = (P::M - f.B <= f.B) && (P::M - f.A >= f.A);
+    return f;
+}
+
+template <class P>
+AA_HD float2 fused_band_value(const RegSrcBand& s, int kp) {
+    float2 y = s.masked(s.zone_bin(kp));
+    if (s.b.z_neg) y.y = -y.y;
+    return y;
+}
+
+// Y[M - kp] = 0: with h = Y[kp] / 2 and t = h conj(w), pack_half_spectrum gives
+//   Z[kp] = h + i t  and  Z[M - kp] = conj(h) + i conj(t)   (w(M - kp) = -conj(w)); both are stored conjugated
+template <class P>
+AA_HD void fused_store_pair(float2* data, int kp, float2 y, float2 w) {
+    const float2 h = cscale(y, 0.5f);
+    const float2 tt = cmulc(h, w);
+    const int mk = P::M - kp;
+    data[fused_input_address<P>(kp)] = make_float2(h.x - tt.y, -(h.y + tt.x));
+    if (mk < P::M) data[fused_input_address<P>(mk)] = make_float2(h.x + tt.y, h.y - tt.x);
+}
+
+template <class P>
+AA_HD void fused_scatter_load(int t, const RegSrcBand& s, const FusedSupport& f, FusedPrefetch* pre) {
+    static_for<0, kFusedPre>([&](auto j_) {
+        constexpr int j = decltype(j_)::value;
+        const int kp = f.A + t + j * P::kThreads;
+        if (kp <= f.B) {
+            pre->y[j] = fused_band_value<P>(s, kp);
+            pre->w[j] = twiddle2(s.twN, kp);
+        }
+    });
+}
+
+template <class P>
+AA_HD void fused_scatter(int t, const RegSrcBand& s, const FusedSupport& f, const FusedPrefetch& pre, float2* data) {
+    if (f.straddle) {
+        // both Y[kp] and Y[M - kp] exist for some bins: the general element, one point per iteration (the mirrored
+        // point of a bin whose partner is outside the support is still built here)
+        for (int kp = f.A + t; kp <= f.B; kp += P::kThreads) {
+            const int mk = P::M - kp;
+            const float2 w = twiddle2(s.twN, kp);
+            if (mk >= f.A && mk <= f.B) data[fused_input_address<P>(kp)] = s.element(kp, true, true, w);
+            else fused_store_pair<P>(data, kp, fused_band_value<P>(s, kp), w);
+        }
+        return;
+    }
+    static_for<0, kFusedPre>([&](auto j_) {
+        constexpr int j = decltype(j_)::value;
+        const int kp = f.A + t + j * P::kThreads;
+        if (kp <= f.B) fused_store_pair<P>(data, kp, pre.y[j], pre.w[j]);
+    });
+    for (int kp = f.A + t + kFusedPre * P::kThreads; kp <= f.B; kp += P::kThreads)
+        fused_store_pair<P>(data, kp, fused_band_value<P>(s, kp), twiddle2(s.twN, kp));
 }
 
 // stage 1: butterfly b transforms the R1 consecutive addresses b R1 .. b R1 + R1 - 1 in place (nothing to do where
@@ -127,44 +243,31 @@ AA_HD void fused_stage1(int t, float2* data) {
     }
 }
 
-// stage 2: butterflies i = k1 + R1 d3; tw2[k1] = exp(-2 pi i k1 / L2)
-template <class P>
-AA_HD void fused_stage2(int t, float2* data, const float2* tw2) {
-    for (int i = t; i < P::M / P::R2; i += P::kThreads) {
-        const int d3 = i / P::R1, k1 = i - d3 * P::R1;
-        float2* base = data + d3 * P::L2 + k1;
-        float2 v[P::R2];
-        static_for<0, P::R2>([&](auto r_) {
-            constexpr int r = decltype(r_)::value;
-            v[r] = base[r * P::R1];
-        });
-        if (k1 != 0) mul_powers<P::R2>(v, load_c(tw2 + k1));
-        dft_r<P::R2>(v);
-        static_for<0, P::R2>([&](auto r_) {
-            constexpr int r = decltype(r_)::value;
-            base[r * P::R1] = v[r];
-        });
-    }
-}
-
-// stage 3: butterflies i = k'; tw3[k'] = exp(-2 pi i k' / M).  The outputs are conjugated (conj != 0) and scaled:
+// stage J >= 2: butterfly i = k' + L_{J-1} b works on addresses b L_J + rho L_{J-1} + k', inputs times w_LJ^{rho k'}
+// (powers of tw[tw_offset(J) + k']), outputs in place.  The last stage conjugates (conj != 0) and scales its outputs:
 // with the conjugated source this is the inverse transform (fft_access.cuh: DstDesc::conj1 / scale1).
-template <class P>
-AA_HD void fused_stage3(int t, float2* data, const float2* tw3, int conj, float scale) {
-    for (int i = t; i < P::L2; i += P::kThreads) {
-        float2* base = data + i;
-        float2 v[P::R3];
-        static_for<0, P::R3>([&](auto r_) {
+template <class P, int J>
+AA_HD void fused_stage(int t, float2* data, const float2* tw, int conj, float scale) {
+    constexpr int R = P::radix(J), Lp = P::len(J - 1), Lj = P::len(J);
+    constexpr bool last = (J == P::kStages);
+    for (int i = t; i < P::M / R; i += P::kThreads) {
+        const int b = i / Lp, kq = i - b * Lp;
+        float2* base = data + b * Lj + kq;
+        float2 v[R];
+        static_for<0, R>([&](auto r_) {
             constexpr int r = decltype(r_)::value;
-            v[r] = base[r * P::L2];
+            v[r] = base[r * Lp];
         });
-        if (i != 0) mul_powers<P::R3>(v, load_c(tw3 + i));
-        dft_r<P::R3>(v);
-        static_for<0, P::R3>([&](auto r_) {
+        if (kq != 0) mul_powers<R>(v, load_c(tw + P::tw_offset(J) + kq));
+        dft_r<R>(v);
+        static_for<0, R>([&](auto r_) {
             constexpr int r = decltype(r_)::value;
             float2 o = v[r];
-            if (conj) o.y = -o.y;
-            base[r * P::L2] = cscale(o, scale);
+            if (last) {
+                if (conj) o.y = -o.y;
+                o = cscale(o, scale);
+            }
+            base[r * Lp] = o;
         });
     }
 }

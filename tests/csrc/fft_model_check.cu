@@ -654,21 +654,28 @@ static void check_real_band(int N, double lo0 = 890.9, double hi0 = 1122.5) {
 // serial emulation of band_fused_kernel's transform (bandfused.cu, fft_fused.cuh): every thread of the CTA, stage by stage
 template <class P>
 static void emu_fused_unit(const RegSrcBand& src, int conj, float scale, float2* data) {
-    std::vector<float2> tw2((size_t)P::kTw2), tw3((size_t)P::kTw3);
-    for (int k = 0; k < P::kTw2; ++k) tw2[(size_t)k] = make_float2((float)cos(2.0 * M_PI * k / P::L2), (float)-sin(2.0 * M_PI * k / P::L2));
-    for (int k = 0; k < P::kTw3; ++k) tw3[(size_t)k] = make_float2((float)cos(2.0 * M_PI * k / P::M), (float)-sin(2.0 * M_PI * k / P::M));
+    std::vector<float2> tw((size_t)P::kTwTotal);
+    for (int j = 2; j <= P::kStages; ++j)
+        for (int k = 0; k < P::len(j - 1); ++k)
+            tw[(size_t)(P::tw_offset(j) + k)] = make_float2((float)cos(2.0 * M_PI * k / P::len(j)), (float)-sin(2.0 * M_PI * k / P::len(j)));
+    const FusedSupport sup = fused_support<P>(src);
+    std::vector<FusedPrefetch> pre((size_t)P::kThreads);
+    for (int t = 0; t < P::kThreads; ++t) fused_scatter_load<P>(t, src, sup, &pre[(size_t)t]);
     for (int t = 0; t < P::kThreads; ++t) fused_clear<P>(t, data);
-    for (int t = 0; t < P::kThreads; ++t) fused_scatter<P>(t, src, data);
+    for (int t = 0; t < P::kThreads; ++t) fused_scatter<P>(t, src, sup, pre[(size_t)t], data);
     for (int t = 0; t < P::kThreads; ++t) fused_stage1<P>(t, data);
-    for (int t = 0; t < P::kThreads; ++t) fused_stage2<P>(t, data, tw2.data());
-    for (int t = 0; t < P::kThreads; ++t) fused_stage3<P>(t, data, tw3.data(), conj, scale);
+    for (int t = 0; t < P::kThreads; ++t) fused_stage<P, 2>(t, data, tw.data(), conj, scale);
+    if constexpr (P::kStages >= 3)
+        for (int t = 0; t < P::kThreads; ++t) fused_stage<P, 3>(t, data, tw.data(), conj, scale);
+    if constexpr (P::kStages >= 4)
+        for (int t = 0; t < P::kThreads; ++t) fused_stage<P, 4>(t, data, tw.data(), conj, scale);
 }
 
 static bool emu_fused(int M, const RegSrcBand& src, int conj, float scale, float2* data) {
-#define X(r1, r2, r3, th, mb)                                              \
-    if (M == (r1) * (r2) * (r3)) {                                         \
-        emu_fused_unit<FusedPlan<r1, r2, r3, th>>(src, conj, scale, data); \
-        return true;                                                       \
+#define X(m, th, mb, ...)                                                   \
+    if (M == (m)) {                                                         \
+        emu_fused_unit<FusedPlan<th, __VA_ARGS__>>(src, conj, scale, data); \
+        return true;                                                        \
     }
     AA_FUSED_LIST(X)
 #undef X
