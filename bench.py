@@ -319,7 +319,8 @@ def run_ours(args):
         # one CTA per unit: masked spectrum -> in-shared-memory inverse -> Schroeder sum -> fits; HBM sees at most the
         # band's zone of the row spectrum (8 B per complex bin = 4 B per synthesised sample) and three results
         "band_fused": (4.0 * rows_n * fused_samples, "fp32 issue / shared memory (the band signal never leaves the SM)",
-                       "band_fused_kernel: deep-decimation classes, synthesis + EDC + fits in one CTA"),
+                       "band_fused_kernel: deep-decimation classes, synthesis + EDC + fits in one CTA (algorithmic bytes by the "
+                       "4 B per synthesised sample convention of the two-pass kernels; see traffic for what it moves)"),
         "band_edc": (4.0 * units * n, "hbm", "edc_kernel<false> on band signals (generic lengths)"),
         "csd": (rows_n * (18 * 4096 * 4.0 + 18 * n_bins * 4.0), "hbm",
                 "csd_tma_kernel: TMA-staged frames, FFT, dB, on-chip normalisation"),

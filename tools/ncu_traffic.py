@@ -24,6 +24,8 @@ def stage_of(name: str):
         return "untangle"
     if "band_fit_kernel" in name:
         return "band_fit"
+    if "band_fused_kernel" in name:
+        return "band_fused"
     if "csd_tma_kernel" in name:
         return "csd"
     m = re.search(r"fft_cols_reg<.*>, (\d+), \d+>", name)
