@@ -71,6 +71,7 @@ int fill_band_fit_args(bandfit::BandFitArgs* out, int n, const aa_decay_params* 
     AA_REQUIRE(!a.cert.on || (a.cert.counts && a.cert.lists), AA_ERR_INVALID_ARGUMENT, "certification without unit lists");
     a.e.min_samples = min_samples;
     a.decim = decim > 1 ? decim : 1;
+    a.inv_decim = 1.0 / (double)a.decim;
     a.full_n = full_n;
     a.aligned = (aligned || decim > 1) ? 1 : 0;
     a.kappa = decim > 1 ? (float)(decim - 1) / (float)(2 * decim) : 0.0f;

@@ -44,6 +44,7 @@ struct BandFitArgs {
     // corrected by the end-point term of the trapezoid rule: E_j = decim * (S_j - kappa y_j^2), kappa = (decim-1)/(2 decim)
     int decim, full_n, aligned;
     float kappa;
+    double inv_decim;         // 1 / decim
     int min_fit_points;
     // addressing: dense (unit = row * nbc + j) or through a unit list (unit_map[unit] = row * nbc + j); the result of
     // class band j of a row goes to rt60_out[(row * out_nb + out_band[j]) * AA_MAX_FITS + f]
@@ -76,7 +77,6 @@ struct FitShared {
     double fit_slope_u[AA_MAX_FITS], fit_b0[AA_MAX_FITS];
     int fit_n_full[AA_MAX_FITS];
     double warp_tot[kW];
-    double e0, inv_e0;
     int cross_ok[kMaxTargets], cross_idx[kMaxTargets];
     double cross_t[kMaxTargets];
     int fit_valid[AA_MAX_FITS], fit_first[AA_MAX_FITS], fit_last[AA_MAX_FITS];
@@ -221,7 +221,7 @@ __device__ __forceinline__ void band_fit_unit(const BandFitArgs& a, int row, int
         if (a.decim > 1 && n > 0) {
             const float yl = fit_ld1<kSmem>(y + (n - 1));
             const double r = (double)(full_len - a.decim * (n - 1));
-            s_end = (r - 0.5 * (double)(a.decim + 1)) / (double)a.decim * (double)__fmul_rn(yl, yl);
+            s_end = (r - 0.5 * (double)(a.decim + 1)) * a.inv_decim * (double)__fmul_rn(yl, yl);
         }
         double running = higher + after + s_end;
         for (int q = per - 1; q >= 0; --q) {
@@ -234,22 +234,22 @@ __device__ __forceinline__ void band_fit_unit(const BandFitArgs& a, int row, int
     }
     __syncthreads();
 
-    // ---- E0 = E[start]
+    // ---- E0 = E[start]: every warp works it out for itself (one tile at sample resolution, identical arithmetic and
+    // therefore identical values), which saves the hand-over through shared memory and its barrier
     const int ks = min(start / TL, NT - 1);
-    if (warp == 0) {
+    double e0 = 0.0;
+    {
         const int pofs = start - ks * TL;
         const int pj = pofs / kSub, pl = (pofs % kSub) >> 2, pc = pofs & 3;
         visit_tile_reverse<NS, kSmem>(y, ks, TL, n, carry[ks], lane, masks, [&](int j, const TileScan& sc, double after) {
             if (j == pj && lane == pl) {
                 const float sj = (pc == 0) ? sc.s[0] : (pc == 1) ? sc.s[1] : (pc == 2) ? sc.s[2] : sc.s[3];
-                const double e = after + (double)__fadd_rn(sc.excl, sj) - kappa * (double)lane_sample_energy(sc, pc);
-                sh.e0 = e;
-                sh.inv_e0 = 1.0 / fmax(e, p.eps);
+                e0 = after + (double)__fadd_rn(sc.excl, sj) - kappa * (double)lane_sample_energy(sc, pc);
             }
         });
+        e0 = __shfl_sync(kFullMask, e0, pl);
     }
-    __syncthreads();
-    const double inv_e0 = sh.inv_e0;
+    const double inv_e0 = 1.0 / fmax(e0, p.eps);
     const int n_targets = 2 + 2 * p.n_fits;
 
     // ---- crossings (decay.py:173-199): first sample <= target, by one warp (all lanes return the same values)
@@ -399,7 +399,8 @@ __device__ __forceinline__ void band_fit_unit(const BandFitArgs& a, int row, int
             const int span = sh.cross_idx[te_i] - sh.cross_idx[ts_i];
             if (sh.cross_ok[ts_i] && sh.cross_ok[te_i] && span > 0) {   // (an invalid fit is flagged whatever these find)
                 const double tau0 = p.target[e ? te_i : ts_i];
-                const double delta = (double)m_b * (p.target[ts_i] - p.target[te_i]) / (double)span +
+                // (a modelled bound: the quotient in float)
+                const double delta = (double)(m_b * (float)(p.target[ts_i] - p.target[te_i]) / (float)span) +
                                      4.342944819 * end_cell * a.gain10[e ? te_i : ts_i];   // 10^(-tau0 / 10), from the host
                 const double tau = tau0 + (minus ? -delta : delta);
                 int found, idx;
@@ -479,8 +480,10 @@ __device__ __forceinline__ void band_fit_unit(const BandFitArgs& a, int row, int
     }
 #pragma unroll
     for (int q = 0; q < AA_MAX_FITS * 3; ++q) {
-        const double s = warp_sum(acc[q]);
-        if (lane == 0) sh.warp_acc[warp][q] = s;
+        if (q < 3 * p.n_fits) {   // (uniform) only the fits the call asked for: each sum is a chain of ten shuffles
+            const double s = warp_sum(acc[q]);
+            if (lane == 0) sh.warp_acc[warp][q] = s;
+        }
     }
     __syncthreads();
     if (threadIdx.x < AA_MAX_FITS) {
@@ -522,29 +525,33 @@ __device__ __forceinline__ void band_fit_unit(const BandFitArgs& a, int row, int
     // end point of the fit by `win` full-rate samples changes the slope by about 6 (win / n) (r / range), r = distance
     // of the curve from the line at that end.  The unit is certified when both ends together stay under cert.tol;
     // otherwise it goes on the list of the next, finer level (bands.cu), whose last level is the full-rate path.
-    if (a.cert.on) {
-        __syncthreads();
-        if (threadIdx.x == 0) {
+    // (The finalising threads sit in warp 0: a warp-level barrier orders their shared-memory writes before the decision,
+    // and the other warps are done.  The decision is a threshold on a modelled bound: float arithmetic.)
+    if (a.cert.on && warp == 0) {
+        __syncwarp();
+        if (lane == 0) {
             bool ok = true;
             for (int f = 0; f < p.n_fits && ok; ++f) {
                 const int ts_i = 2 + 2 * f, te_i = 3 + 2 * f;
                 const int span = sh.cross_idx[te_i] - sh.cross_idx[ts_i];
                 ok = sh.fit_valid[f] && (float)span >= (float)a.cert.min_span[cj] * a.cert.fit_scale[f];
                 if (!ok) break;
-                const double range = p.target[ts_i] - p.target[te_i];
-                const double n_full = (double)sh.fit_n_full[f];
-                double moved = 0.0;
+                const float inv_range = 1.0f / (float)(p.target[ts_i] - p.target[te_i]);
+                const float inv_n_full = 1.0f / (float)sh.fit_n_full[f];
+                const float slope_u = (float)sh.fit_slope_u[f], b0 = (float)sh.fit_b0[f];
+                float moved = 0.0f;
                 for (int e = 0; e < 2 && ok; ++e) {
                     const int lo = sh.cert_idx[4 * f + 2 * e], hi = sh.cert_idx[4 * f + 2 * e + 1];
                     ok = lo >= 0 && hi >= 0 && hi - lo <= max(1, (int)(a.cert.w * (float)span));
-                    const double tc = (e ? sh.fit_te[f] : sh.fit_ts[f]) * (double)p.sr - (double)(sh.fit_first[f] - start);
-                    const double line = sh.fit_b0[f] + sh.fit_slope_u[f] * tc;
-                    const double r = fmax(fabs(p.target[e ? te_i : ts_i] - line), 0.5) + fabs(sh.fit_slope_u[f]) * (double)(hi - lo + 1);
+                    const float tc = (float)((e ? sh.fit_te[f] : sh.fit_ts[f]) * (double)p.sr - (double)(sh.fit_first[f] - start));
+                    const float line = fmaf(slope_u, tc, b0);
+                    const float tgt = (float)p.target[e ? te_i : ts_i];
+                    const float r = fmaxf(fabsf(tgt - line), 0.5f) + fabsf(slope_u) * (float)(hi - lo + 1);
                     // a start target at 0 dB is the first sample whatever the curve (decay.py:186-187)
-                    const double win = (p.target[e ? te_i : ts_i] >= 0.0) ? 0.0 : ((double)(hi - lo) + 0.25) * (double)a.decim;
-                    moved += 6.0 * (win / n_full) * (r / range);
+                    const float win = (tgt >= 0.0f) ? 0.0f : ((float)(hi - lo) + 0.25f) * (float)a.decim;
+                    moved += 6.0f * (win * inv_n_full) * (r * inv_range);
                 }
-                ok = ok && moved <= (double)a.cert.tol;
+                ok = ok && moved <= a.cert.tol;
             }
             if (!ok) flag_unit(a.cert, row, cj);
         }

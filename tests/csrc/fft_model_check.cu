@@ -869,6 +869,7 @@ int main() {
     check_decimated_band(192000, 24, 111.4, 140.3, 3);
     check_decimated_band(288000, 8, 111.4, 140.3, 20011);
     check_decimated_band(288000, 16, 157.5, 198.4, 13);
+    check_decimated_band(288000, 16, 707.0, 891.0, 4321);      // support across the middle of the zone: the fused kernel's paired path
     check_decimated_band(192000, 8, 2227.0, 2300.0, 4321);
     check_decimated_band(192000, 16, 55.7, 70.2, 16001);
     printf("%s (%d failures)\n", failures ? "FAILED" : "ALL OK", failures);
