@@ -66,31 +66,13 @@ struct FusedPlan {
 
 // (M, threads, resident CTAs per SM, R1, R2, ...) per supported length.  R1 is odd so that stage 1's accesses (R1
 // consecutive values per thread) do not collide on banks.
-#ifndef AA_FUSED_VARIANT
-#define AA_FUSED_VARIANT 0
-#endif
-#if AA_FUSED_VARIANT == 1
-#define AA_FUSED_LIST(X)                       \
-    X(9000, 384, 3, 9, 10, 10, 10)             \
-    X(12000, 384, 2, 25, 24, 20)               \
-    X(6000, 256, 4, 15, 20, 20)                \
-    X(8000, 256, 3, 25, 16, 20)
-#elif AA_FUSED_VARIANT == 2
-#define AA_FUSED_LIST(X)                       \
-    X(9000, 512, 3, 9, 10, 10, 10)             \
-    X(12000, 512, 2, 15, 10, 8, 10)            \
-    X(6000, 256, 4, 15, 20, 20)                \
-    X(8000, 256, 3, 25, 16, 20)
-#elif AA_FUSED_VARIANT == 3
-#define AA_FUSED_LIST(X)                       \
-    X(9000, 384, 3, 15, 15, 8, 5)              \
-    X(12000, 384, 2, 15, 10, 8, 10)            \
-    X(6000, 256, 4, 15, 20, 20)                \
-    X(8000, 256, 3, 25, 16, 20)
-#else
+// Tuning of the round (bench classes D = 16 / 12, ms per 8192 rows): 9000 with 192 / 224 / 256 / 320 threads 8.19 / 8.30 /
+// 7.89 / 8.31; four-stage plans 9 x 10 x 10 x 10 and 15 x 15 x 8 x 5 with 384 / 512 threads 8.6-9.4; 12000 with
+// 256 / 320 / 384 / 448 / 512 threads 3.85 / 3.73 / 3.58 / 3.55 / 3.50.
+#ifndef AA_FUSED_LIST
 #define AA_FUSED_LIST(X)                                                                  \
     X(9000, 256, 3, 25, 18, 20)  /* N = 288000 decimated by 16;           73.7 KB */      \
-    X(12000, 384, 2, 25, 24, 20) /* 288000 / 12, 192000 / 8;              97.7 KB */      \
+    X(12000, 512, 2, 25, 24, 20) /* 288000 / 12, 192000 / 8;              97.7 KB */      \
     X(6000, 256, 4, 15, 20, 20)  /* 192000 / 16;                          49.1 KB */      \
     X(8000, 256, 3, 25, 16, 20)  /* 192000 / 12;                          65.5 KB */
 #endif
