@@ -84,6 +84,16 @@ struct FitShared {
     double warp_acc[kW][AA_MAX_FITS * 3];
 };
 
+}  // namespace bandfit
+
+// bandfit.cu: fills the argument block shared by band_fit_kernel and band_fused_kernel (everything but the signal /
+// partial pointers and the tile layout)
+int fill_band_fit_args(bandfit::BandFitArgs* out, int n, const aa_decay_params* p, const int* d_start_idx, int nbc, int out_nb,
+                       const int* d_unit_map, const BandFitCert* cert, int min_samples, double* d_rt60_out, int decim,
+                       int full_n, int aligned);
+
+namespace bandfit {
+
 // One tile at sample resolution, visited by a warp from its last 128-sample step to its first:
 // f(j, scan, after) gets the step's suffix scan and the float64 energy that follows the step
 // (later steps of the tile + later tiles).

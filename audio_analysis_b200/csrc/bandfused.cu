@@ -144,10 +144,6 @@ bool band_fused_supported(int M) {
     return false;
 }
 
-int fill_band_fit_args(bandfit::BandFitArgs* out, int n, const aa_decay_params* p, const int* d_start_idx, int nbc, int out_nb,
-                       const int* d_unit_map, const BandFitCert* cert, int min_samples, double* d_rt60_out, int decim,
-                       int full_n, int aligned);
-
 int launch_band_fused(int M, const float2* d_X, long long x_stride, const BandDev* d_bands, double freq_scale,
                       TwoLevelTwiddle twN, float scale, long long n_units, const aa_decay_params* p,
                       const int* d_start_idx, int nbc, int out_nb, const int* d_unit_map, const BandFitCert* cert,

@@ -690,7 +690,7 @@ static void check_decimated_band(int N, int D, double lo0, double hi0, int shift
     const int half = N / 2, Nd = N / D, Md = Nd / 2;
     BandDev band = make_bandpass(lo0, hi0, 1.0 / 6.0, 24000.0, freq_scale, half + 1);
     // wide bands get a sparse input (a few dozen impulses) so that the direct sums below stay cheap
-    const bool sparse = band.k_last - band.k_first > 3000;
+    const bool sparse = band.k_last - band.k_first > 2000;
     std::vector<float> x((size_t)N, 0.f);
     std::vector<int> nz;
     for (int n = 0; n < N; ++n) {

@@ -63,7 +63,7 @@ def test_fft_index_model_on_cpu(built):
     """The FFT passes' planner, butterflies and accessors, emulated serially against direct DFT sums."""
     exe = ROOT / "build" / "fft_model_check"
     assert exe.exists()
-    out = subprocess.run([str(exe)], capture_output=True, text=True, timeout=300)
+    out = subprocess.run([str(exe)], capture_output=True, text=True, timeout=600)
     assert out.returncode == 0, out.stdout[-2000:]
     assert "ALL OK" in out.stdout
 
