@@ -298,6 +298,17 @@ def run_ours(args):
     if os.environ.get("AA_NO_FUSED_BANDS"):
         fused_samples = 0.0
     band_units_total -= rows_n * fused_samples              # the three-kernel path handles the rest
+    # what the fused kernel must read per row: the bins of the row spectrum inside each of its bands' supports
+    # (pass band + raised-cosine skirts, rt60bands.py:127-167; 8 B per bin) and three float64 results per unit
+    fused_bytes_row = 0.0
+    if fused_samples > 0.0:
+        fac = 2.0 ** float(bs.transition_width_octaves)
+        for b_def, d in zip(out.bands, dec):
+            if not (d > 1 and n % (2 * d) == 0 and n // (2 * d) in fused_lengths):
+                continue
+            lo = 0.0 if b_def.low_edge_hz is None else float(b_def.low_edge_hz) / fac
+            hi = 0.5 * SR if b_def.high_edge_hz is None else min(0.5 * SR, float(b_def.high_edge_hz) * fac)
+            fused_bytes_row += max(0.0, hi - lo) * n / SR * 8.0 + 24.0
     stage_bytes = {
         # read x + write edc_db (8 B/sample)
         "edc": (8.0 * rows_n * n, "hbm", "edc_kernel<true>: fused EDC + crossings + fits (aa_decay_batch)"),
@@ -316,11 +327,10 @@ def run_ours(args):
                           "fft_rows_reg<energy>: second pass of the masked inverse FFT + tile energies"),
         "band_fit": (4.0 * band_units_total / 16.0, "latency (reads the partials and ~10% of the band signal)",
                      "band_fit_kernel: band EDC suffix scan + crossings + fits"),
-        # one CTA per unit: masked spectrum -> in-shared-memory inverse -> Schroeder sum -> fits; HBM sees at most the
-        # band's zone of the row spectrum (8 B per complex bin = 4 B per synthesised sample) and three results
-        "band_fused": (4.0 * rows_n * fused_samples, "fp32 issue / shared memory (the band signal never leaves the SM)",
-                       "band_fused_kernel: deep-decimation classes, synthesis + EDC + fits in one CTA (algorithmic bytes by the "
-                       "4 B per synthesised sample convention of the two-pass kernels; see traffic for what it moves)"),
+        # one CTA per unit: masked spectrum -> in-shared-memory inverse -> Schroeder sum -> fits
+        "band_fused": (rows_n * fused_bytes_row, "latency of its phase chain / fp32 issue (the band signal never leaves the SM; "
+                       "algorithmic bytes = the support bins of the row spectrum it reads + its results)",
+                       "band_fused_kernel: deep-decimation classes, synthesis + EDC + fits in one CTA"),
         "band_edc": (4.0 * units * n, "hbm", "edc_kernel<false> on band signals (generic lengths)"),
         "csd": (rows_n * (18 * 4096 * 4.0 + 18 * n_bins * 4.0), "hbm",
                 "csd_tma_kernel: TMA-staged frames, FFT, dB, on-chip normalisation"),
